@@ -1,0 +1,252 @@
+"""Device-side driver of the assignment hot path: cost build -> LAP -> spot per cell.
+
+PyTorch is used only for device memory (tensors as handles), streams and the
+optional ``torch.distributed`` plumbing; every computation is a call through the
+C ABI of ``libcytospace_b200.so`` (``include/cytospace_b200.h``).  There is no CPU
+fallback: without a CUDA device / the built library every entry raises.
+
+Reference path replaced (paths relative to the CytoSPACE repo):
+``solve_linear_assignment_problem`` cytospace/cytospace.py:304-351 ->
+``calculate_cost`` linear_assignment_solvers.py:42-69 ->
+``matrix_correlation_pearson`` common/common.py:190-199 ->
+``call_solver`` linear_assignment_solvers.py:34-40 (third-party ``lapjv``).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _native
+
+COST_SCALE = 10 ** 6           # integer scale of the correlation distance; precedent cytospace.py:337
+PRECISIONS = {"f16": 0, "f16x3": 1}
+STAT_NAMES = ("status", "phases", "rounds", "bids", "passes", "cost_min", "cost_max", "scale",
+              "grid", "smem_prices", "rounds_le1", "max_bidders", "phase_scans")
+
+
+def _round_up(x: int, a: int) -> int:
+    return (x + a - 1) // a * a
+
+
+@dataclass
+class LapResult:
+    """Device-resident LAP output; ``colsol`` is what CytoSPACE consumes
+    (linear_assignment_solvers.py:38: the row assigned to each column)."""
+    rowsol: torch.Tensor      # int32[n]  column (cell) of LAP row i
+    colsol: torch.Tensor      # int32[n]  LAP row (spot slot) of column j
+    price: torch.Tensor       # int64[n]  column prices, units of 1/(n+1) cost
+    total: int                # sum_i cost[row_map[i], rowsol[i]]
+    stats: dict
+
+    @property
+    def row_scans(self) -> int:
+        """Row scans the solve performed (bids + phase-start re-checks)."""
+        return int(self.stats["bids"]) + int(self.stats["phase_scans"])
+
+
+class AssignmentEngine:
+    """One engine per (process, device).  Buffers are cached and re-used between calls."""
+
+    def __init__(self, device=None, precision: str = "f16x3", cost_scale: float = COST_SCALE):
+        if not torch.cuda.is_available():
+            raise RuntimeError("cytospace_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = _native.load()
+        self.ffi = _native.ffi()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if precision not in PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(PRECISIONS)}")
+        self.precision = precision
+        self.cost_scale = float(cost_scale)
+        self._ws = {}
+        self.profile = False          # True: bracket the cost-build and LAP launches with CUDA events
+        self._events = {}
+        sm, maj, mnr, mem = (self.ffi.new("int *"), self.ffi.new("int *"), self.ffi.new("int *"),
+                             self.ffi.new("size_t *"))
+        _native.check(self.lib.cyb_device_info(self.device.index or 0, sm, maj, mnr, mem))
+        self.sm_count, self.cc, self.total_mem = sm[0], (maj[0], mnr[0]), mem[0]
+        if self.cc[0] != 10:
+            raise RuntimeError(f"cytospace_b200 is built for sm_100a; device is cc {self.cc[0]}.{self.cc[1]}")
+
+    # ------------------------------------------------------------------ helpers
+    def _workspace(self, key: str, nbytes: int) -> torch.Tensor:
+        buf = self._ws.get(key)
+        if buf is None or buf.numel() < nbytes:
+            self._ws[key] = None
+            buf = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+            self._ws[key] = buf
+        return buf
+
+    def _stream(self):
+        return _native.stream_ptr(torch.cuda.current_stream(self.device))
+
+    def _mark(self, name: str, which: int):
+        if self.profile:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(torch.cuda.current_stream(self.device))
+            self._events.setdefault(name, [None, None])[which] = ev
+
+    def last_ms(self, name: str) -> float:
+        """Device time of the last ``cost`` / ``lap`` launch group (needs ``profile = True``)."""
+        a, b = self._events[name]
+        b.synchronize()
+        return a.elapsed_time(b)
+
+    def to_device(self, x, dtype=None) -> torch.Tensor:
+        """numpy / CPU tensor -> device tensor (pinned staging is the caller's choice)."""
+        if isinstance(x, np.ndarray):
+            x = torch.from_numpy(np.ascontiguousarray(x))
+        if dtype is not None and x.dtype != dtype:
+            x = x.to(dtype)
+        return x.to(self.device, non_blocking=True)
+
+    # --------------------------------------------------------------- cost build
+    def cost_build(self, sc: torch.Tensor, st: torch.Tensor, log_tpm: bool = False, out: torch.Tensor | None = None,
+                   return_colstats: bool = False, check_variance: bool = True):
+        """Integer cost ``rint(-cost_scale * pearson)`` as int32 ``[S, ld]`` (ld = N rounded up to 32).
+
+        sc [G x N], st [G x S]: float64 / float32 device tensors, genes x cells row-major -- the
+        arrays ``calculate_cost`` receives (linear_assignment_solvers.py:42).  Raises ``ValueError``
+        when the gene counts differ (common.py:191-192) or (documented deviation; the reference
+        yields NaN, common.py:196-197) when a column has zero variance."""
+        if sc.dim() != 2 or st.dim() != 2:
+            raise ValueError("expression matrices must be 2-D (genes x cells)")
+        if sc.shape[0] != st.shape[0]:
+            raise ValueError("The two matrices v1 and v2 must have equal dimensions; "
+                             "ST and scRNA data must have the same genes")
+        if sc.dtype != st.dtype or sc.dtype not in (torch.float64, torch.float32):
+            raise ValueError("expression matrices must both be float64 or both float32")
+        if not (sc.is_cuda and st.is_cuda):
+            raise ValueError("cost_build takes device tensors (use to_device())")
+        if sc.stride(1) != 1:
+            sc = sc.contiguous()
+        if st.stride(1) != 1:
+            st = st.contiguous()
+        G, N = sc.shape
+        S = st.shape[1]
+        if G == 0 or N == 0 or S == 0:
+            raise ValueError("empty expression matrix")
+        prec = PRECISIONS[self.precision]
+        ld = _round_up(N, 32)
+        if out is None:
+            out = torch.empty((S, ld), dtype=torch.int32, device=self.device)
+        elif out.shape[0] < S or out.stride(0) < N or out.dtype != torch.int32:
+            raise ValueError("bad `out` buffer")
+        ws_bytes = self.lib.cyb_cost_build_workspace_bytes(G, N, S, prec)
+        ws = self._workspace("cost", ws_bytes + 1024)
+        off = (-ws.data_ptr()) % 1024
+        colstat_sc = torch.empty((2, N), dtype=torch.float64, device=self.device) if return_colstats else None
+        colstat_st = torch.empty((2, S), dtype=torch.float64, device=self.device) if return_colstats else None
+        zero_var = torch.zeros(1, dtype=torch.int32, device=self.device)
+        dt = self.lib.CYB_F64 if sc.dtype == torch.float64 else self.lib.CYB_F32
+        self._mark("cost", 0)
+        _native.check(self.lib.cyb_cost_build_pearson(
+            _native.ptr("void *", sc), _native.ptr("void *", st), dt, G, N, S, sc.stride(0), st.stride(0),
+            int(bool(log_tpm)), prec, self.cost_scale, _native.ptr("int32_t *", out), out.stride(0),
+            _native.ptr("double *", colstat_sc), _native.ptr("double *", colstat_st),
+            _native.ptr("int32_t *", zero_var), self.ffi.cast("void *", ws.data_ptr() + off), ws_bytes,
+            self._stream()))
+        self._mark("cost", 1)
+        if check_variance:
+            nz = int(zero_var.item())
+            if nz:
+                raise ValueError(f"{nz} cell/spot column(s) have zero variance: Pearson correlation undefined "
+                                 "(the reference would hand NaN costs to the solver)")
+        if return_colstats:
+            return out, colstat_sc, colstat_st
+        return out
+
+    def quantise(self, cost_f64: torch.Tensor, scale: float) -> torch.Tensor:
+        """int32 ``rint(scale * cost)`` of a float64 device matrix (entry P2)."""
+        n_rows, n_cols = cost_f64.shape
+        ld = _round_up(n_cols, 32)
+        out = torch.empty((n_rows, ld), dtype=torch.int32, device=self.device)
+        bad = torch.zeros(1, dtype=torch.int32, device=self.device)
+        _native.check(self.lib.cyb_quantise_f64(_native.ptr("double *", cost_f64), n_rows, n_cols, cost_f64.stride(0),
+                                                float(scale), _native.ptr("int32_t *", out), ld,
+                                                _native.ptr("int32_t *", bad), self._stream()))
+        if int(bad.item()):
+            raise ValueError("cost matrix contains NaN/inf or values too large to integerise")
+        return out
+
+    # ---------------------------------------------------------------------- LAP
+    def lap_solve(self, cost: torch.Tensor, row_map: torch.Tensor | None = None, n: int | None = None,
+                  grid: int = 0) -> LapResult:
+        """Exact LAP on the int32 device matrix ``cost[row_map[i], j]`` (i, j < n)."""
+        if cost.dtype != torch.int32 or not cost.is_cuda or cost.dim() != 2 or cost.stride(1) != 1:
+            raise ValueError("cost must be a row-major int32 device matrix")
+        if n is None:
+            n = int(row_map.numel()) if row_map is not None else int(cost.shape[0])
+        if row_map is not None:
+            if row_map.dtype != torch.int32 or not row_map.is_cuda or row_map.numel() != n:
+                raise ValueError("row_map must be an int32 device vector of length n")
+        elif cost.shape[0] < n:
+            raise ValueError("cost has fewer rows than n")
+        if cost.shape[1] < n:
+            raise ValueError("LAP must be square: cost has fewer columns than n")
+        if n <= 0:
+            raise ValueError("empty LAP")
+        dev = self.device
+        rowsol = torch.empty(n, dtype=torch.int32, device=dev)
+        colsol = torch.empty(n, dtype=torch.int32, device=dev)
+        price = torch.empty(n, dtype=torch.int64, device=dev)
+        small = torch.zeros(1 + self.lib.CYB_LAP_NSTATS, dtype=torch.int64, device=dev)
+        ws_bytes = self.lib.cyb_lap_workspace_bytes(n)
+        ws = self._workspace("lap", ws_bytes + 256)
+        off = (-ws.data_ptr()) % 256
+        self._mark("lap", 0)
+        _native.check(self.lib.cyb_lap_solve_i32(
+            _native.ptr("int32_t *", cost), cost.stride(0), n, _native.ptr("int32_t *", row_map),
+            _native.ptr("int32_t *", rowsol), _native.ptr("int32_t *", colsol), _native.ptr("int64_t *", price),
+            self.ffi.cast("int64_t *", small.data_ptr()), self.ffi.cast("int64_t *", small.data_ptr() + 8),
+            self.ffi.cast("void *", ws.data_ptr() + off), ws_bytes, int(grid), self._stream()))
+        self._mark("lap", 1)
+        host = small.cpu().tolist()            # one D2H: total + stats (synchronises the stream)
+        stats = dict(zip(STAT_NAMES, host[1:1 + len(STAT_NAMES)]))
+        if stats["status"] != 0:
+            names = {self.lib.CYB_ERR_OVERFLOW: "price overflow", self.lib.CYB_ERR_NOT_CONVERGED: "round cap hit"}
+            raise RuntimeError(f"LAP solve failed on device: {names.get(stats['status'], stats['status'])}")
+        return LapResult(rowsol, colsol, price, int(host[0]), stats)
+
+    def lap_check(self, cost: torch.Tensor, res: LapResult, row_map: torch.Tensor | None = None) -> dict:
+        """On-device optimality certificate; ``max_violation <= 1`` (scaled units) proves the
+        assignment optimal for the integer matrix.  One coalesced pass over the matrix."""
+        n = int(res.rowsol.numel())
+        out = torch.zeros(3, dtype=torch.int64, device=self.device)
+        ws_bytes = self.lib.cyb_lap_workspace_bytes(n)
+        ws = self._workspace("lap", ws_bytes + 256)
+        off = (-ws.data_ptr()) % 256
+        _native.check(self.lib.cyb_lap_check_i32(
+            _native.ptr("int32_t *", cost), cost.stride(0), n, _native.ptr("int32_t *", row_map),
+            _native.ptr("int32_t *", res.rowsol), _native.ptr("int64_t *", res.price),
+            _native.ptr("int64_t *", out), self.ffi.cast("void *", ws.data_ptr() + off), ws_bytes, self._stream()))
+        v, t, bad = out.cpu().tolist()
+        return {"max_violation": v, "total": t, "invalid_rows": bad}
+
+    # --------------------------------------------------------------- whole path
+    def assign(self, sc, st, cell_number_to_node_assignment, log_tpm: bool = False):
+        """cost build + LAP + ``location_repeat[assignment]`` (cytospace.py:319-331).
+
+        Returns ``(spot_of_cell int64 device tensor [N], LapResult, cost int32 [S, ld])``."""
+        cn = np.asarray(cell_number_to_node_assignment).astype(np.int64).ravel()
+        sc = self.to_device(sc) if not (torch.is_tensor(sc) and sc.is_cuda) else sc
+        st = self.to_device(st) if not (torch.is_tensor(st) and st.is_cuda) else st
+        N, S = int(sc.shape[1]), int(st.shape[1])
+        if cn.shape[0] != S:
+            raise ValueError(f"cell_number_to_node_assignment has {cn.shape[0]} entries for {S} spots")
+        if (cn < 0).any():
+            raise ValueError("negative cell count")
+        n = int(cn.sum())
+        if n != N:
+            raise ValueError(f"the assignment must be square: sum(cell_number_to_node_assignment)={n} "
+                             f"but {N} cells were given")
+        cost = self.cost_build(sc, st, log_tpm=log_tpm)
+        if (cn == 1).all():
+            row_map = None
+        else:
+            # location_repeat of linear_assignment_solvers.py:63-65, kept as an index instead of a row copy
+            row_map = torch.from_numpy(np.repeat(np.arange(S, dtype=np.int32), cn)).to(self.device)
+        res = self.lap_solve(cost, row_map, n=N)
+        spot_of_cell = res.colsol.long() if row_map is None else row_map[res.colsol.long()].long()
+        return spot_of_cell, res, cost

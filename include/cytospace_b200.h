@@ -1,0 +1,179 @@
+/* cytospace_b200.h -- C ABI of the B200-native CytoSPACE assignment hot path.
+ *
+ * One shared library, libcytospace_b200.so, built from cytospace_b200/csrc/ for
+ * sm_100a.  Plain pointers and sizes only: every *_dev pointer is a CUDA device
+ * pointer owned by the caller (the Python host layer takes them from torch
+ * tensors), `stream` is a cudaStream_t passed as void*.  The library never
+ * frees caller memory and keeps no state between calls except the per-thread
+ * error string.  Every function returns 0 on success, a negative cyb_status
+ * otherwise; cyb_last_error() describes the last failure on this thread.
+ *
+ * Reference interfaces replaced (paths relative to the CytoSPACE repo):
+ *   cyb_standardise / cyb_cost_gemm_i32 / cyb_cost_build_pearson
+ *       <- matrix_correlation_pearson, cytospace/common/common.py:190-199,
+ *          called from calculate_cost,
+ *          cytospace/linear_assignment_solvers/linear_assignment_solvers.py:53-55
+ *          (the `location_repeat` gather at :63-66 is replaced by `row_map`,
+ *          resolved by index inside the LAP row scans; normalize_data,
+ *          common.py:142-147, is the optional fused `log_tpm` pre-step)
+ *   cyb_quantise_f64
+ *       <- the float64 cost matrix handed to call_solver,
+ *          linear_assignment_solvers.py:34-40 (entry P2: a host cost matrix
+ *          supplied by an unmodified CytoSPACE), integerised with the scale
+ *          precedent of cytospace/cytospace.py:337
+ *   cyb_lap_solve_i32
+ *       <- lapjv.lapjv(cost) as called by call_solver,
+ *          linear_assignment_solvers.py:34-40 (third-party lapjv==1.3.14) from
+ *          solve_linear_assignment_problem, cytospace/cytospace.py:323-332
+ *   cyb_lap_check_i32
+ *       <- no reference counterpart: on-device optimality certificate
+ *          (eps-complementary slackness of the returned prices)
+ */
+#ifndef CYTOSPACE_B200_H
+#define CYTOSPACE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CYB_ABI_VERSION 2
+
+/* status codes */
+#define CYB_OK                 0
+#define CYB_ERR_INVALID       -1   /* bad argument (null pointer, n <= 0, misaligned, unsupported size) */
+#define CYB_ERR_CUDA          -2   /* a CUDA runtime / driver call failed */
+#define CYB_ERR_WORKSPACE     -3   /* workspace too small */
+#define CYB_ERR_OVERFLOW      -4   /* price range exceeded the 46-bit bid field */
+#define CYB_ERR_NOT_CONVERGED -5   /* round cap hit (should not happen) */
+#define CYB_ERR_UNSUPPORTED   -6   /* device is not sm_100 / cooperative launch unavailable */
+
+/* input element types of the expression matrices */
+#define CYB_F64 0
+#define CYB_F32 1
+
+/* operand precision of the correlation GEMM (fp16 operands, fp32 accumulate) */
+#define CYB_PREC_F16    0   /* one fp16 pass                                         */
+#define CYB_PREC_F16X3  1   /* hi/lo split, 3 products in one K-concatenated GEMM:
+                               operand error ~2^-22, fp32-accumulation bound         */
+
+/* number of int64 entries written to stats_dev by cyb_lap_solve_i32 */
+#define CYB_LAP_NSTATS 16
+/* stats_dev layout:
+ *  [0] status (0 ok)        [1] eps-scaling phases      [2] bidding rounds
+ *  [3] bids (= row scans in rounds)  [4] full-matrix row scans (phase starts)
+ *  [5] cost minimum         [6] cost maximum            [7] scale S = n+1
+ *  [8] grid size used       [9] 1 if the price vector was shared-memory resident
+ *  [10] rounds with <= 1 bidder [11] max bidders in a round
+ *  [12] row scans at phase starts (rows whose pair was re-checked)
+ *  [13..15] reserved */
+
+int         cyb_abi_version(void);
+const char *cyb_last_error(void);
+
+/* Device properties the host layer needs for planning (sm count, cc, bytes). */
+int cyb_device_info(int device, int *sm_count, int *cc_major, int *cc_minor,
+                    size_t *total_mem_bytes);
+
+/* ---------------------------------------------------------------- cost build */
+
+/* Columns of the K-major operand one standardised column occupies:
+ * round_up(G, 64) for CYB_PREC_F16, 3 * round_up(G, 64) for CYB_PREC_F16X3. */
+int64_t cyb_operand_k(int64_t n_genes, int precision);
+
+/* Bytes of scratch cyb_standardise needs (per-column partial sums). */
+size_t cyb_standardise_workspace_bytes(int64_t n_genes, int64_t n_cols);
+
+/* Per-column standardisation + transpose of one expression matrix.
+ *   x_dev      [n_genes x n_cols] row-major (genes x cells, as the reference's
+ *              DataFrame.to_numpy()), leading dimension ld_x elements
+ *   log_tpm    1: apply normalize_data (TPM, log2(x+1)) first; 0: x is already
+ *              normalised (what solve_linear_assignment_problem receives)
+ *   operand_b  0: this matrix is the A (spot) operand, 1: the B (cell) operand;
+ *              only matters for CYB_PREC_F16X3 (A = [hi|hi|lo], B = [hi|lo|hi])
+ *   z_dev      fp16 [n_cols x cyb_operand_k()] K-major: z = (x - mean) / sigma,
+ *              K padding zero-filled by this call
+ *   colstat_dev float64 [2 x n_cols] out: mean, population sigma
+ *   zero_var_dev int32[1]: incremented by the number of sigma == 0 columns
+ *              (their z is all-zero => r = 0; the reference yields NaN,
+ *              common.py:196-197 -- the host layer raises on it)            */
+int cyb_standardise(const void *x_dev, int x_dtype, int64_t n_genes, int64_t n_cols,
+                    int64_t ld_x, int log_tpm, int precision, int operand_b,
+                    void *z_dev, double *colstat_dev, int32_t *zero_var_dev,
+                    void *workspace_dev, size_t workspace_bytes, void *stream);
+
+/* cost[s, c] = rint(-scale * sum_k zst[s,k] * zsc[c,k])  as int32,
+ * a TMA-fed tcgen05 GEMM with TMEM accumulators and a fused quantise epilogue.
+ *   zst_dev [n_spots x k] fp16, zsc_dev [n_cells x k] fp16 (K-major, k % 64 == 0,
+ *   16-byte aligned); cost_dev [n_spots x ld_cost] int32 row-major.
+ * With z from cyb_standardise, scale = 1e6 / n_genes gives rint(-1e6 * r).   */
+int cyb_cost_gemm_i32(const void *zst_dev, const void *zsc_dev, int64_t n_spots,
+                      int64_t n_cells, int64_t k, float scale, int32_t *cost_dev,
+                      int64_t ld_cost, void *stream);
+
+/* Bytes of device workspace cyb_cost_build_pearson needs. */
+size_t cyb_cost_build_workspace_bytes(int64_t n_genes, int64_t n_cells, int64_t n_spots,
+                                      int precision);
+
+/* calculate_cost, Pearson branch, in one call: standardise both matrices and run
+ * the GEMM.  cost_dev [n_spots x ld_cost] = rint(-cost_scale * pearson(st, sc)).
+ * colstat_sc_dev / colstat_st_dev: float64 [2 x n] out (may be NULL).           */
+int cyb_cost_build_pearson(const void *sc_dev, const void *st_dev, int x_dtype,
+                           int64_t n_genes, int64_t n_cells, int64_t n_spots,
+                           int64_t ld_sc, int64_t ld_st, int log_tpm, int precision,
+                           double cost_scale, int32_t *cost_dev, int64_t ld_cost,
+                           double *colstat_sc_dev, double *colstat_st_dev,
+                           int32_t *zero_var_dev, void *workspace_dev,
+                           size_t workspace_bytes, void *stream);
+
+/* out[i, j] = rint(scale * in[i, j]) as int32 (entry P2: an n_rows x n_cols float64
+ * cost matrix built by the reference itself).  bad_dev int32[1] is incremented by
+ * the number of non-finite or out-of-range (|scale*x| >= 2^30) entries.           */
+int cyb_quantise_f64(const double *in_dev, int64_t n_rows, int64_t n_cols, int64_t ld_in,
+                     double scale, int32_t *out_dev, int64_t ld_out, int32_t *bad_dev,
+                     void *stream);
+
+/* ----------------------------------------------------------------------- LAP */
+
+/* Bytes of device workspace cyb_lap_solve_i32 needs for an n x n problem. */
+size_t cyb_lap_workspace_bytes(int64_t n);
+
+/* Exact dense LAP: min sum_i cost[row_map[i], x(i)] over permutations x.
+ *   cost_dev    int32 [n_rows_compact x ld] row-major; |cost| < 2^30
+ *   row_map_dev int32[n] or NULL (identity): LAP row i is compact row row_map[i]
+ *   rowsol_dev  int32[n] out: column (cell) of LAP row i
+ *   colsol_dev  int32[n] out: LAP row (spot slot) of column j -- what CytoSPACE
+ *               consumes (linear_assignment_solvers.py:38)
+ *   price_dev   int64[n] out: column prices in units of 1/(n+1) cost
+ *   total_dev   int64[1] out: sum_i cost[row_map[i], rowsol[i]]
+ *   stats_dev   int64[CYB_LAP_NSTATS] out (layout above)
+ *   grid_hint   0 = auto (one CTA per SM); otherwise the number of CTAs
+ * Synchronous eps-scaling auction (Jacobi rounds) in one persistent cooperative
+ * kernel; costs scaled by n+1, last phase eps = 1 => the returned assignment is
+ * optimal for the integer matrix.  Deterministic: lowest column index wins a
+ * row's tie, highest bid then lowest row index wins a column.               */
+int cyb_lap_solve_i32(const int32_t *cost_dev, int64_t ld, int64_t n,
+                      const int32_t *row_map_dev, int32_t *rowsol_dev,
+                      int32_t *colsol_dev, int64_t *price_dev, int64_t *total_dev,
+                      int64_t *stats_dev, void *workspace_dev, size_t workspace_bytes,
+                      int grid_hint, void *stream);
+
+/* Optimality certificate / row-scan pass: for every LAP row computes
+ * m_i = min_j (cost*(n+1) + price) and writes
+ *   out_dev[0] = max_i ( (cost[i,rowsol[i]]*(n+1) + price[rowsol[i]]) - m_i )
+ *                (<= 1 certifies optimality), out_dev[1] = total cost,
+ *   out_dev[2] = number of rows whose rowsol is not a valid column.
+ * One coalesced pass over the whole matrix (n*n*4 bytes): the HBM roofline
+ * probe of the LAP row scan.  Workspace: cyb_lap_workspace_bytes(n).
+ * Synchronises the stream once (it needs the cost minimum on the host). */
+int cyb_lap_check_i32(const int32_t *cost_dev, int64_t ld, int64_t n,
+                      const int32_t *row_map_dev, const int32_t *rowsol_dev,
+                      const int64_t *price_dev, int64_t *out_dev, void *workspace_dev,
+                      size_t workspace_bytes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CYTOSPACE_B200_H */

@@ -1,0 +1,135 @@
+"""GPU: the whole path behind the reference-facing entry points."""
+import numpy as np
+import pandas as pd
+import pytest
+import torch
+
+import oracle
+from oracle import cost_oracle as co
+import cytospace_b200
+from cytospace_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+
+def oracle_total_on(cost_i32, row_map=None):
+    return oracle.lapjv_i32(cost_i32, row_map)[2][0]
+
+
+def test_solve_linear_assignment_problem_cfg1(engine):
+    """cfg1: 1k x 1k x 2k genes.  LAP parity is defined on the GPU-built integer matrix:
+    the device total must equal the CPU JV oracle's total on that same matrix."""
+    sc, st, cn = syn.structured_counts(1000, 1000, 2000, 1, seed=1001)
+    sc_n, st_n = co.normalize_data(sc), co.normalize_data(st)
+    mapped, pidx = cytospace_b200.solve_linear_assignment_problem(
+        sc_n, st_n, cn, "lapjv_b200", None, 1, "Pearson_correlation", process_idx=3)
+    assert pidx == 3 and isinstance(mapped, list) and len(mapped) == 1000
+    assert sorted(mapped) == list(range(1000))                     # cn == 1: a permutation of the spots
+    spot_of_cell, res, cost = engine.assign(sc_n, st_n, cn)
+    assert spot_of_cell.cpu().tolist() == mapped                   # deterministic
+    cost_np = cost[:, :1000].cpu().numpy()
+    assert res.total == oracle_total_on(cost_np)
+    # against the float64 reference formulation: the GPU assignment's float64 cost is within
+    # n * 4e-6 of the float64 optimum (quantisation + fp16x3 tolerance)
+    f64 = -co.matrix_correlation_pearson(sc_n, st_n)
+    tot_f64_gpu = f64[np.array(mapped), np.arange(1000)].sum()
+    tot_f64_opt = oracle.lapjv_f64(f64)[2][0]
+    assert tot_f64_gpu >= tot_f64_opt - 1e-9 and tot_f64_gpu - tot_f64_opt <= 1000 * 4e-6
+
+
+def test_visium_like_repeated_spots(engine):
+    sc, st, cn = syn.structured_counts(900, 150, 800, 6, seed=1004)
+    sc_n, st_n = co.normalize_data(sc), co.normalize_data(st)
+    mapped, _ = cytospace_b200.solve_linear_assignment_problem(
+        sc_n, st_n, cn, "lapjv", None, 1, "Pearson_correlation")
+    assert np.array_equal(np.bincount(mapped, minlength=150), cn)   # every spot gets exactly cn cells
+    _, res, cost = engine.assign(sc_n, st_n, cn)
+    row_map = np.repeat(np.arange(150, dtype=np.int32), 6)
+    assert res.total == oracle_total_on(cost[:, :900].cpu().numpy(), row_map)
+
+
+def test_uneven_capacities_and_empty_spots(engine):
+    rng = np.random.default_rng(0)
+    cn = rng.integers(0, 5, 80)
+    sc, st, _ = syn.structured_counts(int(cn.sum()), 80, 400, cn, seed=12)
+    sc_n, st_n = co.normalize_data(sc), co.normalize_data(st)
+    mapped, _ = cytospace_b200.solve_linear_assignment_problem(
+        sc_n, st_n, cn, "lapjv_compat", None, 1, "Pearson_correlation")
+    assert np.array_equal(np.bincount(mapped, minlength=80), cn)
+
+
+def test_non_square_raises(engine):
+    sc, st, cn = syn.structured_counts(50, 40, 100, 1, seed=1)
+    with pytest.raises(ValueError, match="square"):
+        cytospace_b200.solve_linear_assignment_problem(co.normalize_data(sc), co.normalize_data(st), cn,
+                                                       "lapjv", None, 1, "Pearson_correlation")
+
+
+def test_lapjv_callable_conventions(engine):
+    """P2: unmodified call_solver convention on a float64 host matrix (LAS:34-40)."""
+    from cytospace_b200 import import_solver, call_solver
+    rng = np.random.default_rng(4)
+    cost = rng.random((120, 120)) * 2 - 1
+    row_ind, col_ind, (total, u, v) = import_solver("lapjv")(cost)
+    q = np.rint(cost * 1e6).astype(np.int32)
+    assert int(q[np.arange(120), row_ind].sum()) == oracle_total_on(q)
+    assert np.array_equal(col_ind[row_ind], np.arange(120))
+    assert abs(total - cost[np.arange(120), row_ind].sum()) < 1e-9
+    red = cost - u[:, None] - v[None, :]
+    assert red.min() > -2e-6                                        # duals feasible up to quantisation
+    y = call_solver(import_solver("lapjv"), "lapjv", cost)
+    assert np.array_equal(y, col_ind)
+    tot2, x2, y2 = import_solver("lapjv_compat")(cost)
+    assert np.array_equal(call_solver(import_solver("lapjv_compat"), "lapjv_compat", cost), y2)
+    assert np.array_equal(x2, row_ind)
+    with pytest.raises(ValueError):
+        import_solver("lapjv")(np.zeros((3, 4)))
+
+
+def test_calculate_cost_compat(engine, cost_golden):
+    g = cost_golden
+    d, loc = cytospace_b200.calculate_cost(g["b_sc_norm"], g["b_st_norm"], g["b_cn"], "lapjv", "Pearson_correlation")
+    assert np.array_equal(loc, g["b_location_repeat"])
+    assert np.abs(d - g["b_distance_repeat"]).max() <= 5e-6
+
+
+def test_apply_linear_assignment_chunked_single_cell(engine):
+    """--single-cell -noss: matched blocks of spots and cells (cytospace.py:628-633)."""
+    from cytospace_b200 import partition_indices, apply_linear_assignment
+    n = 700
+    sc, st, cn = syn.structured_counts(n, n, 600, 1, seed=77)
+    sc_df = pd.DataFrame(sc, columns=[f"cell{i}" for i in range(n)])
+    st_df = pd.DataFrame(st, columns=[f"spot{i}" for i in range(n)])
+    coords = pd.DataFrame({"row": np.arange(n), "col": np.arange(n) * 2}, index=st_df.columns)
+    np.random.seed(1)
+    isc = partition_indices(np.arange(n), split_by_interval_int=300, shuffle=True)
+    ist = partition_indices(np.arange(n), split_by_interval_int=300, shuffle=True)
+    locs, cells = apply_linear_assignment(sc_df, st_df, coords, cn, "lapjv_b200", None, 1, "Pearson_correlation", 4,
+                                          isc, index_st_list=ist)
+    assert len(locs) == n and len(cells) == n
+    assert sorted(locs.index.tolist()) == sorted(st_df.columns.tolist())     # each spot used once
+    assert sorted(cells.tolist()) == sorted(sc_df.columns.tolist())
+    # chunk k's cells only land on chunk k's spots
+    pos = 0
+    for a, b in zip(isc, ist):
+        got = set(locs.index[pos:pos + len(a)]); pos += len(a)
+        assert got == set(st_df.columns[b])
+
+
+def test_apply_linear_assignment_sub_spots(engine):
+    """--sampling-sub-spots: blocks of cells against all spots with sub-sampled capacities (:650-660)."""
+    from cytospace_b200 import partition_indices, apply_linear_assignment
+    sc, st, cn = syn.structured_counts(480, 80, 500, 6, seed=31)
+    sc_df = pd.DataFrame(sc, columns=[f"cell{i}" for i in range(480)])
+    st_df = pd.DataFrame(st, columns=[f"spot{i}" for i in range(80)])
+    coords = pd.DataFrame({"row": np.arange(80)}, index=st_df.columns)
+    np.random.seed(2)
+    isc = partition_indices(np.arange(480), split_by_interval_int=200, shuffle=True)
+    agg = np.repeat(np.arange(80), cn)
+    parts = partition_indices(agg, split_by_interval_int=200, shuffle=True)
+    subs = [np.bincount(p, minlength=80) for p in parts]
+    locs, cells = apply_linear_assignment(sc_df, st_df, coords, cn, "lapjv", None, 1, "Pearson_correlation", 2,
+                                          isc, subsampled_cell_number_to_node_assignment_list=subs)
+    counts = locs.index.value_counts()
+    assert all(counts[f"spot{s}"] == cn[s] for s in range(80))
+    assert sorted(cells.tolist()) == sorted(sc_df.columns.tolist())
