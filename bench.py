@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""bench.py -- cell-spot assignments/sec of the CytoSPACE assignment hot path on B200.
+
+A "step" is one pass of the hot path (Pearson cost build + exact LAP) over one synthetic
+N-cell x S-spot x G-gene problem.  Default workload = BASELINE.json configs[1]
+(10k x 10k x 20k genes).  Prints ONE JSON line (rank 0).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg1|cfg2|cfg3|cfg4] [--impl reference]
+
+* ``value``  : whole-job assignments/s, inputs resident in HBM when the timed region starts.
+* ``e2e``    : same metric through the reference-facing call with HOST buffers (pinned H2D of both
+               expression matrices + D2H of the assignment inside the timed region).
+* ``roofline``: the dominant kernel (the LAP auction kernel): algorithmic row-scan bytes / its
+               CUDA-event time vs the measured HBM peak (MEASURED_PEAKS.json).
+* ``cpu_baseline``: the oracle (restated JV + numpy cost build) on this box's host cores.
+* ``--impl reference``: the reference's own CPU formulation (float64 numpy cost build, 1e-16 tie-noise,
+               restated float64 JV -- the lapjv wheel is absent) on a bounded sample of the workload.
+N > 1 (torchrun): one rank per GPU, each rank solves its own independent sub-problem (CytoSPACE's
+chunks are independent, cytospace.py:430-451), one all-gather of the assignment indices per step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "cfg1": dict(n_cells=1000, n_spots=1000, n_genes=2000, cps=1, seed=1001,
+                 desc="synthetic 1k cells x 1k spots x 2k genes"),
+    "cfg2": dict(n_cells=10000, n_spots=10000, n_genes=20000, cps=1, seed=1002,
+                 desc="synthetic 10k cells x 10k spots x 20k genes, cost-build + LAP"),
+    "cfg3": dict(n_cells=50000, n_spots=50000, n_genes=20000, cps=1, seed=1003,
+                 desc="synthetic 50k cells x 50k spots x 20k genes"),
+    "cfg4": dict(n_cells=30000, n_spots=5000, n_genes=30000, cps=6, seed=1004,
+                 desc="Visium-shaped 30k cells x 5k spots (6 cells/spot) x 30k genes"),
+    "chunk25k": dict(n_cells=25000, n_spots=25000, n_genes=20000, cps=1, seed=1005,
+                     desc="one 25k x 25k x 20k-gene sub-LAP of the 200k chunked problem (cfg5)"),
+}
+METRIC = "cell-spot assignments/sec"
+UNIT = "assignments/s"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), d.get("bf16_tflops_sustained", 1400.0), "measured"
+    return 6650.0, 1590.0, 1400.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.th.join(timeout=2)
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 7 and r[3 + i] == "Active" for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- reference arm (CPU)
+def reference_step(sc_n, st_n, cn, seed=1):
+    """The reference's formulation of one solve (cytospace.py:304-332) on the CPU: float64 numpy cost
+    build (LAS:42-69 / COM:190-199), 1e-16 * U(0,1) tie-noise (CYT:325-327), dense JV on float64
+    (restated: the lapjv wheel is absent), location_repeat[assignment] (CYT:331)."""
+    import oracle
+    from oracle import cost_oracle as co
+    distance_repeat, location_repeat = co.calculate_cost(sc_n, st_n, cn)
+    np.random.seed(seed)
+    cost_scaled = distance_repeat + 1e-16 * np.random.rand(*distance_repeat.shape)
+    _, colsol, (total, _, _) = oracle.lapjv_f64(cost_scaled)
+    return location_repeat[colsol], total
+
+
+def run_reference(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+    from oracle import cost_oracle as co
+    from cytospace_b200 import synthetic as syn
+    oracle.build()
+    cores = os.cpu_count() or 1
+    budget_s = 150.0 / max(1, args.steps + args.warmup)
+    est_full = 45.0 * (wl["n_cells"] / 10000.0) ** 2.6 * (wl["n_genes"] / 20000.0) ** 0.5
+    n = wl["n_cells"]
+    for cand in (wl["n_cells"], 7000, 5000, 4000, 3000, 2000, 1000, 500):
+        if cand <= wl["n_cells"] and est_full * (cand / wl["n_cells"]) ** 2.6 <= budget_s:
+            n = cand
+            break
+    else:
+        n = min(500, wl["n_cells"])
+    n_spots = max(1, n // wl["cps"])
+    n = n_spots * wl["cps"]
+    sc, st, cn = syn.structured_counts(n, n_spots, wl["n_genes"], wl["cps"], seed=wl["seed"])
+    sc_n, st_n = co.normalize_data(sc), co.normalize_data(st)
+    del sc, st
+    for _ in range(args.warmup):
+        reference_step(sc_n, st_n, cn)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        _, total = reference_step(sc_n, st_n, cn)
+    dt = (time.perf_counter() - t0) / max(1, args.steps)
+    value = n / dt
+    sample = (f"{n} cells x {n_spots} spots x {wl['n_genes']} genes block of {args.workload} "
+              f"(full problem {wl['n_cells']} x {wl['n_spots']}); float64 numpy cost build on {cores} threads + "
+              "restated float64 JV (1 thread; lapjv wheel absent)")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {wl['desc']}", "sample_n": n},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "total_cost_f64": total}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------- B200 arm
+def cpu_baseline(cost_np, row_map, sc_host, st_host, wl, total_gpu):
+    """Oracle on this box's host cores: restated JV (int32, 1 thread) on the GPU-built matrix (full
+    size up to 10k, else its leading 10k block) + numpy float64 cost build on a 2k x 2k x G block."""
+    import oracle
+    from oracle import cost_oracle as co
+    oracle.build()
+    cores = os.cpu_count() or 1
+    n = cost_np.shape[1]
+    b = min(2000, sc_host.shape[1], st_host.shape[1])
+    t0 = time.perf_counter()
+    co.cost_matrix_i32(sc_host[:, :b].numpy(), st_host[:, :b].numpy())
+    t_cost_blk = time.perf_counter() - t0
+    t_cost = t_cost_blk * (sc_host.shape[1] / b) * (st_host.shape[1] / b)
+    out = {"unit": UNIT, "cores": cores, "kind": "port"}
+    if n <= 10000:
+        t0 = time.perf_counter()
+        total_cpu = oracle.lapjv_i32(cost_np, row_map)[2][0]
+        t_lap = time.perf_counter() - t0
+        out.update(value=n / (t_cost + t_lap), lap_s=t_lap, cost_build_s_scaled=t_cost,
+                   total_cost=int(total_cpu), total_equal=bool(total_cpu == total_gpu),
+                   sample=f"LAP: restated JV (int32, 1 thread) on the full GPU-built {n}x{n} matrix; cost build: "
+                          f"numpy float64 on a {b}x{b}x{wl['n_genes']} block ({cores} BLAS threads) scaled by "
+                          f"{(sc_host.shape[1] / b) * (st_host.shape[1] / b):.1f}")
+    else:
+        m = 8000
+        sub = np.ascontiguousarray(cost_np[:m, :m]) if row_map is None else None
+        if sub is None:
+            rm = row_map[:m]
+            t0 = time.perf_counter(); oracle.lapjv_i32(np.ascontiguousarray(cost_np[:, :m]), rm); t_blk = time.perf_counter() - t0
+        else:
+            t0 = time.perf_counter(); oracle.lapjv_i32(sub); t_blk = time.perf_counter() - t0
+        t_lap = t_blk * (n / m) ** 2.6
+        out.update(value=n / (t_cost + t_lap), lap_s=t_lap, cost_build_s_scaled=t_cost, total_equal=None,
+                   sample=f"LAP: restated JV on the leading {m}x{m} block, extrapolated with n^2.6; cost build: "
+                          f"numpy float64 on a {b}x{b} block scaled")
+    return out
+
+
+def run_b200(args, wl):
+    import torch
+    import torch.distributed as dist
+    from cytospace_b200 import synthetic as syn
+    from cytospace_b200.engine import AssignmentEngine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    eng = AssignmentEngine(device=dev, precision=args.precision)
+    eng.profile = True
+    n_cells, n_spots, n_genes, cps = wl["n_cells"], wl["n_spots"], wl["n_genes"], wl["cps"]
+
+    # ---- synthetic inputs (sampled on the device, normalised like CYT:398-399) -- not timed
+    sc_raw, st_raw, cn = syn.structured_counts_torch(n_cells, n_spots, n_genes, cps, seed=wl["seed"] + 17 * rank,
+                                                     device=dev)
+    sc_dev = syn.normalize_data_torch(sc_raw); del sc_raw
+    st_dev = syn.normalize_data_torch(st_raw); del st_raw
+    sc_host = sc_dev.cpu().pin_memory()
+    st_host = st_dev.cpu().pin_memory()
+    h2d = sc_host.numel() * 8 + st_host.numel() * 8
+    d2h = n_cells * 8
+    gathered = [torch.empty(n_cells, dtype=torch.int64, device=dev) for _ in range(world)] if world > 1 else None
+
+    def step_resident():
+        spot, res, cost = eng.assign(sc_dev, st_dev, cn)
+        if world > 1:
+            dist.all_gather(gathered, spot)
+        return spot, res, cost
+
+    def step_e2e():
+        sc_dev.copy_(sc_host, non_blocking=True)
+        st_dev.copy_(st_host, non_blocking=True)
+        spot, res, cost = eng.assign(sc_dev, st_dev, cn)
+        if world > 1:
+            dist.all_gather(gathered, spot)
+        return spot.cpu(), res, cost
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            out = fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        lap_ms, cost_ms = [], []
+        e0.record()
+        for _ in range(steps):
+            out = fn()
+            lap_ms.append(eng.last_ms("lap")); cost_ms.append(eng.last_ms("cost"))
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), out, float(np.mean(lap_ms)), float(np.mean(cost_ms))
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    tot_ms, (spot, res, cost), lap_ms, cost_ms = timed(step_resident, args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+    e2e_ms, _, _, _ = timed(step_e2e, args.steps, min(args.warmup, 1))
+
+    if rank == 0:
+        hbm, tf_burst, tf_sus, peak_src = measured_peaks()
+        ms_per_step = tot_ms / args.steps
+        value = world * n_cells / (ms_per_step / 1e3)
+        e2e_value = world * n_cells / (e2e_ms / args.steps / 1e3)
+        n = n_cells
+        scans = res.row_scans + n                    # bids + phase-start re-checks + the min/max pass
+        lap_bytes = scans * n * 4
+        ach = lap_bytes / (lap_ms / 1e3) / 1e9
+        kop = n_genes if args.precision == "f16" else 3 * n_genes
+        gemm_flop_alg = 2.0 * n_spots * n_cells * n_genes
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int32/int64 LAP; fp16(hi/lo split)->fp32 cost GEMM",
+            "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {wl['desc']}", "n_cells": n_cells, "n_spots": n_spots,
+                       "n_genes": n_genes, "cells_per_spot": cps, "precision": args.precision,
+                       "l2": "inputs larger than L2 (expression matrices %.1f GB, cost matrix %.2f GB)"
+                             % (h2d / 1e9, n_spots * n_cells * 4 / 1e9),
+                       "per_rank": "each rank solves its own independent sub-problem" if world > 1 else "single GPU"},
+            "roofline": {"kernel": "lap_auction_kernel", "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s",
+                         "frac": ach / hbm, "traffic": None, "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)",
+                         "row_scans": scans, "bytes_per_scan": n * 4, "kernel_ms": lap_ms},
+            "roofline_cost_build": {"bound": "tensor", "algorithmic_flop": gemm_flop_alg, "ms": cost_ms,
+                                    "achieved": gemm_flop_alg / (cost_ms / 1e3) / 1e12, "peak": tf_burst,
+                                    "unit": "TFLOP/s", "frac": gemm_flop_alg / (cost_ms / 1e3) / 1e12 / tf_burst,
+                                    "executed_flop": 2.0 * n_spots * n_cells * kop,
+                                    "note": "ms covers standardise pre-pass + GEMM; f16x3 executes 3x the algorithmic flop"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": args.steps * 8,
+            "clocks": clocks,
+            "lap_stats": {k: res.stats[k] for k in ("phases", "rounds", "bids", "rounds_le1", "max_bidders", "grid",
+                                                    "smem_prices")},
+            "total_cost": res.total, "lap_ms": lap_ms, "cost_build_ms": cost_ms,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            row_map = None if cps == 1 else np.repeat(np.arange(n_spots, dtype=np.int32), cn)
+            cost_np = cost[:, :n_cells].cpu().numpy()
+            line["cpu_baseline"] = cpu_baseline(cost_np, row_map, sc_host, st_host, wl, res.total)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--precision", default="f16x3", choices=["f16", "f16x3"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl)
+    else:
+        run_b200(args, wl)
+
+
+if __name__ == "__main__":
+    main()

@@ -148,14 +148,19 @@ class AssignmentEngine:
             _native.ptr("int32_t *", zero_var), self.ffi.cast("void *", ws.data_ptr() + off), ws_bytes,
             self._stream()))
         self._mark("cost", 1)
+        self._zero_var = zero_var
         if check_variance:
-            nz = int(zero_var.item())
-            if nz:
-                raise ValueError(f"{nz} cell/spot column(s) have zero variance: Pearson correlation undefined "
-                                 "(the reference would hand NaN costs to the solver)")
+            self.check_zero_variance()
         if return_colstats:
             return out, colstat_sc, colstat_st
         return out
+
+    def check_zero_variance(self):
+        """Raises if the last cost build met a zero-variance column (one small D2H read)."""
+        nz = int(self._zero_var.item())
+        if nz:
+            raise ValueError(f"{nz} cell/spot column(s) have zero variance: Pearson correlation undefined "
+                             "(the reference would hand NaN costs to the solver)")
 
     def quantise(self, cost_f64: torch.Tensor, scale: float) -> torch.Tensor:
         """int32 ``rint(scale * cost)`` of a float64 device matrix (entry P2)."""
@@ -241,12 +246,13 @@ class AssignmentEngine:
         if n != N:
             raise ValueError(f"the assignment must be square: sum(cell_number_to_node_assignment)={n} "
                              f"but {N} cells were given")
-        cost = self.cost_build(sc, st, log_tpm=log_tpm)
+        cost = self.cost_build(sc, st, log_tpm=log_tpm, check_variance=False)   # checked after the solve: one sync
         if (cn == 1).all():
             row_map = None
         else:
             # location_repeat of linear_assignment_solvers.py:63-65, kept as an index instead of a row copy
             row_map = torch.from_numpy(np.repeat(np.arange(S, dtype=np.int32), cn)).to(self.device)
         res = self.lap_solve(cost, row_map, n=N)
+        self.check_zero_variance()
         spot_of_cell = res.colsol.long() if row_map is None else row_map[res.colsol.long()].long()
         return spot_of_cell, res, cost

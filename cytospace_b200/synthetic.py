@@ -49,3 +49,47 @@ def uniform_cost_i32(n, seed=11, high=2_000_000):
     """LAP-only input: int32 uniform on [0, high)."""
     rng = np.random.default_rng(seed)
     return rng.integers(0, high, size=(n, n), dtype=np.int32)
+
+
+def structured_counts_torch(n_cells, n_spots, n_genes, cells_per_spot=1, seed=1001, n_types=20, depth=1500.0,
+                            spot_depth_factor=10.0, device="cuda", dtype=None, block=4096):
+    """Same distribution as ``structured_counts`` sampled with torch on ``device`` (bench-sized
+    inputs in seconds instead of minutes; NOT the same random stream).  Returns
+    (sc_counts [G x N], st_counts [G x S], cn int64 ndarray[S])."""
+    import torch
+    dtype = dtype or torch.float64
+    gen = torch.Generator(device=device)
+    gen.manual_seed(int(seed))
+    cn = np.full(n_spots, cells_per_spot, dtype=np.int64) if np.isscalar(cells_per_spot) \
+        else np.asarray(cells_per_spot, dtype=np.int64)
+    base = torch.randn(n_genes, generator=gen, device=device) * 1.5 - 2.0
+    mu = base.repeat(n_types, 1)
+    marker = torch.rand((n_types, n_genes), generator=gen, device=device) < 0.02
+    mu = mu + marker * (torch.randn((n_types, n_genes), generator=gen, device=device) * 0.5 + 2.0)
+    rate = torch.softmax(mu, dim=1)                                      # [K x G]
+    sc = torch.empty((n_genes, n_cells), dtype=dtype, device=device)
+    sc_type = torch.randint(0, n_types, (n_cells,), generator=gen, device=device)
+    for c0 in range(0, n_cells, block):
+        t = sc_type[c0:c0 + block]
+        sc[:, c0:c0 + block] = torch.poisson(depth * rate[t], generator=gen).T.to(dtype)
+    st = torch.empty((n_genes, n_spots), dtype=dtype, device=device)
+    cn_t = torch.from_numpy(np.maximum(cn, 1)).to(device)
+    kmax = int(cn_t.max().item())
+    for s0 in range(0, n_spots, block):
+        k = cn_t[s0:s0 + block]
+        types = torch.randint(0, n_types, (k.numel(), kmax), generator=gen, device=device)
+        w = (torch.arange(kmax, device=device)[None, :] < k[:, None]).to(rate.dtype)     # first cn[s] draws count
+        mix = torch.zeros((k.numel(), n_types), device=device, dtype=rate.dtype)
+        mix.scatter_add_(1, types, w)
+        lam = depth * spot_depth_factor * (mix @ rate)
+        st[:, s0:s0 + block] = torch.poisson(lam, generator=gen).T.to(dtype)
+    return sc, st, cn
+
+
+def normalize_data_torch(x):
+    """``normalize_data`` (cytospace/common/common.py:142-147) with torch ops -- bench input
+    preparation only (the product's fused version is the ``log_tpm`` flag of cyb_standardise)."""
+    import torch
+    x = torch.nan_to_num(x).to(torch.float64)
+    x = x * (1e6 / x.sum(0, keepdim=True))
+    return torch.nan_to_num(torch.log2(x + 1))
