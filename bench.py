@@ -296,8 +296,8 @@ def run_b200(args, wl):
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": args.steps * 8,
             "clocks": clocks,
-            "lap_stats": {k: res.stats[k] for k in ("phases", "rounds", "bids", "rounds_le1", "max_bidders", "grid",
-                                                    "smem_prices")},
+            "lap_stats": {k: res.stats[k] for k in ("phases", "rounds", "bids", "tail_bids", "tails", "rounds_le1",
+                                                    "max_bidders", "grid", "smem_prices")},
             "total_cost": res.total, "lap_ms": lap_ms, "cost_build_ms": cost_ms,
         }
         if world == 1 and not args.no_cpu_baseline:

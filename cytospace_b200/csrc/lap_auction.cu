@@ -39,8 +39,9 @@
 // HBM traffic: each bid reads one row (n*4 bytes) once; prices, owners, lists
 // and slots live in shared memory / L2.
 
-#include <cstdint>
 #include <climits>
+#include <cstdint>
+#include <cstdlib>
 
 #include "common.h"
 
@@ -53,6 +54,7 @@ constexpr long long kInf = 0x3FFFFFFFFFFFFFFFll;
 constexpr long long kBidLimit = 1ll << 45;                     // 46-bit bid field
 constexpr int kTheta = 8;
 constexpr int kEps0Div = 4;
+constexpr int kTailMax = 64;                                   // capacity of the tail FIFO
 
 struct LapParams {
     const int32_t *cost;
@@ -72,6 +74,7 @@ struct LapParams {
     int *gmm;                // [0] cmin, [1] cmax, [2] status
     int qcap;
     long long max_rounds;
+    int tail_t;              // rounds with <= tail_t bidders are finished by CTA 0 alone (Gauss-Seidel tail)
 };
 
 struct Best {
@@ -212,6 +215,7 @@ __global__ void __launch_bounds__(kThreads, 1) lap_auction_kernel(const LapParam
     int *myq = reinterpret_cast<int *>(smem_raw + off);
     __shared__ long long red_b1[32], red_b2[32];
     __shared__ int red_j[32], wcnt[32];
+    __shared__ int tq[kTailMax], tq_head, tq_cnt, tq_status;
 
     const int G = gridDim.x, b = blockIdx.x, t = threadIdx.x;
     const long long S = (long long)n + 1;
@@ -251,8 +255,9 @@ __global__ void __launch_bounds__(kThreads, 1) lap_auction_kernel(const LapParam
     long long eps = ((long long)cmax - (long long)cmin) * S / kEps0Div;
     if (eps < 1) eps = 1;
 
-    long long rounds = 0, bids = 0, passes = 0, phases = 0, rounds1 = 0, maxF = 0;
+    long long rounds = 0, bids = 0, passes = 0, phases = 0, rounds1 = 0, maxF = 0, tail_bids = 0, tails = 0;
     int status = 0, par = 0;
+    const int tail_t = min(P.tail_t, kTailMax);
 
     for (;;) {
         ++phases;
@@ -289,7 +294,48 @@ __global__ void __launch_bounds__(kThreads, 1) lap_auction_kernel(const LapParam
         __syncthreads();
 
         // ---- bidding rounds --------------------------------------------------
+        bool ran_tail = false;
         while (F > 0) {
+            if (F <= tail_t) {
+                // ---- Gauss-Seidel tail: few bidders left, a grid barrier per round would cost more
+                // than the bids.  CTA 0 alone drains a FIFO of free rows; every bid sees the prices
+                // the previous one left and the lone bidder always wins, so nothing is exchanged
+                // until the phase ends.  (Same auction, sequential order: still eps-CS, still exact.)
+                grid_barrier(P.bar, bar_target, G);          // every CTA has finished its resolve writes
+                ran_tail = true; ++tails;
+                if (b == 0) {
+                    if (t < F) tq[t] = __ldcg(P.list[par] + t);
+                    if (t == 0) { tq_head = 0; tq_cnt = F; tq_status = 0; }
+                    __syncthreads();
+                    while (tq_cnt > 0 && tq_status == 0) {
+                        const int i = tq[tq_head];
+                        const int32_t *r = rowptr(i);
+                        const Best s = scan_row<SMEMP>(r, n, cmin, S, price_rd, vec_ok, red_b1, red_b2, red_j);
+                        ++tail_bids;
+                        if (t == 0) {
+                            const long long pj = SMEMP ? sprice[s.j1] : __ldcg(P.price + s.j1);
+                            const long long bid = pj + (n > 1 ? s.b2 - s.b1 : 0) + eps;
+                            if (bid >= kBidLimit) tq_status = CYB_ERR_OVERFLOW;
+                            if (tail_bids + rounds > P.max_rounds) tq_status = CYB_ERR_NOT_CONVERGED;
+                            const int prev = __ldcg(P.owner + s.j1);
+                            P.owner[s.j1] = i; P.rowsol[i] = s.j1; P.price[s.j1] = bid;
+                            if (SMEMP) sprice[s.j1] = bid;
+                            int head = tq_head + 1; if (head == kTailMax) head = 0;
+                            int cnt = tq_cnt - 1;
+                            if (prev >= 0) {
+                                P.rowsol[prev] = -1;
+                                int tail = head + cnt; if (tail >= kTailMax) tail -= kTailMax;
+                                tq[tail] = prev; ++cnt;
+                            }
+                            tq_head = head; tq_cnt = cnt;
+                        }
+                        __syncthreads();
+                    }
+                    if (t == 0 && tq_status) atomicExch(P.gmm + 2, tq_status);
+                }
+                F = 0;
+                break;
+            }
             if (++rounds > P.max_rounds) { status = CYB_ERR_NOT_CONVERGED; break; }
             bids += F;
             if (F <= 1) ++rounds1;
@@ -344,7 +390,15 @@ __global__ void __launch_bounds__(kThreads, 1) lap_auction_kernel(const LapParam
             __syncthreads();
         }
         if (status) break;
-        grid_barrier(P.bar, bar_target, G);        // rowsol of the last resolve becomes visible
+        grid_barrier(P.bar, bar_target, G);        // rowsol of the last resolve / the tail becomes visible
+        if (ran_tail) {
+            status = __ldcg(P.gmm + 2);
+            if (status) break;
+            if (SMEMP) {                            // pick up the prices CTA 0 moved during the tail
+                for (int j = t; j < n; j += kThreads) sprice[j] = __ldcg(P.price + j);
+                __syncthreads();
+            }
+        }
         if (eps == 1) break;
         eps /= kTheta;
         if (eps < 1) eps = 1;
@@ -365,7 +419,7 @@ __global__ void __launch_bounds__(kThreads, 1) lap_auction_kernel(const LapParam
         P.stats[0] = status; P.stats[1] = phases; P.stats[2] = rounds; P.stats[3] = bids;
         P.stats[4] = passes; P.stats[5] = cmin; P.stats[6] = cmax; P.stats[7] = S;
         P.stats[8] = G; P.stats[9] = SMEMP ? 1 : 0; P.stats[10] = rounds1; P.stats[11] = maxF;
-        P.stats[12] = (phases - 1) * (long long)n; P.stats[13] = 0; P.stats[14] = 0; P.stats[15] = 0;
+        P.stats[12] = (phases - 1) * (long long)n; P.stats[13] = tail_bids; P.stats[14] = tails; P.stats[15] = 0;
     }
 }
 
@@ -514,6 +568,8 @@ extern "C" int cyb_lap_solve_i32(const int32_t *cost_dev, int64_t ld, int64_t n,
     P.gmm = reinterpret_cast<int *>(ws + L.small + 16);
     P.qcap = (int)((n + G - 1) / G);
     P.max_rounds = 2000ll * n + 100000;
+    P.tail_t = 2;
+    if (const char *e = getenv("CYB_LAP_TAIL")) P.tail_t = atoi(e);
 
     // small block: barrier counter, cmin = INT_MAX, cmax = INT_MIN, status = 0
     const int init[8] = {0, 0, 0, 0, INT_MAX, INT_MIN, 0, 0};

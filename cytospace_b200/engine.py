@@ -23,7 +23,7 @@ from . import _native
 COST_SCALE = 10 ** 6           # integer scale of the correlation distance; precedent cytospace.py:337
 PRECISIONS = {"f16": 0, "f16x3": 1}
 STAT_NAMES = ("status", "phases", "rounds", "bids", "passes", "cost_min", "cost_max", "scale",
-              "grid", "smem_prices", "rounds_le1", "max_bidders", "phase_scans")
+              "grid", "smem_prices", "rounds_le1", "max_bidders", "phase_scans", "tail_bids", "tails")
 
 
 def _round_up(x: int, a: int) -> int:
@@ -42,8 +42,8 @@ class LapResult:
 
     @property
     def row_scans(self) -> int:
-        """Row scans the solve performed (bids + phase-start re-checks)."""
-        return int(self.stats["bids"]) + int(self.stats["phase_scans"])
+        """Row scans the solve performed (round bids + tail bids + phase-start re-checks)."""
+        return int(self.stats["bids"]) + int(self.stats["tail_bids"]) + int(self.stats["phase_scans"])
 
 
 class AssignmentEngine:

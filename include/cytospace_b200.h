@@ -68,7 +68,8 @@ extern "C" {
  *  [8] grid size used       [9] 1 if the price vector was shared-memory resident
  *  [10] rounds with <= 1 bidder [11] max bidders in a round
  *  [12] row scans at phase starts (rows whose pair was re-checked)
- *  [13..15] reserved */
+ *  [13] bids made in Gauss-Seidel tails (one CTA, no grid barrier)  [14] tails run
+ *  [15] reserved */
 
 int         cyb_abi_version(void);
 const char *cyb_last_error(void);

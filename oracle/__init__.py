@@ -61,7 +61,7 @@ def _load():
         lib.lapjv_i32_min_reduced_cost.argtypes = [ctypes.c_int, i32p, ctypes.c_int64, i32p, i64p, i64p]
         lib.auction_model_i32.restype = ctypes.c_int
         lib.auction_model_i32.argtypes = [ctypes.c_int, i32p, ctypes.c_int64, i32p, i32p, i32p, i64p, i64p,
-                                          ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_int64, i64p, i32p, ctypes.c_int64]
+                                          ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_int64, i64p, i32p, ctypes.c_int64, ctypes.c_int64]
         _lib = lib
     return _lib
 
@@ -136,7 +136,7 @@ def min_reduced_cost_i32(cost, u, v, row_map=None) -> int:
                                               _ptr(v, ctypes.c_int64)))
 
 
-def auction_model(cost, row_map=None, theta=8, eps0_div=4, keep_cs=True, stop_free=0, round_cap=0):
+def auction_model(cost, row_map=None, theta=8, eps0_div=4, keep_cs=True, stop_free=0, round_cap=0, tail_t=0):
     lib = _load()
     cost, row_map, n = _prep(cost, row_map, np.int32)
     rowsol = np.empty(n, np.int32); colsol = np.empty(n, np.int32)
@@ -146,7 +146,7 @@ def auction_model(cost, row_map=None, theta=8, eps0_div=4, keep_cs=True, stop_fr
                                _ptr(rowsol, ctypes.c_int32), _ptr(colsol, ctypes.c_int32),
                                _ptr(price, ctypes.c_int64), _ptr(total, ctypes.c_int64),
                                theta, eps0_div, int(keep_cs), stop_free, _ptr(stats, ctypes.c_int64),
-                               _ptr(rlog, ctypes.c_int32), round_cap)
+                               _ptr(rlog, ctypes.c_int32), round_cap, tail_t)
     if rc != 0:
         raise RuntimeError(f"auction_model_i32 failed rc={rc}")
     return rowsol, colsol, int(total[0]), price, stats, rlog[:min(round_cap, int(stats[1]))]

@@ -23,12 +23,12 @@
 #define ROWP(i) (cost + (size_t)(row_map ? row_map[(i)] : (i)) * (size_t)ld)
 
 /* stats[0]=phases, [1]=rounds, [2]=bids (row scans), [3]=full-matrix passes,
- * [4]=rounds with <=148 bidders, [5]=bids in those rounds.
+ * [4]=rounds with <=148 bidders, [5]=bids made in the Gauss-Seidel tail.
  * round_log (may be NULL, capacity round_cap): bidders per round. */
 int auction_model_i32(int n, const int32_t *cost, int64_t ld, const int32_t *row_map,
                       int32_t *rowsol, int32_t *colsol, int64_t *price,
                       int64_t *total, int64_t theta, int64_t eps0_div, int keep_cs, int64_t stop_free,
-                      int64_t *stats, int32_t *round_log, int64_t round_cap)
+                      int64_t *stats, int32_t *round_log, int64_t round_cap, int64_t tail_t)
 {
     if (n <= 0) { if (total) *total = 0; return n == 0 ? 0 : -1; }
     const int64_t S = (int64_t)n + 1;
@@ -71,9 +71,32 @@ int auction_model_i32(int n, const int32_t *cost, int64_t ld, const int32_t *row
             }
         }
         while (nfree > (eps == 1 ? 0 : stop_free)) {
+            if (nfree <= tail_t) {
+                /* Gauss-Seidel tail (what CTA 0 runs alone on the device): FIFO of free rows, every
+                 * bid sees the prices left by the previous one; the lone bidder always wins. */
+                int head = 0, tailp = nfree;                 /* circular queue in freel[0..n) */
+                int cnt = nfree;
+                while (cnt > 0) {
+                    int i = freel[head]; head = (head + 1) % n; --cnt;
+                    const int32_t *r = ROWP(i);
+                    int64_t b1 = INT64_MAX, b2 = INT64_MAX; int j1 = -1;
+                    for (int j = 0; j < n; ++j) {
+                        int64_t h = (int64_t)r[j] * S + price[j];
+                        if (h < b1) { b2 = b1; b1 = h; j1 = j; }
+                        else if (h < b2) b2 = h;
+                    }
+                    price[j1] += (n > 1 ? b2 - b1 : 0) + eps;
+                    int old = colsol[j1];
+                    colsol[j1] = i; rowsol[i] = j1;
+                    if (old >= 0) { rowsol[old] = -1; freel[tailp % n] = old; tailp = (tailp + 1) % n; ++cnt; }
+                    ++st[2]; ++st[5];
+                }
+                nfree = 0;
+                break;
+            }
             if (round_log && st[1] < round_cap) round_log[st[1]] = nfree;
             ++st[1]; st[2] += nfree;
-            if (nfree <= 148) { ++st[4]; st[5] += nfree; }
+            if (nfree <= 148) ++st[4];
             int ntouched = 0;
             for (int k = 0; k < nfree; ++k) {
                 int i = freel[k];
