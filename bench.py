@@ -269,8 +269,9 @@ def run_b200(args, wl):
         value = world * n_cells / (ms_per_step / 1e3)
         e2e_value = world * n_cells / (e2e_ms / args.steps / 1e3)
         n = n_cells
+        n_obj = int(res.price.numel())               # a scan reads one bidder's row: n_obj int32
         scans = res.row_scans + n                    # bids + phase-start re-checks + the min/max pass
-        lap_bytes = scans * n * 4
+        lap_bytes = scans * n_obj * 4
         ach = lap_bytes / (lap_ms / 1e3) / 1e9
         kop = n_genes if args.precision == "f16" else 3 * n_genes
         gemm_flop_alg = 2.0 * n_spots * n_cells * n_genes
@@ -286,7 +287,7 @@ def run_b200(args, wl):
                        "per_rank": "each rank solves its own independent sub-problem" if world > 1 else "single GPU"},
             "roofline": {"kernel": "lap_auction_kernel", "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s",
                          "frac": ach / hbm, "traffic": None, "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)",
-                         "row_scans": scans, "bytes_per_scan": n * 4, "kernel_ms": lap_ms},
+                         "row_scans": scans, "bytes_per_scan": n_obj * 4, "kernel_ms": lap_ms},
             "roofline_cost_build": {"bound": "tensor", "algorithmic_flop": gemm_flop_alg, "ms": cost_ms,
                                     "achieved": gemm_flop_alg / (cost_ms / 1e3) / 1e12, "peak": tf_burst,
                                     "unit": "TFLOP/s", "frac": gemm_flop_alg / (cost_ms / 1e3) / 1e12 / tf_burst,
@@ -302,7 +303,8 @@ def run_b200(args, wl):
         }
         if world == 1 and not args.no_cpu_baseline:
             row_map = None if cps == 1 else np.repeat(np.arange(n_spots, dtype=np.int32), cn)
-            cost_np = cost[:, :n_cells].cpu().numpy()
+            # the oracle takes the reference's orientation (spots x cells)
+            cost_np = np.ascontiguousarray((cost[:, :n_cells] if cps == 1 else cost[:, :n_spots].T).cpu().numpy())
             line["cpu_baseline"] = cpu_baseline(cost_np, row_map, sc_host, st_host, wl, res.total)
         print(json.dumps(line), flush=True)
     if world > 1:

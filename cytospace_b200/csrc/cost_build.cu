@@ -526,6 +526,7 @@ extern "C" int cyb_standardise(const void *x_dev, int x_dtype, int64_t n_genes, 
 
 extern "C" int cyb_cost_gemm_i32(const void *zst_dev, const void *zsc_dev, int64_t n_spots, int64_t n_cells,
                                  int64_t k, float scale, int32_t *cost_dev, int64_t ld_cost, void *stream_v) {
+    // (local names: "spots" = rows of the output / operand A, "cells" = columns / operand B)
     cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
     if (!zst_dev || !zsc_dev || !cost_dev)
         return cyb::set_error(CYB_ERR_INVALID, "cyb_cost_gemm_i32: null pointer argument");
@@ -555,33 +556,33 @@ extern "C" int cyb_cost_gemm_i32(const void *zst_dev, const void *zsc_dev, int64
 }
 
 namespace {
-struct BuildLayout { size_t zst, zsc, std_ws, total; };
-BuildLayout build_layout(int64_t n_genes, int64_t n_cells, int64_t n_spots, int precision) {
+struct BuildLayout { size_t za, zb, std_ws, total; };
+BuildLayout build_layout(int64_t n_genes, int64_t n_a, int64_t n_b, int precision) {
     BuildLayout L; size_t o = 0;
     auto take = [&](size_t b) { size_t r = o; o = cyb::align_up(o + b, 1024); return r; };
     const size_t kop = (size_t)cyb_operand_k(n_genes, precision);
-    L.zst = take((size_t)n_spots * kop * 2);
-    L.zsc = take((size_t)n_cells * kop * 2);
-    L.std_ws = take(std_layout(std::max(n_cells, n_spots)).total);
+    L.za = take((size_t)n_a * kop * 2);
+    L.zb = take((size_t)n_b * kop * 2);
+    L.std_ws = take(std_layout(std::max(n_a, n_b)).total);
     L.total = o;
     return L;
 }
 }  // namespace
 
-extern "C" size_t cyb_cost_build_workspace_bytes(int64_t n_genes, int64_t n_cells, int64_t n_spots, int precision) {
-    if (n_genes <= 0 || n_cells <= 0 || n_spots <= 0) return 1024;
-    return build_layout(n_genes, n_cells, n_spots, precision).total;
+extern "C" size_t cyb_cost_build_workspace_bytes(int64_t n_genes, int64_t n_a, int64_t n_b, int precision) {
+    if (n_genes <= 0 || n_a <= 0 || n_b <= 0) return 1024;
+    return build_layout(n_genes, n_a, n_b, precision).total;
 }
 
-extern "C" int cyb_cost_build_pearson(const void *sc_dev, const void *st_dev, int x_dtype, int64_t n_genes,
-                                      int64_t n_cells, int64_t n_spots, int64_t ld_sc, int64_t ld_st, int log_tpm_flag,
+extern "C" int cyb_cost_build_pearson(const void *a_dev, const void *b_dev, int x_dtype, int64_t n_genes,
+                                      int64_t n_a, int64_t n_b, int64_t ld_a, int64_t ld_b, int log_tpm_flag,
                                       int precision, double cost_scale, int32_t *cost_dev, int64_t ld_cost,
-                                      double *colstat_sc_dev, double *colstat_st_dev, int32_t *zero_var_dev,
+                                      double *colstat_a_dev, double *colstat_b_dev, int32_t *zero_var_dev,
                                       void *workspace_dev, size_t workspace_bytes, void *stream) {
     if (!workspace_dev) return cyb::set_error(CYB_ERR_INVALID, "cyb_cost_build_pearson: null workspace");
-    if (n_genes <= 0 || n_cells <= 0 || n_spots <= 0)
+    if (n_genes <= 0 || n_a <= 0 || n_b <= 0)
         return cyb::set_error(CYB_ERR_INVALID, "cyb_cost_build_pearson: empty problem");
-    const BuildLayout L = build_layout(n_genes, n_cells, n_spots, precision);
+    const BuildLayout L = build_layout(n_genes, n_a, n_b, precision);
     if (workspace_bytes < L.total)
         return cyb::set_error(CYB_ERR_WORKSPACE, "cyb_cost_build_pearson: workspace %zu < required %zu",
                               workspace_bytes, L.total);
@@ -589,11 +590,12 @@ extern "C" int cyb_cost_build_pearson(const void *sc_dev, const void *st_dev, in
         return cyb::set_error(CYB_ERR_INVALID, "cyb_cost_build_pearson: workspace must be 1024-byte aligned");
     char *ws = static_cast<char *>(workspace_dev);
     const size_t std_bytes = L.total - L.std_ws;
-    if (int rc = cyb_standardise(st_dev, x_dtype, n_genes, n_spots, ld_st, log_tpm_flag, precision, 0, ws + L.zst,
-                                 colstat_st_dev, zero_var_dev, ws + L.std_ws, std_bytes, stream)) return rc;
-    if (int rc = cyb_standardise(sc_dev, x_dtype, n_genes, n_cells, ld_sc, log_tpm_flag, precision, 1, ws + L.zsc,
-                                 colstat_sc_dev, zero_var_dev, ws + L.std_ws, std_bytes, stream)) return rc;
-    return cyb_cost_gemm_i32(ws + L.zst, ws + L.zsc, n_spots, n_cells, cyb_operand_k(n_genes, precision),
+    // matrix a supplies the rows of the output (GEMM operand A), matrix b the columns (operand B)
+    if (int rc = cyb_standardise(a_dev, x_dtype, n_genes, n_a, ld_a, log_tpm_flag, precision, 0, ws + L.za,
+                                 colstat_a_dev, zero_var_dev, ws + L.std_ws, std_bytes, stream)) return rc;
+    if (int rc = cyb_standardise(b_dev, x_dtype, n_genes, n_b, ld_b, log_tpm_flag, precision, 1, ws + L.zb,
+                                 colstat_b_dev, zero_var_dev, ws + L.std_ws, std_bytes, stream)) return rc;
+    return cyb_cost_gemm_i32(ws + L.za, ws + L.zb, n_a, n_b, cyb_operand_k(n_genes, precision),
                              (float)(cost_scale / (double)n_genes), cost_dev, ld_cost, stream);
 }
 

@@ -1,43 +1,54 @@
-// Exact dense linear assignment on sm_100a: synchronous (Jacobi) eps-scaling
-// auction in ONE persistent cooperative kernel, one CTA per SM.
+// Exact dense linear assignment (transportation form) on sm_100a: synchronous
+// (Jacobi) eps-scaling auction with capacitated objects in ONE persistent
+// cooperative kernel, one CTA per SM.
 //
 // Replaces the third-party `lapjv.lapjv(cost)` call CytoSPACE makes at
 // cytospace/linear_assignment_solvers/linear_assignment_solvers.py:38 (from
-// cytospace/cytospace.py:329).  Rows = spot slots, columns = cells; the
-// `cost[location_repeat, :]` expansion of linear_assignment_solvers.py:63-66 is
-// never materialised -- LAP row i reads compact row row_map[i].
+// cytospace/cytospace.py:329) on the expanded matrix `cost[location_repeat, :]`
+// (linear_assignment_solvers.py:63-66).  The expansion is never materialised:
+// PERSONS are the cells (rows of M = cost^T, cells x spots), OBJECTS are the
+// spots, object o has cap[o] = cell_number_to_node_assignment[o] SLOTS.
+//     min sum_i M[i, obj(i)]   s.t.  object o holds exactly cap[o] persons
+// is the same optimisation problem as the reference's square LAP (identical
+// optimal total); duplicated spot rows become capacity instead of price wars.
 //
-// Algorithm (min-cost form).  C = (cost - cmin) * (n+1) >= 0, prices p >= 0,
-// h(i,j) = C[i,j] + p[j].  A free row i bids for j1 = argmin_j h (lowest j on
-// ties) at price p[j1] + (second-min h - min h) + eps; per column the highest
-// bid wins (lowest row on ties), the previous owner becomes free.  eps is
-// divided by 8 per phase down to 1; because costs carry the factor n+1, the
-// eps = 1 phase ends with an assignment whose total is < n+1 scaled units from
-// optimal, i.e. optimal for the integer matrix.  At each phase start the pairs
-// that already satisfy eps-CS for the new eps are kept.
+// Algorithm.  C = (M - cmin) * (P+1) >= 0.  Every slot has a price (its last
+// accepted bid) and a holder; the object's price lambda[o] is its cheapest
+// slot.  A free person i scans its row: v1 = min_o (C[i,o] + lambda[o]) at o*
+// (lowest o on ties), w = the minimum over o != o*; it bids
+// b = lambda[o*] + (w - v1) + eps for the cheapest slot of o*.  Per object the
+// highest bid of a round wins (lowest person on ties) and evicts the slot's
+// holder.  Invariant (eps-CS): an assigned person's C[i,o] + (own slot price) is
+// within eps of its best alternative object, and lambda[o] <= own slot price.
+// eps is divided by 8 per phase down to 1; at a phase start a pair is kept iff
+// C[i,o] + lambda[o] <= alt + eps, and its slot price is clamped down to
+// alt + eps - C[i,o] (never below lambda[o], so object prices never decrease).
+// With the factor P+1 on the costs, eps = 1 leaves the total < P+1 scaled units
+// from optimal, i.e. optimal for the integer matrix (DESIGN.md has the proof).
 //
-// Execution model.  Every round costs exactly one grid barrier:
+// Execution model.  Every bidding round costs exactly one grid barrier:
 //   [bid r]      CTA b scans the rows at positions k = b (mod G) of the free
 //                list: one coalesced pass over the row in HBM against the
-//                price vector held in shared memory (or L2 when n is too big),
+//                object prices held in shared memory (L2 when O is too big),
 //                warp-shuffle + shared-memory reduction of (min, 2nd min,
-//                argmin), then one 64-bit atomicMax of (bid | ~row) on the
-//                column's bid slot and a record (column, previous owner).
+//                argmin), one 64-bit atomicMax of (bid | ~person) on the
+//                object's bid word and a record (object, slot, slot holder).
 //   barrier
-//   [resolve r]  EVERY CTA replays all F records (they are tiny and L2
-//                resident): winners update the CTA's private shared-memory
-//                price replica, the column owner (identical values written by
-//                all CTAs, so each CTA's own view is complete without a second
-//                barrier) and the next free list (a block-wide prefix sum gives
-//                every CTA the same positions; CTA b keeps positions = b mod G
-//                as its next work queue).
-// Buffers touched by atomics / records / lists alternate by round parity, so a
-// fast CTA bidding in round r+1 never disturbs a slow CTA resolving round r.
-// Bid slots are never reset: a stale slot value is <= the column's current
-// price and every new bid is strictly greater.
+//   [resolve r]  EVERY CTA replays all F records (tiny, L2 resident): winners
+//                update the slot, the object's cheapest slot / price (also in
+//                the CTA's shared-memory replica) and the next free list (a
+//                block-wide prefix sum gives every CTA the same positions;
+//                CTA b keeps positions = b mod G as its next work queue).  All
+//                CTAs write identical values, so each CTA's own view of the
+//                state is complete without a second barrier.
+// Lists, records and bid words rotate over three buffers by round: a fast CTA
+// bidding in round r+1 never disturbs a slow CTA resolving round r, and the bid
+// words of round r-1 are cleared during resolve r (their next use is round r+2).
+// When <= tail_t bidders are left, CTA 0 alone drains them as a Gauss-Seidel
+// FIFO (no barrier per bid); the other CTAs pick up the prices at the phase end.
 //
-// HBM traffic: each bid reads one row (n*4 bytes) once; prices, owners, lists
-// and slots live in shared memory / L2.
+// HBM traffic: each bid reads one row (O*4 bytes) once; prices, holders, lists
+// and bid words live in shared memory / L2.
 
 #include <climits>
 #include <cstdint>
@@ -48,33 +59,36 @@
 namespace {
 
 constexpr int kThreads = 1024;
-constexpr int kRowBits = 18;                                   // n < 2^18
-constexpr unsigned long long kRowMask = (1ull << kRowBits) - 1;
-constexpr long long kInf = 0x3FFFFFFFFFFFFFFFll;
+constexpr int kPersonBits = 18;                                // P < 2^18
+constexpr unsigned long long kPersonMask = (1ull << kPersonBits) - 1;
+constexpr long long kInf = 1ll << 60;                          // price of an object without capacity
 constexpr long long kBidLimit = 1ll << 45;                     // 46-bit bid field
 constexpr int kTheta = 8;
 constexpr int kEps0Div = 4;
 constexpr int kTailMax = 64;                                   // capacity of the tail FIFO
 
 struct LapParams {
-    const int32_t *cost;
+    const int32_t *cost;     // M: persons x objects
     long long ld;
-    int n;
-    const int32_t *row_map;
-    int32_t *rowsol;
-    int32_t *owner;          // == colsol output
-    long long *price;
+    int P, O;
+    const int32_t *soff;     // slot offsets [O+1] (nullptr: every capacity is 1)
+    int32_t *person_obj;     // out: object of person i
+    int32_t *slot_owner;     // out: person holding slot t (slots ordered by object)
+    long long *lambda;       // out: object prices (scaled by P+1)
     long long *total;
     long long *stats;
-    int32_t *list[2];
-    int2 *rec[2];
-    unsigned long long *slot[2];
+    long long *slot_price;
+    int32_t *person_slot;
+    int32_t *minslot;
+    int32_t *list[3];
+    int4 *rec[3];            // (object, slot, holder of that slot, -)
+    unsigned long long *bidw[3];
     int32_t *flag;
     unsigned int *bar;
     int *gmm;                // [0] cmin, [1] cmax, [2] status
     int qcap;
     long long max_rounds;
-    int tail_t;              // rounds with <= tail_t bidders are finished by CTA 0 alone (Gauss-Seidel tail)
+    int tail_t;              // rounds with <= tail_t bidders are finished by CTA 0 alone
 };
 
 struct Best {
@@ -140,13 +154,13 @@ __device__ __forceinline__ int block_excl_count(bool valid, int *wcnt, int &tota
     return woff + within;
 }
 
-// CTA-wide scan of one LAP row: min / second-min / argmin of (c-cmin)*S + p.
+// CTA-wide scan of one person's row: min / second-min / argmin of (c-cmin)*S + lambda.
 // The result is valid in thread 0.
 template <bool SMEMP>
 __device__ __forceinline__ Best scan_row(const int32_t *__restrict__ r, int n, int cmin, long long S,
                                          const long long *__restrict__ price, bool vec_ok,
                                          long long *red_b1, long long *red_b2, int *red_j) {
-    Best s{kInf, kInf, -1};
+    Best s{LLONG_MAX, LLONG_MAX, -1};
     const int t = threadIdx.x;
     int jtail = 0;
     if (vec_ok) {
@@ -177,9 +191,8 @@ __device__ __forceinline__ Best scan_row(const int32_t *__restrict__ r, int n, i
         const long long p = SMEMP ? price[j] : __ldcg(price + j);
         upd(s, (long long)(__ldg(r + j) - cmin) * S + p, j);
     }
-    // NOTE: in the vectorised loop a thread's columns are not globally
-    // increasing against the tail loop, but tail columns are all larger than
-    // vector columns, and `upd` keeps the earlier (lower) column on ties.
+    // A thread's columns increase over its iterations and tail columns are larger than vector
+    // columns; `upd` keeps the earlier (lower) column on ties, `combine` the lower index.
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
         Best o;
@@ -206,34 +219,44 @@ __device__ __forceinline__ Best scan_row(const int32_t *__restrict__ r, int n, i
     return s;
 }
 
+// Cheapest slot of object o (lowest slot index on ties) when slot `t_new` holds `p_new` and
+// every other slot its stored price.
+__device__ __forceinline__ void cheapest_slot(const LapParams &P, int o, int t_new, long long p_new,
+                                              int &ms, long long &mp) {
+    const int s0 = P.soff ? __ldg(P.soff + o) : o, s1 = P.soff ? __ldg(P.soff + o + 1) : o + 1;
+    ms = s0; mp = (s0 == t_new) ? p_new : __ldcg(P.slot_price + s0);
+    for (int t = s0 + 1; t < s1; ++t) {
+        const long long p = (t == t_new) ? p_new : __ldcg(P.slot_price + t);
+        if (p < mp) { mp = p; ms = t; }
+    }
+}
+
 template <bool SMEMP>
 __global__ void __launch_bounds__(kThreads, 1) lap_auction_kernel(const LapParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int n = P.n;
+    const int np = P.P, no = P.O;
     long long *sprice = reinterpret_cast<long long *>(smem_raw);
-    size_t off = SMEMP ? ((size_t)n * 8 + 15) / 16 * 16 : 0;
+    size_t off = SMEMP ? ((size_t)no * 8 + 15) / 16 * 16 : 0;
     int *myq = reinterpret_cast<int *>(smem_raw + off);
     __shared__ long long red_b1[32], red_b2[32];
     __shared__ int red_j[32], wcnt[32];
     __shared__ int tq[kTailMax], tq_head, tq_cnt, tq_status;
 
     const int G = gridDim.x, b = blockIdx.x, t = threadIdx.x;
-    const long long S = (long long)n + 1;
+    const long long S = (long long)np + 1;
     const bool vec_ok = ((P.ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(P.cost) & 15) == 0);
     unsigned int bar_target = 0;
-    const long long *price_rd = SMEMP ? sprice : P.price;
+    const long long *price_rd = SMEMP ? sprice : P.lambda;
 
-    auto rowptr = [&](int i) -> const int32_t * {
-        const long long r = P.row_map ? (long long)__ldg(P.row_map + i) : (long long)i;
-        return P.cost + r * P.ld;
-    };
+    auto rowptr = [&](int i) -> const int32_t * { return P.cost + (long long)i * P.ld; };
+    auto capacity = [&](int o) -> int { return P.soff ? __ldg(P.soff + o + 1) - __ldg(P.soff + o) : 1; };
 
     // ---- pass 0: state init and the cost range ------------------------------
     {
         int lmin = INT_MAX, lmax = INT_MIN;
-        for (int i = b; i < n; i += G) {
+        for (int i = b; i < np; i += G) {
             const int32_t *r = rowptr(i);
-            for (int j = t; j < n; j += kThreads) {
+            for (int j = t; j < no; j += kThreads) {
                 const int c = __ldg(r + j);
                 lmin = min(lmin, c); lmax = max(lmax, c);
             }
@@ -244,11 +267,15 @@ __global__ void __launch_bounds__(kThreads, 1) lap_auction_kernel(const LapParam
             lmax = max(lmax, __shfl_xor_sync(0xffffffffu, lmax, d));
         }
         if ((t & 31) == 0 && lmin <= lmax) { atomicMin(P.gmm + 0, lmin); atomicMax(P.gmm + 1, lmax); }
-        for (int j = b * kThreads + t; j < n; j += G * kThreads) {
-            P.price[j] = 0; P.owner[j] = -1; P.rowsol[j] = -1;
-            P.slot[0][j] = 0ull; P.slot[1][j] = 0ull;
+        for (int i = b * kThreads + t; i < np; i += G * kThreads) {
+            P.slot_price[i] = 0; P.slot_owner[i] = -1; P.person_obj[i] = -1; P.person_slot[i] = -1;
         }
-        if (SMEMP) for (int j = t; j < n; j += kThreads) sprice[j] = 0;
+        for (int o = b * kThreads + t; o < no; o += G * kThreads) {
+            P.lambda[o] = capacity(o) > 0 ? 0 : kInf;          // a spot that takes no cell is priced out
+            P.minslot[o] = P.soff ? __ldg(P.soff + o) : o;
+            P.bidw[0][o] = 0ull; P.bidw[1][o] = 0ull; P.bidw[2][o] = 0ull;
+        }
+        if (SMEMP) for (int o = t; o < no; o += kThreads) sprice[o] = capacity(o) > 0 ? 0 : kInf;
     }
     grid_barrier(P.bar, bar_target, G);
     const int cmin = __ldcg(P.gmm + 0), cmax = __ldcg(P.gmm + 1);
@@ -256,40 +283,61 @@ __global__ void __launch_bounds__(kThreads, 1) lap_auction_kernel(const LapParam
     if (eps < 1) eps = 1;
 
     long long rounds = 0, bids = 0, passes = 0, phases = 0, rounds1 = 0, maxF = 0, tail_bids = 0, tails = 0;
-    int status = 0, par = 0;
+    int status = 0;
+    int cur = 0;             // buffer of the current round; the previous round used (cur + 2) % 3
+    int prevF = 0;           // records of the previous round (their bid words are cleared in this resolve)
     const int tail_t = min(P.tail_t, kTailMax);
 
     for (;;) {
         ++phases;
         // ---- phase start: which pairs survive eps-CS at the new eps? --------
-        for (int i = b; i < n; i += G) {
-            const int j0 = __ldcg(P.rowsol + i);
-            int f = 1;
-            if (j0 >= 0) {
-                const int32_t *r = rowptr(i);
-                const Best s = scan_row<SMEMP>(r, n, cmin, S, price_rd, vec_ok, red_b1, red_b2, red_j);
-                if (t == 0) {
-                    const long long pj = SMEMP ? sprice[j0] : __ldcg(P.price + j0);
-                    const long long h0 = (long long)(__ldg(r + j0) - cmin) * S + pj;
-                    f = (h0 > s.b1 + eps) ? j0 + 2 : 0;
+        if (phases > 1) {
+            for (int i = b; i < np; i += G) {
+                const int o = __ldcg(P.person_obj + i);
+                int f = 1;
+                if (o >= 0) {
+                    const int32_t *r = rowptr(i);
+                    const Best s = scan_row<SMEMP>(r, no, cmin, S, price_rd, vec_ok, red_b1, red_b2, red_j);
+                    if (t == 0) {
+                        const long long alt = (s.j1 == o) ? s.b2 : s.b1;
+                        const long long base = (long long)(__ldg(r + o) - cmin) * S;
+                        const long long lam = SMEMP ? sprice[o] : __ldcg(P.lambda + o);
+                        const int ps = __ldcg(P.person_slot + i);
+                        f = 0;
+                        if (alt < kInf / 2) {
+                            if (base + lam > alt + eps) f = ps + 2;                       // drop: vacate slot ps
+                            else if (base + __ldcg(P.slot_price + ps) > alt + eps)
+                                P.slot_price[ps] = alt + eps - base;                      // clamp (>= lambda[o])
+                        }
+                    }
                 }
+                if (t == 0) P.flag[i] = f;
             }
-            if (t == 0) P.flag[i] = f;
+            ++passes;
+            grid_barrier(P.bar, bar_target, G);
         }
-        ++passes;
-        grid_barrier(P.bar, bar_target, G);
         int F = 0;
-        for (int i0 = 0; i0 < n; i0 += kThreads) {
+        for (int i0 = 0; i0 < np; i0 += kThreads) {
             const int i = i0 + t;
-            const int f = i < n ? __ldcg(P.flag + i) : 0;
+            const int f = (i < np) ? (phases == 1 ? 1 : __ldcg(P.flag + i)) : 0;
             if (f >= 2) {
-                P.owner[f - 2] = -1;                       // identical write from every CTA
-                if (i % G == b) P.rowsol[i] = -1;
+                P.slot_owner[f - 2] = -1;                    // identical write from every CTA; price stays
+                if (i % G == b) { P.person_obj[i] = -1; P.person_slot[i] = -1; }
             }
             int tot;
             const int pos = F + block_excl_count(f != 0, wcnt, tot);
-            if (f != 0 && pos % G == b) { P.list[par][pos] = i; myq[pos / G] = i; }
+            if (f != 0 && pos % G == b) { P.list[cur][pos] = i; myq[pos / G] = i; }
             F += tot;
+        }
+        if (phases > 1 && P.soff) {
+            // clamps may have created an equally cheap slot with a lower index: refresh the argmin
+            for (int o = t; o < no; o += kThreads) {
+                if (capacity(o) > 1) {
+                    int ms; long long mp;
+                    cheapest_slot(P, o, -1, 0, ms, mp);
+                    P.minslot[o] = ms;                       // identical write from every CTA
+                }
+            }
         }
         __syncthreads();
 
@@ -298,32 +346,37 @@ __global__ void __launch_bounds__(kThreads, 1) lap_auction_kernel(const LapParam
         while (F > 0) {
             if (F <= tail_t) {
                 // ---- Gauss-Seidel tail: few bidders left, a grid barrier per round would cost more
-                // than the bids.  CTA 0 alone drains a FIFO of free rows; every bid sees the prices
-                // the previous one left and the lone bidder always wins, so nothing is exchanged
-                // until the phase ends.  (Same auction, sequential order: still eps-CS, still exact.)
+                // than the bids.  CTA 0 alone drains a FIFO of free persons; every bid sees the
+                // prices the previous one left and the lone bidder always wins, so nothing is
+                // exchanged until the phase ends.  (Same auction, sequential order: still exact.)
                 grid_barrier(P.bar, bar_target, G);          // every CTA has finished its resolve writes
                 ran_tail = true; ++tails;
                 if (b == 0) {
-                    if (t < F) tq[t] = __ldcg(P.list[par] + t);
+                    if (t < F) tq[t] = __ldcg(P.list[cur] + t);
                     if (t == 0) { tq_head = 0; tq_cnt = F; tq_status = 0; }
                     __syncthreads();
                     while (tq_cnt > 0 && tq_status == 0) {
                         const int i = tq[tq_head];
-                        const int32_t *r = rowptr(i);
-                        const Best s = scan_row<SMEMP>(r, n, cmin, S, price_rd, vec_ok, red_b1, red_b2, red_j);
+                        const Best s = scan_row<SMEMP>(rowptr(i), no, cmin, S, price_rd, vec_ok, red_b1, red_b2, red_j);
                         ++tail_bids;
                         if (t == 0) {
-                            const long long pj = SMEMP ? sprice[s.j1] : __ldcg(P.price + s.j1);
-                            const long long bid = pj + (n > 1 ? s.b2 - s.b1 : 0) + eps;
+                            const int o = s.j1;
+                            const long long lam = SMEMP ? sprice[o] : __ldcg(P.lambda + o);
+                            const long long bid = lam + (s.b2 < kInf / 2 ? s.b2 - s.b1 : 0) + eps;
                             if (bid >= kBidLimit) tq_status = CYB_ERR_OVERFLOW;
                             if (tail_bids + rounds > P.max_rounds) tq_status = CYB_ERR_NOT_CONVERGED;
-                            const int prev = __ldcg(P.owner + s.j1);
-                            P.owner[s.j1] = i; P.rowsol[i] = s.j1; P.price[s.j1] = bid;
-                            if (SMEMP) sprice[s.j1] = bid;
+                            const int slot = __ldcg(P.minslot + o);
+                            const int prev = __ldcg(P.slot_owner + slot);
+                            P.slot_owner[slot] = i; P.slot_price[slot] = bid;
+                            P.person_obj[i] = o; P.person_slot[i] = slot;
+                            int ms; long long mp;
+                            cheapest_slot(P, o, slot, bid, ms, mp);
+                            P.minslot[o] = ms; P.lambda[o] = mp;
+                            if (SMEMP) sprice[o] = mp;
                             int head = tq_head + 1; if (head == kTailMax) head = 0;
                             int cnt = tq_cnt - 1;
                             if (prev >= 0) {
-                                P.rowsol[prev] = -1;
+                                P.person_obj[prev] = -1; P.person_slot[prev] = -1;
                                 int tail = head + cnt; if (tail >= kTailMax) tail -= kTailMax;
                                 tq[tail] = prev; ++cnt;
                             }
@@ -343,59 +396,78 @@ __global__ void __launch_bounds__(kThreads, 1) lap_auction_kernel(const LapParam
             const int myn = F > b ? (F - b - 1) / G + 1 : 0;
             for (int q = 0; q < myn; ++q) {
                 const int i = myq[q];
-                const Best s = scan_row<SMEMP>(rowptr(i), n, cmin, S, price_rd, vec_ok, red_b1, red_b2, red_j);
+                const Best s = scan_row<SMEMP>(rowptr(i), no, cmin, S, price_rd, vec_ok, red_b1, red_b2, red_j);
                 if (t == 0) {
-                    const long long gamma = (n > 1 ? s.b2 - s.b1 : 0) + eps;
-                    const long long pj = SMEMP ? sprice[s.j1] : __ldcg(P.price + s.j1);
-                    const long long bid = pj + gamma;
+                    const int o = s.j1;
+                    const long long lam = SMEMP ? sprice[o] : __ldcg(P.lambda + o);
+                    const long long bid = lam + (s.b2 < kInf / 2 ? s.b2 - s.b1 : 0) + eps;
                     if (bid >= kBidLimit) atomicExch(P.gmm + 2, CYB_ERR_OVERFLOW);
-                    const int prev = __ldcg(P.owner + s.j1);
-                    P.rec[par][q * G + b] = make_int2(s.j1, prev);
-                    atomicMax(P.slot[par] + s.j1,
-                              ((unsigned long long)bid << kRowBits) | (kRowMask - (unsigned long long)i));
+                    const int slot = __ldcg(P.minslot + o);
+                    const int prev = __ldcg(P.slot_owner + slot);
+                    P.rec[cur][q * G + b] = make_int4(o, slot, prev, 0);
+                    atomicMax(P.bidw[cur] + o,
+                              ((unsigned long long)bid << kPersonBits) | (kPersonMask - (unsigned long long)i));
                 }
             }
             grid_barrier(P.bar, bar_target, G);
             status = __ldcg(P.gmm + 2);
             if (status) break;
             // ---- resolve: every CTA replays every record ----------------------
+            const int nxt = cur == 2 ? 0 : cur + 1, prv = cur == 0 ? 2 : cur - 1;
+            // clear the bid words of the previous round (their next use is two rounds ahead)
+            for (int k = b * kThreads + t; k < prevF; k += G * kThreads)
+                P.bidw[prv][__ldcg(&P.rec[prv][k].x)] = 0ull;
             int Fn = 0;
             for (int k0 = 0; k0 < F; k0 += kThreads) {
                 const int k = k0 + t;
                 int entry = -1;
                 if (k < F) {
-                    const int i = __ldcg(P.list[par] + k);
-                    const int2 rc = __ldcg(P.rec[par] + k);
-                    const unsigned long long key = __ldcg(P.slot[par] + rc.x);
-                    const int wrow = (int)(kRowMask - (key & kRowMask));
-                    if (wrow == i) {
-                        const long long bid = (long long)(key >> kRowBits);
+                    const int i = __ldcg(P.list[cur] + k);
+                    const int4 rc = __ldcg(P.rec[cur] + k);
+                    const unsigned long long key = __ldcg(P.bidw[cur] + rc.x);
+                    const int wperson = (int)(kPersonMask - (key & kPersonMask));
+                    if (wperson == i) {
+                        const long long bid = (long long)(key >> kPersonBits);
                         const bool mine = (k % G == b);
-                        if (SMEMP) { sprice[rc.x] = bid; if (mine) P.price[rc.x] = bid; }
-                        else P.price[rc.x] = bid;              // identical write from every CTA
-                        P.owner[rc.x] = i;                     // identical write from every CTA
-                        if (mine) { P.rowsol[i] = rc.x; if (rc.y >= 0) P.rowsol[rc.y] = -1; }
-                        entry = rc.y;
+                        P.slot_owner[rc.y] = i; P.slot_price[rc.y] = bid;     // identical writes from every CTA
+                        int ms; long long mp;
+                        cheapest_slot(P, rc.x, rc.y, bid, ms, mp);
+                        P.minslot[rc.x] = ms;
+                        if (SMEMP) { sprice[rc.x] = mp; if (mine) P.lambda[rc.x] = mp; }
+                        else P.lambda[rc.x] = mp;
+                        if (mine) {
+                            P.person_obj[i] = rc.x; P.person_slot[i] = rc.y;
+                            if (rc.z >= 0) { P.person_obj[rc.z] = -1; P.person_slot[rc.z] = -1; }
+                        }
+                        entry = rc.z;
                     } else {
                         entry = i;
                     }
                 }
                 int tot;
                 const int pos = Fn + block_excl_count(entry >= 0, wcnt, tot);
-                if (entry >= 0 && pos % G == b) { P.list[par ^ 1][pos] = entry; myq[pos / G] = entry; }
+                if (entry >= 0 && pos % G == b) { P.list[nxt][pos] = entry; myq[pos / G] = entry; }
                 Fn += tot;
             }
+            prevF = F;
             F = Fn;
-            par ^= 1;
+            cur = nxt;
             __syncthreads();
         }
         if (status) break;
-        grid_barrier(P.bar, bar_target, G);        // rowsol of the last resolve / the tail becomes visible
+        grid_barrier(P.bar, bar_target, G);        // state of the last resolve / the tail becomes visible
+        {
+            // the bid words of the last round back to zero before the next phase
+            const int prv = cur == 0 ? 2 : cur - 1;
+            for (int k = b * kThreads + t; k < prevF; k += G * kThreads)
+                P.bidw[prv][__ldcg(&P.rec[prv][k].x)] = 0ull;
+            prevF = 0;
+        }
         if (ran_tail) {
             status = __ldcg(P.gmm + 2);
             if (status) break;
             if (SMEMP) {                            // pick up the prices CTA 0 moved during the tail
-                for (int j = t; j < n; j += kThreads) sprice[j] = __ldcg(P.price + j);
+                for (int o = t; o < no; o += kThreads) sprice[o] = __ldcg(P.lambda + o);
                 __syncthreads();
             }
         }
@@ -407,9 +479,9 @@ __global__ void __launch_bounds__(kThreads, 1) lap_auction_kernel(const LapParam
     // ---- total cost of the assignment -------------------------------------------
     if (!status) {
         long long sum = 0;
-        for (int i = b * kThreads + t; i < n; i += G * kThreads) {
-            const int j = __ldcg(P.rowsol + i);
-            if (j >= 0) sum += (long long)__ldg(rowptr(i) + j);
+        for (int i = b * kThreads + t; i < np; i += G * kThreads) {
+            const int o = __ldcg(P.person_obj + i);
+            if (o >= 0) sum += (long long)__ldg(rowptr(i) + o);
         }
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
@@ -419,35 +491,33 @@ __global__ void __launch_bounds__(kThreads, 1) lap_auction_kernel(const LapParam
         P.stats[0] = status; P.stats[1] = phases; P.stats[2] = rounds; P.stats[3] = bids;
         P.stats[4] = passes; P.stats[5] = cmin; P.stats[6] = cmax; P.stats[7] = S;
         P.stats[8] = G; P.stats[9] = SMEMP ? 1 : 0; P.stats[10] = rounds1; P.stats[11] = maxF;
-        P.stats[12] = (phases - 1) * (long long)n; P.stats[13] = tail_bids; P.stats[14] = tails; P.stats[15] = 0;
+        P.stats[12] = (phases - 1) * (long long)np; P.stats[13] = tail_bids; P.stats[14] = tails; P.stats[15] = 0;
     }
 }
 
 // ---------------------------------------------------------------------------------
-// Certificate / row-scan pass.  Grid = (column tiles, row groups); a CTA stages a
-// tile of prices in shared memory once and streams `rows_per_cta` rows against
-// it, one warp per row, so the cost matrix is read exactly once from HBM and the
-// price vector once per row group from L2.
+// Certificate / row-scan pass.  Grid = (object tiles, person groups); a CTA stages a
+// tile of object prices in shared memory once and streams `rows_per_cta` rows
+// against it, one warp per row, so the cost matrix is read exactly once from HBM and
+// the price vector once per person group from L2.
 constexpr int kChkThreads = 512;
 constexpr int kChkTileCols = 4096;
 
 __global__ void __launch_bounds__(kChkThreads) lap_rowmin_kernel(
-    const int32_t *__restrict__ cost, long long ld, int n, const int32_t *__restrict__ row_map,
-    const long long *__restrict__ price, long long S, int rows_per_cta,
-    long long *__restrict__ rowmin) {
+    const int32_t *__restrict__ cost, long long ld, int np, int no,
+    const long long *__restrict__ price, long long S, int rows_per_cta, long long *__restrict__ rowmin) {
     __shared__ __align__(16) long long sp[kChkTileCols];
     const int c0 = blockIdx.x * kChkTileCols;
-    const int nc = min(kChkTileCols, n - c0);
+    const int nc = min(kChkTileCols, no - c0);
     for (int j = threadIdx.x; j < nc; j += kChkThreads) sp[j] = price[c0 + j];
     __syncthreads();
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int r0 = blockIdx.y * rows_per_cta;
-    const int r1 = min(n, r0 + rows_per_cta);
+    const int r1 = min(np, r0 + rows_per_cta);
     const bool vec_ok = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(cost) & 15) == 0);
     for (int i = r0 + w; i < r1; i += kChkThreads / 32) {
-        const long long rr = row_map ? (long long)row_map[i] : (long long)i;
-        const int32_t *r = cost + rr * ld + c0;
-        long long m = kInf;
+        const int32_t *r = cost + (long long)i * ld + c0;
+        long long m = LLONG_MAX;
         int jt = 0;
         if (vec_ok) {
             const int4 *r4 = reinterpret_cast<const int4 *>(r);
@@ -471,20 +541,19 @@ __global__ void __launch_bounds__(kChkThreads) lap_rowmin_kernel(
     }
 }
 
-__global__ void lap_check_finish_kernel(const int32_t *__restrict__ cost, long long ld, int n,
-                                        const int32_t *__restrict__ row_map,
-                                        const int32_t *__restrict__ rowsol,
+__global__ void lap_check_finish_kernel(const int32_t *__restrict__ cost, long long ld, int np, int no,
+                                        const int32_t *__restrict__ person_obj,
                                         const long long *__restrict__ price, long long S,
-                                        const long long *__restrict__ rowmin, long long *out) {
+                                        const long long *__restrict__ rowmin, int32_t *__restrict__ count,
+                                        long long *out) {
     long long viol = LLONG_MIN, tot = 0, bad = 0;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const int j = rowsol[i];
-        if (j < 0 || j >= n) { ++bad; continue; }
-        const long long rr = row_map ? (long long)row_map[i] : (long long)i;
-        const int c = cost[rr * ld + j];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < np; i += gridDim.x * blockDim.x) {
+        const int o = person_obj[i];
+        if (o < 0 || o >= no) { ++bad; continue; }
+        const int c = cost[(long long)i * ld + o];
         tot += c;
-        const long long h = (long long)c * S + price[j];
-        viol = max(viol, h - rowmin[i]);
+        atomicAdd(count + o, 1);
+        viol = max(viol, (long long)c * S + price[o] - rowmin[i]);
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
@@ -499,19 +568,35 @@ __global__ void lap_check_finish_kernel(const int32_t *__restrict__ cost, long l
     }
 }
 
+__global__ void lap_check_capacity_kernel(const int32_t *__restrict__ soff, int no,
+                                          const int32_t *__restrict__ count, long long *out) {
+    long long bad = 0;
+    for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < no; o += gridDim.x * blockDim.x) {
+        const int cap = soff ? soff[o + 1] - soff[o] : 1;
+        if (count[o] != cap) ++bad;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) bad += __shfl_xor_sync(0xffffffffu, bad, d);
+    if ((threadIdx.x & 31) == 0 && bad) atomicAdd(reinterpret_cast<unsigned long long *>(out + 3), (unsigned long long)bad);
+}
+
 struct WsLayout {
-    size_t list0, list1, rec0, rec1, slot0, slot1, flag, rowmin, small, total;
+    size_t list[3], rec[3], bidw[3], flag, slot_price, person_slot, minslot, rowmin, count, small, total;
 };
 
-WsLayout ws_layout(int64_t n) {
+WsLayout ws_layout(int64_t np, int64_t no) {
     WsLayout L;
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t r = o; o = cyb::align_up(o + bytes, 256); return r; };
-    L.list0 = take((size_t)n * 4); L.list1 = take((size_t)n * 4);
-    L.rec0 = take((size_t)n * 8);  L.rec1 = take((size_t)n * 8);
-    L.slot0 = take((size_t)n * 8); L.slot1 = take((size_t)n * 8);
-    L.flag = take((size_t)n * 4);
-    L.rowmin = take((size_t)n * 8);
+    for (int k = 0; k < 3; ++k) L.list[k] = take((size_t)np * 4);
+    for (int k = 0; k < 3; ++k) L.rec[k] = take((size_t)np * 16);
+    for (int k = 0; k < 3; ++k) L.bidw[k] = take((size_t)no * 8);
+    L.flag = take((size_t)np * 4);
+    L.slot_price = take((size_t)np * 8);
+    L.person_slot = take((size_t)np * 4);
+    L.minslot = take((size_t)no * 4);
+    L.rowmin = take((size_t)np * 8);
+    L.count = take((size_t)no * 4);
     L.small = take(256);
     L.total = o;
     return L;
@@ -519,23 +604,29 @@ WsLayout ws_layout(int64_t n) {
 
 }  // namespace
 
-extern "C" size_t cyb_lap_workspace_bytes(int64_t n) {
-    if (n <= 0) return 256;
-    return ws_layout(n).total;
+extern "C" size_t cyb_lap_workspace_bytes(int64_t n_persons, int64_t n_objects) {
+    if (n_persons <= 0 || n_objects <= 0) return 256;
+    return ws_layout(n_persons, n_objects).total;
 }
 
-extern "C" int cyb_lap_solve_i32(const int32_t *cost_dev, int64_t ld, int64_t n,
-                                 const int32_t *row_map_dev, int32_t *rowsol_dev,
-                                 int32_t *colsol_dev, int64_t *price_dev, int64_t *total_dev,
+extern "C" int cyb_lap_solve_i32(const int32_t *cost_dev, int64_t ld, int64_t n_persons, int64_t n_objects,
+                                 const int32_t *slot_offset_dev, int32_t *person_obj_dev,
+                                 int32_t *slot_owner_dev, int64_t *price_dev, int64_t *total_dev,
                                  int64_t *stats_dev, void *workspace_dev, size_t workspace_bytes,
                                  int grid_hint, void *stream_v) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
-    if (n <= 0 || n >= (1ll << kRowBits))
-        return cyb::set_error(CYB_ERR_INVALID, "cyb_lap_solve_i32: n=%lld outside [1, 2^18)", (long long)n);
-    if (!cost_dev || !rowsol_dev || !colsol_dev || !price_dev || !total_dev || !stats_dev || !workspace_dev)
+    const int64_t np = n_persons, no = n_objects;
+    if (np <= 0 || np >= (1ll << kPersonBits) || no <= 0 || no > np)
+        return cyb::set_error(CYB_ERR_INVALID,
+                              "cyb_lap_solve_i32: persons=%lld objects=%lld outside 1 <= objects <= persons < 2^18",
+                              (long long)np, (long long)no);
+    if (!slot_offset_dev && no != np)
+        return cyb::set_error(CYB_ERR_INVALID, "cyb_lap_solve_i32: without capacities the problem must be square");
+    if (!cost_dev || !person_obj_dev || !slot_owner_dev || !price_dev || !total_dev || !stats_dev || !workspace_dev)
         return cyb::set_error(CYB_ERR_INVALID, "cyb_lap_solve_i32: null pointer argument");
-    if (ld < n) return cyb::set_error(CYB_ERR_INVALID, "cyb_lap_solve_i32: ld=%lld < n=%lld", (long long)ld, (long long)n);
-    const WsLayout L = ws_layout(n);
+    if (ld < no)
+        return cyb::set_error(CYB_ERR_INVALID, "cyb_lap_solve_i32: ld=%lld < objects=%lld", (long long)ld, (long long)no);
+    const WsLayout L = ws_layout(np, no);
     if (workspace_bytes < L.total)
         return cyb::set_error(CYB_ERR_WORKSPACE, "cyb_lap_solve_i32: workspace %zu < required %zu", workspace_bytes, L.total);
     if (reinterpret_cast<uintptr_t>(workspace_dev) & 255)
@@ -551,23 +642,28 @@ extern "C" int cyb_lap_solve_i32(const int32_t *cost_dev, int64_t ld, int64_t n,
 
     int G = grid_hint > 0 ? grid_hint : sms;
     if (G > sms) G = sms;
-    if (G > n) G = (int)n;
+    if (G > np) G = (int)np;
     if (G < 1) G = 1;
 
     char *ws = static_cast<char *>(workspace_dev);
     LapParams P;
-    P.cost = cost_dev; P.ld = ld; P.n = (int)n; P.row_map = row_map_dev;
-    P.rowsol = rowsol_dev; P.owner = colsol_dev; P.price = reinterpret_cast<long long *>(price_dev);
+    P.cost = cost_dev; P.ld = ld; P.P = (int)np; P.O = (int)no; P.soff = slot_offset_dev;
+    P.person_obj = person_obj_dev; P.slot_owner = slot_owner_dev;
+    P.lambda = reinterpret_cast<long long *>(price_dev);
     P.total = reinterpret_cast<long long *>(total_dev); P.stats = reinterpret_cast<long long *>(stats_dev);
-    P.list[0] = reinterpret_cast<int32_t *>(ws + L.list0); P.list[1] = reinterpret_cast<int32_t *>(ws + L.list1);
-    P.rec[0] = reinterpret_cast<int2 *>(ws + L.rec0); P.rec[1] = reinterpret_cast<int2 *>(ws + L.rec1);
-    P.slot[0] = reinterpret_cast<unsigned long long *>(ws + L.slot0);
-    P.slot[1] = reinterpret_cast<unsigned long long *>(ws + L.slot1);
+    for (int k = 0; k < 3; ++k) {
+        P.list[k] = reinterpret_cast<int32_t *>(ws + L.list[k]);
+        P.rec[k] = reinterpret_cast<int4 *>(ws + L.rec[k]);
+        P.bidw[k] = reinterpret_cast<unsigned long long *>(ws + L.bidw[k]);
+    }
     P.flag = reinterpret_cast<int32_t *>(ws + L.flag);
+    P.slot_price = reinterpret_cast<long long *>(ws + L.slot_price);
+    P.person_slot = reinterpret_cast<int32_t *>(ws + L.person_slot);
+    P.minslot = reinterpret_cast<int32_t *>(ws + L.minslot);
     P.bar = reinterpret_cast<unsigned int *>(ws + L.small);
     P.gmm = reinterpret_cast<int *>(ws + L.small + 16);
-    P.qcap = (int)((n + G - 1) / G);
-    P.max_rounds = 2000ll * n + 100000;
+    P.qcap = (int)((np + G - 1) / G);
+    P.max_rounds = 2000ll * np + 100000;
     P.tail_t = 2;
     if (const char *e = getenv("CYB_LAP_TAIL")) P.tail_t = atoi(e);
 
@@ -577,8 +673,8 @@ extern "C" int cyb_lap_solve_i32(const int32_t *cost_dev, int64_t ld, int64_t n,
     CYB_CUDA_CHECK(cudaMemsetAsync(total_dev, 0, sizeof(int64_t), stream));
 
     const size_t q_bytes = cyb::align_up((size_t)P.qcap * 4, 16);
-    const size_t smem_with_price = cyb::align_up((size_t)n * 8, 16) + q_bytes;
-    const size_t static_smem = 32 * 8 * 2 + 32 * 4 * 2 + 64;
+    const size_t smem_with_price = cyb::align_up((size_t)no * 8, 16) + q_bytes;
+    const size_t static_smem = 32 * 8 * 2 + 32 * 4 * 2 + kTailMax * 4 + 128;
     const bool smemp = smem_with_price + static_smem <= (size_t)max_smem;
     const size_t dyn = smemp ? smem_with_price : q_bytes;
     const void *fn = smemp ? (const void *)lap_auction_kernel<true> : (const void *)lap_auction_kernel<false>;
@@ -593,39 +689,45 @@ extern "C" int cyb_lap_solve_i32(const int32_t *cost_dev, int64_t ld, int64_t n,
     return CYB_OK;
 }
 
-extern "C" int cyb_lap_check_i32(const int32_t *cost_dev, int64_t ld, int64_t n,
-                                 const int32_t *row_map_dev, const int32_t *rowsol_dev,
+extern "C" int cyb_lap_check_i32(const int32_t *cost_dev, int64_t ld, int64_t n_persons, int64_t n_objects,
+                                 const int32_t *slot_offset_dev, const int32_t *person_obj_dev,
                                  const int64_t *price_dev, int64_t *out_dev, void *workspace_dev,
                                  size_t workspace_bytes, void *stream_v) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
-    if (n <= 0 || n >= (1ll << kRowBits))
-        return cyb::set_error(CYB_ERR_INVALID, "cyb_lap_check_i32: n=%lld outside [1, 2^18)", (long long)n);
-    if (!cost_dev || !rowsol_dev || !price_dev || !out_dev || !workspace_dev)
+    const int64_t np = n_persons, no = n_objects;
+    if (np <= 0 || np >= (1ll << kPersonBits) || no <= 0 || no > np)
+        return cyb::set_error(CYB_ERR_INVALID, "cyb_lap_check_i32: persons=%lld objects=%lld out of range",
+                              (long long)np, (long long)no);
+    if (!cost_dev || !person_obj_dev || !price_dev || !out_dev || !workspace_dev)
         return cyb::set_error(CYB_ERR_INVALID, "cyb_lap_check_i32: null pointer argument");
-    const WsLayout L = ws_layout(n);
+    const WsLayout L = ws_layout(np, no);
     if (workspace_bytes < L.total)
         return cyb::set_error(CYB_ERR_WORKSPACE, "cyb_lap_check_i32: workspace %zu < required %zu", workspace_bytes, L.total);
     char *ws = static_cast<char *>(workspace_dev);
     long long *rowmin = reinterpret_cast<long long *>(ws + L.rowmin);
-    CYB_CUDA_CHECK(cudaMemsetAsync(rowmin, 0x7F, (size_t)n * 8, stream));     // large positive sentinel
-    const long long out_init[3] = {LLONG_MIN, 0, 0};
+    int32_t *count = reinterpret_cast<int32_t *>(ws + L.count);
+    CYB_CUDA_CHECK(cudaMemsetAsync(rowmin, 0x7F, (size_t)np * 8, stream));     // large positive sentinel
+    CYB_CUDA_CHECK(cudaMemsetAsync(count, 0, (size_t)no * 4, stream));
+    const long long out_init[4] = {LLONG_MIN, 0, 0, 0};
     CYB_CUDA_CHECK(cudaMemcpyAsync(out_dev, out_init, sizeof(out_init), cudaMemcpyHostToDevice, stream));
     int dev = 0, sms = 0;
     CYB_CUDA_CHECK(cudaGetDevice(&dev));
     CYB_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const long long S = n + 1;
-    const int tiles = (int)((n + kChkTileCols - 1) / kChkTileCols);
-    // enough row groups for >= 4 waves of CTAs, at least 16 rows each
-    int rows_per_cta = (int)((n * (long long)tiles + (long long)sms * 8 - 1) / ((long long)sms * 8));
+    const long long S = np + 1;
+    const int tiles = (int)((no + kChkTileCols - 1) / kChkTileCols);
+    // enough person groups for ~8 CTAs per SM, at least 16 rows each
+    int rows_per_cta = (int)((np * (long long)tiles + (long long)sms * 8 - 1) / ((long long)sms * 8));
     if (rows_per_cta < 16) rows_per_cta = 16;
-    const int groups = (int)((n + rows_per_cta - 1) / rows_per_cta);
+    const int groups = (int)((np + rows_per_cta - 1) / rows_per_cta);
     lap_rowmin_kernel<<<dim3(tiles, groups), kChkThreads, 0, stream>>>(
-        cost_dev, ld, (int)n, row_map_dev, reinterpret_cast<const long long *>(price_dev), S,
-        rows_per_cta, rowmin);
+        cost_dev, ld, (int)np, (int)no, reinterpret_cast<const long long *>(price_dev), S, rows_per_cta, rowmin);
     CYB_CUDA_CHECK(cudaGetLastError());
-    lap_check_finish_kernel<<<sms, 256, 0, stream>>>(cost_dev, ld, (int)n, row_map_dev, rowsol_dev,
-                                                     reinterpret_cast<const long long *>(price_dev), S,
-                                                     rowmin, reinterpret_cast<long long *>(out_dev));
+    lap_check_finish_kernel<<<sms, 256, 0, stream>>>(cost_dev, ld, (int)np, (int)no, person_obj_dev,
+                                                     reinterpret_cast<const long long *>(price_dev), S, rowmin, count,
+                                                     reinterpret_cast<long long *>(out_dev));
+    CYB_CUDA_CHECK(cudaGetLastError());
+    lap_check_capacity_kernel<<<sms, 256, 0, stream>>>(slot_offset_dev, (int)no, count,
+                                                       reinterpret_cast<long long *>(out_dev));
     CYB_CUDA_CHECK(cudaGetLastError());
     return CYB_OK;
 }

@@ -32,13 +32,23 @@ def _round_up(x: int, a: int) -> int:
 
 @dataclass
 class LapResult:
-    """Device-resident LAP output; ``colsol`` is what CytoSPACE consumes
+    """Device-resident LAP output.  With unit capacities ``person_obj`` / ``slot_owner`` are
+    lapjv's ``row_ind`` / ``col_ind``; CytoSPACE consumes ``col_ind``
     (linear_assignment_solvers.py:38: the row assigned to each column)."""
-    rowsol: torch.Tensor      # int32[n]  column (cell) of LAP row i
-    colsol: torch.Tensor      # int32[n]  LAP row (spot slot) of column j
-    price: torch.Tensor       # int64[n]  column prices, units of 1/(n+1) cost
-    total: int                # sum_i cost[row_map[i], rowsol[i]]
+    person_obj: torch.Tensor  # int32[P]  object (spot) of person (cell) i
+    slot_owner: torch.Tensor  # int32[P]  person in slot t (slots ordered by object)
+    price: torch.Tensor       # int64[O]  object prices, units of 1/(P+1) cost
+    total: int                # sum_i cost[i, person_obj[i]]
     stats: dict
+    slot_offsets: torch.Tensor | None = None   # int32[O+1] device (None: unit capacities)
+
+    @property
+    def rowsol(self):
+        return self.person_obj
+
+    @property
+    def colsol(self):
+        return self.slot_owner
 
     @property
     def row_scans(self) -> int:
@@ -103,8 +113,10 @@ class AssignmentEngine:
 
     # --------------------------------------------------------------- cost build
     def cost_build(self, sc: torch.Tensor, st: torch.Tensor, log_tpm: bool = False, out: torch.Tensor | None = None,
-                   return_colstats: bool = False, check_variance: bool = True):
-        """Integer cost ``rint(-cost_scale * pearson)`` as int32 ``[S, ld]`` (ld = N rounded up to 32).
+                   return_colstats: bool = False, check_variance: bool = True, layout: str = "cells_x_spots"):
+        """Integer cost ``rint(-cost_scale * pearson)`` as int32, row-major with ld = columns rounded
+        up to 32.  ``layout="cells_x_spots"`` ([N, ld]: the TRANSPOSE of the reference's ``cost``, a
+        cell's row contiguous) or ``"spots_x_cells"`` ([S, ld]: the reference's own orientation).
 
         sc [G x N], st [G x S]: float64 / float32 device tensors, genes x cells row-major -- the
         arrays ``calculate_cost`` receives (linear_assignment_solvers.py:42).  Raises ``ValueError``
@@ -128,10 +140,13 @@ class AssignmentEngine:
         if G == 0 or N == 0 or S == 0:
             raise ValueError("empty expression matrix")
         prec = PRECISIONS[self.precision]
-        ld = _round_up(N, 32)
+        if layout not in ("cells_x_spots", "spots_x_cells"):
+            raise ValueError("layout must be 'cells_x_spots' or 'spots_x_cells'")
+        rows, cols = (N, S) if layout == "cells_x_spots" else (S, N)
+        ld = _round_up(cols, 32)
         if out is None:
-            out = torch.empty((S, ld), dtype=torch.int32, device=self.device)
-        elif out.shape[0] < S or out.stride(0) < N or out.dtype != torch.int32:
+            out = torch.empty((rows, ld), dtype=torch.int32, device=self.device)
+        elif out.shape[0] < rows or out.stride(0) < cols or out.dtype != torch.int32:
             raise ValueError("bad `out` buffer")
         ws_bytes = self.lib.cyb_cost_build_workspace_bytes(G, N, S, prec)
         ws = self._workspace("cost", ws_bytes + 1024)
@@ -141,10 +156,13 @@ class AssignmentEngine:
         zero_var = torch.zeros(1, dtype=torch.int32, device=self.device)
         dt = self.lib.CYB_F64 if sc.dtype == torch.float64 else self.lib.CYB_F32
         self._mark("cost", 0)
+        # the library builds cost[first, second]; the first matrix supplies the rows
+        a, b, na, nb, csa, csb = (sc, st, N, S, colstat_sc, colstat_st) if layout == "cells_x_spots" \
+            else (st, sc, S, N, colstat_st, colstat_sc)
         _native.check(self.lib.cyb_cost_build_pearson(
-            _native.ptr("void *", sc), _native.ptr("void *", st), dt, G, N, S, sc.stride(0), st.stride(0),
+            _native.ptr("void *", a), _native.ptr("void *", b), dt, G, na, nb, a.stride(0), b.stride(0),
             int(bool(log_tpm)), prec, self.cost_scale, _native.ptr("int32_t *", out), out.stride(0),
-            _native.ptr("double *", colstat_sc), _native.ptr("double *", colstat_st),
+            _native.ptr("double *", csa), _native.ptr("double *", csb),
             _native.ptr("int32_t *", zero_var), self.ffi.cast("void *", ws.data_ptr() + off), ws_bytes,
             self._stream()))
         self._mark("cost", 1)
@@ -176,34 +194,49 @@ class AssignmentEngine:
         return out
 
     # ---------------------------------------------------------------------- LAP
-    def lap_solve(self, cost: torch.Tensor, row_map: torch.Tensor | None = None, n: int | None = None,
-                  grid: int = 0) -> LapResult:
-        """Exact LAP on the int32 device matrix ``cost[row_map[i], j]`` (i, j < n)."""
+    def _slot_offsets(self, capacities, n_objects):
+        if capacities is None:
+            return None, n_objects
+        cap = np.asarray(capacities).astype(np.int64).ravel()
+        if cap.shape[0] != n_objects:
+            raise ValueError(f"{cap.shape[0]} capacities for {n_objects} objects")
+        if (cap < 0).any():
+            raise ValueError("negative capacity")
+        if (cap == 1).all():
+            return None, n_objects
+        soff = np.zeros(n_objects + 1, dtype=np.int32)
+        np.cumsum(cap, out=soff[1:])
+        return torch.from_numpy(soff).to(self.device), int(soff[-1])
+
+    def lap_solve(self, cost: torch.Tensor, capacities=None, n_persons: int | None = None,
+                  n_objects: int | None = None, grid: int = 0) -> LapResult:
+        """Exact assignment on the int32 device matrix ``cost[person, object]``: every person gets one
+        object, object ``o`` exactly ``capacities[o]`` persons (None: 1 each, the square LAP)."""
         if cost.dtype != torch.int32 or not cost.is_cuda or cost.dim() != 2 or cost.stride(1) != 1:
             raise ValueError("cost must be a row-major int32 device matrix")
-        if n is None:
-            n = int(row_map.numel()) if row_map is not None else int(cost.shape[0])
-        if row_map is not None:
-            if row_map.dtype != torch.int32 or not row_map.is_cuda or row_map.numel() != n:
-                raise ValueError("row_map must be an int32 device vector of length n")
-        elif cost.shape[0] < n:
-            raise ValueError("cost has fewer rows than n")
-        if cost.shape[1] < n:
-            raise ValueError("LAP must be square: cost has fewer columns than n")
-        if n <= 0:
+        if n_persons is None:
+            n_persons = int(cost.shape[0])
+        if n_objects is None:
+            n_objects = n_persons if capacities is None else int(np.asarray(capacities).size)
+        if n_persons <= 0 or n_objects <= 0:
             raise ValueError("empty LAP")
+        if cost.shape[0] < n_persons or cost.shape[1] < n_objects:
+            raise ValueError("LAP must be square: cost is smaller than persons x objects")
+        soff, n_slots = self._slot_offsets(capacities, n_objects)
+        if n_slots != n_persons:
+            raise ValueError(f"the assignment must be square: {n_slots} slots for {n_persons} persons")
         dev = self.device
-        rowsol = torch.empty(n, dtype=torch.int32, device=dev)
-        colsol = torch.empty(n, dtype=torch.int32, device=dev)
-        price = torch.empty(n, dtype=torch.int64, device=dev)
+        person_obj = torch.empty(n_persons, dtype=torch.int32, device=dev)
+        slot_owner = torch.empty(n_persons, dtype=torch.int32, device=dev)
+        price = torch.empty(n_objects, dtype=torch.int64, device=dev)
         small = torch.zeros(1 + self.lib.CYB_LAP_NSTATS, dtype=torch.int64, device=dev)
-        ws_bytes = self.lib.cyb_lap_workspace_bytes(n)
+        ws_bytes = self.lib.cyb_lap_workspace_bytes(n_persons, n_objects)
         ws = self._workspace("lap", ws_bytes + 256)
         off = (-ws.data_ptr()) % 256
         self._mark("lap", 0)
         _native.check(self.lib.cyb_lap_solve_i32(
-            _native.ptr("int32_t *", cost), cost.stride(0), n, _native.ptr("int32_t *", row_map),
-            _native.ptr("int32_t *", rowsol), _native.ptr("int32_t *", colsol), _native.ptr("int64_t *", price),
+            _native.ptr("int32_t *", cost), cost.stride(0), n_persons, n_objects, _native.ptr("int32_t *", soff),
+            _native.ptr("int32_t *", person_obj), _native.ptr("int32_t *", slot_owner), _native.ptr("int64_t *", price),
             self.ffi.cast("int64_t *", small.data_ptr()), self.ffi.cast("int64_t *", small.data_ptr() + 8),
             self.ffi.cast("void *", ws.data_ptr() + off), ws_bytes, int(grid), self._stream()))
         self._mark("lap", 1)
@@ -212,28 +245,34 @@ class AssignmentEngine:
         if stats["status"] != 0:
             names = {self.lib.CYB_ERR_OVERFLOW: "price overflow", self.lib.CYB_ERR_NOT_CONVERGED: "round cap hit"}
             raise RuntimeError(f"LAP solve failed on device: {names.get(stats['status'], stats['status'])}")
-        return LapResult(rowsol, colsol, price, int(host[0]), stats)
+        return LapResult(person_obj, slot_owner, price, int(host[0]), stats, soff)
 
-    def lap_check(self, cost: torch.Tensor, res: LapResult, row_map: torch.Tensor | None = None) -> dict:
-        """On-device optimality certificate; ``max_violation <= 1`` (scaled units) proves the
-        assignment optimal for the integer matrix.  One coalesced pass over the matrix."""
-        n = int(res.rowsol.numel())
-        out = torch.zeros(3, dtype=torch.int64, device=self.device)
-        ws_bytes = self.lib.cyb_lap_workspace_bytes(n)
+    def lap_check(self, cost: torch.Tensor, res: LapResult) -> dict:
+        """On-device optimality certificate; ``max_violation <= 1`` (scaled units) with no invalid
+        person / capacity mismatch proves the assignment optimal for the integer matrix.  One
+        coalesced pass over the matrix."""
+        n_persons, n_objects = int(res.person_obj.numel()), int(res.price.numel())
+        out = torch.zeros(4, dtype=torch.int64, device=self.device)
+        ws_bytes = self.lib.cyb_lap_workspace_bytes(n_persons, n_objects)
         ws = self._workspace("lap", ws_bytes + 256)
         off = (-ws.data_ptr()) % 256
+        self._mark("check", 0)
         _native.check(self.lib.cyb_lap_check_i32(
-            _native.ptr("int32_t *", cost), cost.stride(0), n, _native.ptr("int32_t *", row_map),
-            _native.ptr("int32_t *", res.rowsol), _native.ptr("int64_t *", res.price),
-            _native.ptr("int64_t *", out), self.ffi.cast("void *", ws.data_ptr() + off), ws_bytes, self._stream()))
-        v, t, bad = out.cpu().tolist()
-        return {"max_violation": v, "total": t, "invalid_rows": bad}
+            _native.ptr("int32_t *", cost), cost.stride(0), n_persons, n_objects,
+            _native.ptr("int32_t *", res.slot_offsets), _native.ptr("int32_t *", res.person_obj),
+            _native.ptr("int64_t *", res.price), _native.ptr("int64_t *", out),
+            self.ffi.cast("void *", ws.data_ptr() + off), ws_bytes, self._stream()))
+        self._mark("check", 1)
+        v, t, bad, badcap = out.cpu().tolist()
+        return {"max_violation": v, "total": t, "invalid_rows": bad, "capacity_mismatch": badcap}
 
     # --------------------------------------------------------------- whole path
     def assign(self, sc, st, cell_number_to_node_assignment, log_tpm: bool = False):
         """cost build + LAP + ``location_repeat[assignment]`` (cytospace.py:319-331).
 
-        Returns ``(spot_of_cell int64 device tensor [N], LapResult, cost int32 [S, ld])``."""
+        Returns ``(spot_of_cell int64 device tensor [N], LapResult, cost int32 device matrix)``; the
+        matrix is persons x objects of the solve: spots x cells when every spot takes one cell, cells x
+        spots otherwise."""
         cn = np.asarray(cell_number_to_node_assignment).astype(np.int64).ravel()
         sc = self.to_device(sc) if not (torch.is_tensor(sc) and sc.is_cuda) else sc
         st = self.to_device(st) if not (torch.is_tensor(st) and st.is_cuda) else st
@@ -246,13 +285,18 @@ class AssignmentEngine:
         if n != N:
             raise ValueError(f"the assignment must be square: sum(cell_number_to_node_assignment)={n} "
                              f"but {N} cells were given")
-        cost = self.cost_build(sc, st, log_tpm=log_tpm, check_variance=False)   # checked after the solve: one sync
         if (cn == 1).all():
-            row_map = None
+            # square LAP: the spots bid for the cells (the reference's own orientation).  Either side
+            # may bid; measured on B200 the noisier side (the cells) makes the better OBJECTS -- larger
+            # gaps between a bidder's best and second-best object, shorter price wars.
+            cost = self.cost_build(sc, st, log_tpm=log_tpm, check_variance=False, layout="spots_x_cells")
+            res = self.lap_solve(cost, None, n_persons=S, n_objects=N)
+            spot_of_cell = res.slot_owner.long()
         else:
-            # location_repeat of linear_assignment_solvers.py:63-65, kept as an index instead of a row copy
-            row_map = torch.from_numpy(np.repeat(np.arange(S, dtype=np.int32), cn)).to(self.device)
-        res = self.lap_solve(cost, row_map, n=N)
-        self.check_zero_variance()
-        spot_of_cell = res.colsol.long() if row_map is None else row_map[res.colsol.long()].long()
+            # location_repeat (linear_assignment_solvers.py:63-65) becomes the spots' capacities:
+            # the cells bid for spots that hold cn[s] cells each
+            cost = self.cost_build(sc, st, log_tpm=log_tpm, check_variance=False, layout="cells_x_spots")
+            res = self.lap_solve(cost, cn, n_persons=N, n_objects=S)
+            spot_of_cell = res.person_obj.long()
+        self.check_zero_variance()                   # one sync, after the solve
         return spot_of_cell, res, cost

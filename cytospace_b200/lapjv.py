@@ -42,9 +42,9 @@ def _solve(cost_matrix):
         raise ValueError("cost matrix contains NaN or inf")
     scale = float(COST_SCALE) if amax <= 1000.0 else float(2 ** 29) / amax
     dev = eng.quantise(eng.to_device(c64), scale)
-    res = eng.lap_solve(dev, n=cost.shape[0])
-    rowsol = res.rowsol.cpu().numpy()
-    colsol = res.colsol.cpu().numpy()
+    res = eng.lap_solve(dev, n_persons=cost.shape[0], n_objects=cost.shape[0])    # persons = rows, objects = columns
+    rowsol = res.person_obj.cpu().numpy()
+    colsol = res.slot_owner.cpu().numpy()
     n = cost.shape[0]
     # duals in the caller's units: v_j = -price_j / ((n+1) * scale), u_i = c[i, x_i] - v[x_i]
     v = -(res.price.cpu().numpy().astype(np.float64)) / ((n + 1) * scale)

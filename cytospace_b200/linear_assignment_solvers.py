@@ -68,9 +68,9 @@ def calculate_cost(expressions_tpm_scRNA_log, expressions_tpm_st_log, cell_numbe
     eng = get_engine()
     sc = eng.to_device(np.asarray(expressions_tpm_scRNA_log, dtype=np.float64))
     st = eng.to_device(np.asarray(expressions_tpm_st_log, dtype=np.float64))
-    cost_i32 = eng.cost_build(sc, st)
-    n_cells = sc.shape[1]
-    cost = cost_i32[:, :n_cells].cpu().numpy().astype(np.float64) / COST_SCALE
+    cost_i32 = eng.cost_build(sc, st)                      # cells x spots on the device
+    n_spots = st.shape[1]
+    cost = cost_i32[:, :n_spots].T.cpu().numpy().astype(np.float64) / COST_SCALE    # spots x cells like the reference
     location_repeat = np.repeat(np.arange(len(cell_number_to_node_assignment)),
                                 cell_number_to_node_assignment).astype(int)
     distance_repeat = cost[location_repeat, :]

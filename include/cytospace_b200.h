@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define CYB_ABI_VERSION 2
+#define CYB_ABI_VERSION 3
 
 /* status codes */
 #define CYB_OK                 0
@@ -92,8 +92,9 @@ size_t cyb_standardise_workspace_bytes(int64_t n_genes, int64_t n_cols);
  *              DataFrame.to_numpy()), leading dimension ld_x elements
  *   log_tpm    1: apply normalize_data (TPM, log2(x+1)) first; 0: x is already
  *              normalised (what solve_linear_assignment_problem receives)
- *   operand_b  0: this matrix is the A (spot) operand, 1: the B (cell) operand;
- *              only matters for CYB_PREC_F16X3 (A = [hi|hi|lo], B = [hi|lo|hi])
+ *   operand_b  0: this matrix is the A operand (rows of the cost matrix: cells), 1: the
+ *              B operand (columns: spots); only matters for CYB_PREC_F16X3
+ *              (A = [hi|hi|lo], B = [hi|lo|hi])
  *   z_dev      fp16 [n_cols x cyb_operand_k()] K-major: z = (x - mean) / sigma,
  *              K padding zero-filled by this call
  *   colstat_dev float64 [2 x n_cols] out: mean, population sigma
@@ -105,27 +106,29 @@ int cyb_standardise(const void *x_dev, int x_dtype, int64_t n_genes, int64_t n_c
                     void *z_dev, double *colstat_dev, int32_t *zero_var_dev,
                     void *workspace_dev, size_t workspace_bytes, void *stream);
 
-/* cost[s, c] = rint(-scale * sum_k zst[s,k] * zsc[c,k])  as int32,
+/* cost[a, b] = rint(-scale * sum_k za[a,k] * zb[b,k])  as int32,
  * a TMA-fed tcgen05 GEMM with TMEM accumulators and a fused quantise epilogue.
- *   zst_dev [n_spots x k] fp16, zsc_dev [n_cells x k] fp16 (K-major, k % 64 == 0,
- *   16-byte aligned); cost_dev [n_spots x ld_cost] int32 row-major.
+ *   za_dev [n_a x k] fp16, zb_dev [n_b x k] fp16 (K-major, k % 64 == 0,
+ *   16-byte aligned); cost_dev [n_a x ld_cost] int32 row-major.
  * With z from cyb_standardise, scale = 1e6 / n_genes gives rint(-1e6 * r).   */
-int cyb_cost_gemm_i32(const void *zst_dev, const void *zsc_dev, int64_t n_spots,
-                      int64_t n_cells, int64_t k, float scale, int32_t *cost_dev,
+int cyb_cost_gemm_i32(const void *za_dev, const void *zb_dev, int64_t n_a,
+                      int64_t n_b, int64_t k, float scale, int32_t *cost_dev,
                       int64_t ld_cost, void *stream);
 
 /* Bytes of device workspace cyb_cost_build_pearson needs. */
-size_t cyb_cost_build_workspace_bytes(int64_t n_genes, int64_t n_cells, int64_t n_spots,
-                                      int precision);
+size_t cyb_cost_build_workspace_bytes(int64_t n_genes, int64_t n_a, int64_t n_b, int precision);
 
-/* calculate_cost, Pearson branch, in one call: standardise both matrices and run
- * the GEMM.  cost_dev [n_spots x ld_cost] = rint(-cost_scale * pearson(st, sc)).
- * colstat_sc_dev / colstat_st_dev: float64 [2 x n] out (may be NULL).           */
-int cyb_cost_build_pearson(const void *sc_dev, const void *st_dev, int x_dtype,
-                           int64_t n_genes, int64_t n_cells, int64_t n_spots,
-                           int64_t ld_sc, int64_t ld_st, int log_tpm, int precision,
+/* calculate_cost, Pearson branch, in one call: standardise both matrices and run the GEMM.
+ *   cost[i, j] = rint(-cost_scale * pearson(a[:, i], b[:, j]))   int32 [n_a x ld_cost]
+ * a_dev [n_genes x n_a], b_dev [n_genes x n_b] (genes x columns, row-major).  The caller picks
+ * the orientation: a = ST, b = scRNA gives the reference's `cost` (spots x cells,
+ * linear_assignment_solvers.py:55); a = scRNA, b = ST its transpose (cells x spots), the
+ * layout the capacitated LAP scans.  colstat_*_dev: float64 [2 x n] out (may be NULL).   */
+int cyb_cost_build_pearson(const void *a_dev, const void *b_dev, int x_dtype,
+                           int64_t n_genes, int64_t n_a, int64_t n_b,
+                           int64_t ld_a, int64_t ld_b, int log_tpm, int precision,
                            double cost_scale, int32_t *cost_dev, int64_t ld_cost,
-                           double *colstat_sc_dev, double *colstat_st_dev,
+                           double *colstat_a_dev, double *colstat_b_dev,
                            int32_t *zero_var_dev, void *workspace_dev,
                            size_t workspace_bytes, void *stream);
 
@@ -138,39 +141,48 @@ int cyb_quantise_f64(const double *in_dev, int64_t n_rows, int64_t n_cols, int64
 
 /* ----------------------------------------------------------------------- LAP */
 
-/* Bytes of device workspace cyb_lap_solve_i32 needs for an n x n problem. */
-size_t cyb_lap_workspace_bytes(int64_t n);
+/* Bytes of device workspace cyb_lap_solve_i32 / cyb_lap_check_i32 need. */
+size_t cyb_lap_workspace_bytes(int64_t n_persons, int64_t n_objects);
 
-/* Exact dense LAP: min sum_i cost[row_map[i], x(i)] over permutations x.
- *   cost_dev    int32 [n_rows_compact x ld] row-major; |cost| < 2^30
- *   row_map_dev int32[n] or NULL (identity): LAP row i is compact row row_map[i]
- *   rowsol_dev  int32[n] out: column (cell) of LAP row i
- *   colsol_dev  int32[n] out: LAP row (spot slot) of column j -- what CytoSPACE
- *               consumes (linear_assignment_solvers.py:38)
- *   price_dev   int64[n] out: column prices in units of 1/(n+1) cost
- *   total_dev   int64[1] out: sum_i cost[row_map[i], rowsol[i]]
- *   stats_dev   int64[CYB_LAP_NSTATS] out (layout above)
- *   grid_hint   0 = auto (one CTA per SM); otherwise the number of CTAs
- * Synchronous eps-scaling auction (Jacobi rounds) in one persistent cooperative
- * kernel; costs scaled by n+1, last phase eps = 1 => the returned assignment is
- * optimal for the integer matrix.  Deterministic: lowest column index wins a
- * row's tie, highest bid then lowest row index wins a column.               */
-int cyb_lap_solve_i32(const int32_t *cost_dev, int64_t ld, int64_t n,
-                      const int32_t *row_map_dev, int32_t *rowsol_dev,
-                      int32_t *colsol_dev, int64_t *price_dev, int64_t *total_dev,
+/* Exact dense assignment in transportation form:
+ *     min sum_i cost[i, obj(i)]   s.t. object o holds exactly cap[o] persons.
+ * For CytoSPACE the persons are the cells, the objects the spots and cap =
+ * cell_number_to_node_assignment: the same optimisation problem as lapjv on the
+ * expanded matrix cost[location_repeat, :] (linear_assignment_solvers.py:63-66) with the
+ * same optimal total, without materialising the expansion.
+ *   cost_dev        int32 [n_persons x ld] row-major (cells x spots); |cost| < 2^30
+ *   slot_offset_dev int32[n_objects + 1], exclusive prefix sum of the capacities
+ *                   (slot_offset[n_objects] == n_persons), or NULL: every capacity is 1
+ *                   (then n_objects == n_persons: the plain square LAP)
+ *   person_obj_dev  int32[n_persons] out: object (spot) of person (cell) i -- with cap == 1
+ *                   this is lapjv's row_ind for the matrix as given
+ *   slot_owner_dev  int32[n_persons] out: person held by slot t; the slots of object o are
+ *                   slot_offset[o] .. slot_offset[o+1]-1 -- with cap == 1 this is lapjv's
+ *                   col_ind, the vector CytoSPACE consumes (linear_assignment_solvers.py:38)
+ *   price_dev       int64[n_objects] out: object prices in units of 1/(n_persons+1) cost
+ *   total_dev       int64[1] out: sum_i cost[i, person_obj[i]]
+ *   stats_dev       int64[CYB_LAP_NSTATS] out (layout above)
+ *   grid_hint       0 = auto (one CTA per SM); otherwise the number of CTAs
+ * Synchronous eps-scaling auction (Jacobi rounds, Gauss-Seidel tail) in one persistent
+ * cooperative kernel; costs scaled by n_persons+1, last phase eps = 1 => the returned
+ * assignment is optimal for the integer matrix.  Deterministic: lowest object index wins a
+ * person's tie, highest bid then lowest person index wins an object.               */
+int cyb_lap_solve_i32(const int32_t *cost_dev, int64_t ld, int64_t n_persons, int64_t n_objects,
+                      const int32_t *slot_offset_dev, int32_t *person_obj_dev,
+                      int32_t *slot_owner_dev, int64_t *price_dev, int64_t *total_dev,
                       int64_t *stats_dev, void *workspace_dev, size_t workspace_bytes,
                       int grid_hint, void *stream);
 
-/* Optimality certificate / row-scan pass: for every LAP row computes
- * m_i = min_j (cost*(n+1) + price) and writes
- *   out_dev[0] = max_i ( (cost[i,rowsol[i]]*(n+1) + price[rowsol[i]]) - m_i )
- *                (<= 1 certifies optimality), out_dev[1] = total cost,
- *   out_dev[2] = number of rows whose rowsol is not a valid column.
- * One coalesced pass over the whole matrix (n*n*4 bytes): the HBM roofline
- * probe of the LAP row scan.  Workspace: cyb_lap_workspace_bytes(n).
- * Synchronises the stream once (it needs the cost minimum on the host). */
-int cyb_lap_check_i32(const int32_t *cost_dev, int64_t ld, int64_t n,
-                      const int32_t *row_map_dev, const int32_t *rowsol_dev,
+/* Optimality certificate / row-scan pass: for every person computes
+ * m_i = min_o (cost[i,o]*(n_persons+1) + price[o]) and writes
+ *   out_dev[0] = max_i ( cost[i,obj(i)]*(n_persons+1) + price[obj(i)] - m_i )
+ *                (<= 1 together with out[2] == out[3] == 0 certifies optimality),
+ *   out_dev[1] = total cost, out_dev[2] = persons without a valid object,
+ *   out_dev[3] = objects whose holder count differs from their capacity.
+ * One coalesced pass over the whole matrix (n_persons*n_objects*4 bytes): the HBM roofline
+ * probe of the LAP row scan.  Workspace: cyb_lap_workspace_bytes().  out_dev: int64[4]. */
+int cyb_lap_check_i32(const int32_t *cost_dev, int64_t ld, int64_t n_persons, int64_t n_objects,
+                      const int32_t *slot_offset_dev, const int32_t *person_obj_dev,
                       const int64_t *price_dev, int64_t *out_dev, void *workspace_dev,
                       size_t workspace_bytes, void *stream);
 

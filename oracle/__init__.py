@@ -60,8 +60,8 @@ def _load():
         lib.lapjv_i32_min_reduced_cost.restype = ctypes.c_int64
         lib.lapjv_i32_min_reduced_cost.argtypes = [ctypes.c_int, i32p, ctypes.c_int64, i32p, i64p, i64p]
         lib.auction_model_i32.restype = ctypes.c_int
-        lib.auction_model_i32.argtypes = [ctypes.c_int, i32p, ctypes.c_int64, i32p, i32p, i32p, i64p, i64p,
-                                          ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_int64, i64p, i32p, ctypes.c_int64, ctypes.c_int64]
+        lib.auction_model_i32.argtypes = [ctypes.c_int, ctypes.c_int, i32p, ctypes.c_int64, i32p, i32p, i32p, i64p, i64p,
+                                          ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, i64p, i32p, ctypes.c_int64, ctypes.c_int]
         _lib = lib
     return _lib
 
@@ -136,17 +136,24 @@ def min_reduced_cost_i32(cost, u, v, row_map=None) -> int:
                                               _ptr(v, ctypes.c_int64)))
 
 
-def auction_model(cost, row_map=None, theta=8, eps0_div=4, keep_cs=True, stop_free=0, round_cap=0, tail_t=0):
+def auction_model(m, cap=None, theta=8, eps0_div=4, tail_t=0, round_cap=0, variant=1):
+    """Sequential model of the device auction.  ``m`` is persons x objects (cells x spots: the
+    TRANSPOSE of the reference's cost), ``cap`` the object capacities (None: all 1).
+    Returns (person_obj, slot_owner, total, lambda, stats, round_log)."""
     lib = _load()
-    cost, row_map, n = _prep(cost, row_map, np.int32)
-    rowsol = np.empty(n, np.int32); colsol = np.empty(n, np.int32)
-    price = np.zeros(n, np.int64); total = np.zeros(1, np.int64); stats = np.zeros(6, np.int64)
+    m = np.ascontiguousarray(m, dtype=np.int32)
+    P, O = m.shape
+    capa = None if cap is None else np.ascontiguousarray(cap, dtype=np.int32)
+    if (O if capa is None else int(capa.sum())) != P:
+        raise ValueError("capacities must sum to the number of persons")
+    person_obj = np.empty(P, np.int32); slot_owner = np.empty(P, np.int32)
+    lam = np.zeros(O, np.int64); total = np.zeros(1, np.int64); stats = np.zeros(6, np.int64)
     rlog = np.zeros(max(round_cap, 1), np.int32)
-    rc = lib.auction_model_i32(n, _ptr(cost, ctypes.c_int32), cost.shape[1], _ptr(row_map, ctypes.c_int32),
-                               _ptr(rowsol, ctypes.c_int32), _ptr(colsol, ctypes.c_int32),
-                               _ptr(price, ctypes.c_int64), _ptr(total, ctypes.c_int64),
-                               theta, eps0_div, int(keep_cs), stop_free, _ptr(stats, ctypes.c_int64),
-                               _ptr(rlog, ctypes.c_int32), round_cap, tail_t)
+    rc = lib.auction_model_i32(P, O, _ptr(m, ctypes.c_int32), m.shape[1], _ptr(capa, ctypes.c_int32),
+                               _ptr(person_obj, ctypes.c_int32), _ptr(slot_owner, ctypes.c_int32),
+                               _ptr(lam, ctypes.c_int64), _ptr(total, ctypes.c_int64),
+                               theta, eps0_div, tail_t, _ptr(stats, ctypes.c_int64),
+                               _ptr(rlog, ctypes.c_int32), round_cap, variant)
     if rc != 0:
         raise RuntimeError(f"auction_model_i32 failed rc={rc}")
-    return rowsol, colsol, int(total[0]), price, stats, rlog[:min(round_cap, int(stats[1]))]
+    return person_obj, slot_owner, int(total[0]), lam, stats, rlog[:min(round_cap, int(stats[1]))]

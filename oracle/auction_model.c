@@ -1,94 +1,140 @@
-/* TEST INFRASTRUCTURE ONLY -- sequential CPU model of the synchronous
- * (Jacobi) epsilon-scaling auction that the device LAP solver
- * (cytospace_b200/csrc/lap_auction.cu) runs.  It exists so the device
- * algorithm's exactness argument and its round/bid counts can be checked
- * without a GPU; it is never linked into the product library.
+/* TEST INFRASTRUCTURE ONLY -- sequential CPU model of the synchronous (Jacobi)
+ * eps-scaling auction with CAPACITATED objects that the device LAP solver
+ * (cytospace_b200/csrc/lap_auction.cu) runs.  It exists so the device algorithm's
+ * exactness argument, tie-breaks and round/bid counts can be checked without a
+ * GPU; it is never linked into the product library.
  *
- * Problem: min sum_i c[i, x(i)] over permutations x; rows = spot slots,
- * columns = cells (same orientation as lapjv_oracle.c).
+ * Problem (transportation form of CytoSPACE's expanded LAP,
+ * linear_assignment_solvers.py:63-66): persons i = 0..P-1 (cells), objects
+ * o = 0..O-1 (spots) with capacity cap[o], sum cap = P;
+ *     min sum_i m[i, obj(i)]   s.t. object o holds exactly cap[o] persons.
+ * m is persons x objects, row-major (the transpose of the reference's cost).
  *
- * Exactness: costs are scaled by (n+1), prices are int64, the last phase runs
- * with eps = 1.  eps-complementary-slackness then bounds the scaled total
- * within n*eps = n < n+1 of optimal, i.e. the unscaled total is optimal
- * (Bertsekas 1988, integer-data corollary).
+ * Every object owns cap[o] SLOTS, each with its own price (the last accepted bid)
+ * and holder; the object's price lambda[o] is the minimum slot price.  A free
+ * person scans its row: v1 = min_o (M[i,o] + lambda[o]) at o* (lowest o on ties),
+ * w = min over o != o*; it bids  b = lambda[o*] + (w - v1) + eps  for the cheapest
+ * slot of o* (lowest slot index on ties).  Per object the highest bid of a round
+ * wins (lowest person on equal bids), the slot's previous holder becomes free.
+ * "Similar objects" never fight each other: the second-best value excludes the
+ * sibling slots of o*, so duplicated spot rows cause no price war.
  *
- * Tie-breaks (shared with the device kernels): a row's best column is the
- * lowest j attaining min_j (C[i,j] + p[j]); a column's winning bid is the
- * highest bid price, lowest row index on equal prices.
+ * Exactness: costs are scaled by (P+1), prices are int64, the last phase runs
+ * with eps = 1.  eps-CS w.r.t. lambda then bounds the scaled total within P*eps
+ * < P+1 of optimal, i.e. the unscaled total is optimal.
  */
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
 
-#define ROWP(i) (cost + (size_t)(row_map ? row_map[(i)] : (i)) * (size_t)ld)
+#define AUCTION_INF ((int64_t)1 << 60)
+#define GAP(b1, b2) (((b2) >= AUCTION_INF / 2) ? 0 : (b2) - (b1))   /* no alternative object: bid eps */
 
 /* stats[0]=phases, [1]=rounds, [2]=bids (row scans), [3]=full-matrix passes,
  * [4]=rounds with <=148 bidders, [5]=bids made in the Gauss-Seidel tail.
  * round_log (may be NULL, capacity round_cap): bidders per round. */
-int auction_model_i32(int n, const int32_t *cost, int64_t ld, const int32_t *row_map,
-                      int32_t *rowsol, int32_t *colsol, int64_t *price,
-                      int64_t *total, int64_t theta, int64_t eps0_div, int keep_cs, int64_t stop_free,
-                      int64_t *stats, int32_t *round_log, int64_t round_cap, int64_t tail_t)
+int auction_model_i32(int P, int O, const int32_t *m, int64_t ld, const int32_t *cap,
+                      int32_t *person_obj, int32_t *slot_owner, int64_t *lambda,
+                      int64_t *total, int64_t theta, int64_t eps0_div, int64_t tail_t,
+                      int64_t *stats, int32_t *round_log, int64_t round_cap, int variant)
 {
-    if (n <= 0) { if (total) *total = 0; return n == 0 ? 0 : -1; }
-    const int64_t S = (int64_t)n + 1;
+    if (P <= 0 || O <= 0) { if (total) *total = 0; return (P == 0) ? 0 : -1; }
+    const int64_t S = (int64_t)P + 1;
+    int32_t *soff = (int32_t *)malloc(sizeof(int32_t) * ((size_t)O + 1));
+    soff[0] = 0;
+    for (int o = 0; o < O; ++o) soff[o + 1] = soff[o] + (cap ? cap[o] : 1);
+    if (soff[O] != P) { free(soff); return -3; }
     int32_t cmin = INT32_MAX, cmax = INT32_MIN;
-    for (int i = 0; i < n; ++i) {
-        const int32_t *r = ROWP(i);
-        for (int j = 0; j < n; ++j) { if (r[j] < cmin) cmin = r[j]; if (r[j] > cmax) cmax = r[j]; }
+    for (int i = 0; i < P; ++i) {
+        const int32_t *r = m + (size_t)i * ld;
+        for (int o = 0; o < O; ++o) { if (r[o] < cmin) cmin = r[o]; if (r[o] > cmax) cmax = r[o]; }
     }
-    int32_t *freel = (int32_t *)malloc(sizeof(int32_t) * (size_t)n);
-    int32_t *nextl = (int32_t *)malloc(sizeof(int32_t) * (size_t)n);
-    int64_t *bidp  = (int64_t *)malloc(sizeof(int64_t) * (size_t)n);   /* best bid price per column */
-    int32_t *bidr  = (int32_t *)malloc(sizeof(int32_t) * (size_t)n);   /* bidding row per column */
-    int32_t *touched = (int32_t *)malloc(sizeof(int32_t) * (size_t)n);
-    if (!freel || !nextl || !bidp || !bidr || !touched) return -2;
-    for (int j = 0; j < n; ++j) { price[j] = 0; colsol[j] = -1; bidr[j] = -1; }
-    for (int i = 0; i < n; ++i) rowsol[i] = -1;
+    int64_t *slot_price = (int64_t *)calloc((size_t)P, sizeof(int64_t));
+    int32_t *minslot = (int32_t *)malloc(sizeof(int32_t) * (size_t)O);
+    int32_t *person_slot = (int32_t *)malloc(sizeof(int32_t) * (size_t)P);
+    int32_t *freel = (int32_t *)malloc(sizeof(int32_t) * (size_t)P);
+    int32_t *nextl = (int32_t *)malloc(sizeof(int32_t) * (size_t)P);
+    int64_t *bidp = (int64_t *)malloc(sizeof(int64_t) * (size_t)O);
+    int32_t *bidr = (int32_t *)malloc(sizeof(int32_t) * (size_t)O);
+    int32_t *kobj = (int32_t *)malloc(sizeof(int32_t) * (size_t)P);
+    /* an object without capacity (a spot that takes no cell, cytospace.py:686-694) is priced out */
+    for (int o = 0; o < O; ++o) { lambda[o] = (soff[o + 1] > soff[o]) ? 0 : AUCTION_INF; minslot[o] = soff[o]; bidr[o] = -1; }
+    for (int t = 0; t < P; ++t) slot_owner[t] = -1;
+    for (int i = 0; i < P; ++i) { person_obj[i] = -1; person_slot[i] = -1; }
     int64_t st[6] = {0, 0, 0, 1, 0, 0};
+
+#define SCAN(i, b1, b2, o1)                                                        \
+    do {                                                                           \
+        const int32_t *r_ = m + (size_t)(i) * ld;                                  \
+        b1 = INT64_MAX; b2 = INT64_MAX; o1 = -1;                                   \
+        for (int o_ = 0; o_ < O; ++o_) {                                           \
+            int64_t h_ = (int64_t)(r_[o_] - cmin) * S + lambda[o_];                \
+            if (h_ < b1) { b2 = b1; b1 = h_; o1 = o_; }                            \
+            else if (h_ < b2) b2 = h_;                                             \
+        }                                                                          \
+    } while (0)
+#define REFRESH(o)                                                                 \
+    do {                                                                           \
+        int ms_ = soff[o]; int64_t mp_ = slot_price[ms_];                          \
+        for (int t_ = soff[o] + 1; t_ < soff[(o) + 1]; ++t_)                       \
+            if (slot_price[t_] < mp_) { mp_ = slot_price[t_]; ms_ = t_; }          \
+        minslot[o] = ms_; lambda[o] = mp_;                                         \
+    } while (0)
 
     int64_t eps = ((int64_t)cmax - (int64_t)cmin) * S / (eps0_div > 0 ? eps0_div : 4);
     if (eps < 1) eps = 1;
     for (;;) {
         ++st[0];
-        /* phase start: decide who is free */
         int nfree = 0;
-        if (st[0] == 1 || !keep_cs) {
-            for (int i = 0; i < n; ++i) { rowsol[i] = -1; freel[nfree++] = i; }
-            for (int j = 0; j < n; ++j) colsol[j] = -1;
+        if (st[0] == 1) {
+            for (int i = 0; i < P; ++i) freel[nfree++] = i;
         } else {
-            /* keep pairs that already satisfy eps-CS at the new eps */
+            /* keep the pairs that already satisfy eps-CS at the new eps.  The test uses the person's
+             * OWN slot price (>= lambda of its object, which may still rise up to it) against the best
+             * alternative object, so the pair stays eps-CS for the rest of the phase.  A vacated slot
+             * keeps its price. */
             ++st[3];
-            for (int i = 0; i < n; ++i) {
-                const int32_t *r = ROWP(i);
-                int64_t m = INT64_MAX;
-                for (int j = 0; j < n; ++j) { int64_t h = (int64_t)r[j] * S + price[j]; if (h < m) m = h; }
-                int j0 = rowsol[i];
-                if (j0 < 0 || (int64_t)r[j0] * S + price[j0] > m + eps) {
-                    if (j0 >= 0) colsol[j0] = -1;
-                    rowsol[i] = -1; freel[nfree++] = i;
+            for (int i = 0; i < P; ++i) {
+                int64_t b1, b2; int o1;
+                SCAN(i, b1, b2, o1);
+                const int o = person_obj[i];
+                int drop = 1;
+                if (o >= 0) {
+                    const int64_t alt = (o1 == o) ? b2 : b1;
+                    const int64_t base = (int64_t)(m[(size_t)i * ld + o] - cmin) * S;
+                    if (alt >= AUCTION_INF / 2) drop = 0;
+                    else if (variant == 0) drop = base + slot_price[person_slot[i]] > alt + eps;
+                    else {
+                        /* test against the OBJECT price, then clamp the own slot price down to the
+                         * highest level that is still eps-CS (>= lambda[o], so lambda never drops) */
+                        drop = base + lambda[o] > alt + eps;
+                        if (!drop && base + slot_price[person_slot[i]] > alt + eps) slot_price[person_slot[i]] = alt + eps - base;
+                    }
+                }
+                if (drop) {
+                    if (o >= 0) slot_owner[person_slot[i]] = -1;
+                    person_obj[i] = -1; person_slot[i] = -1; freel[nfree++] = i;
                 }
             }
         }
-        while (nfree > (eps == 1 ? 0 : stop_free)) {
+        if (st[0] > 1 && variant) for (int o = 0; o < O; ++o) if (soff[o + 1] > soff[o]) REFRESH(o);
+        while (nfree > 0) {
             if (nfree <= tail_t) {
-                /* Gauss-Seidel tail (what CTA 0 runs alone on the device): FIFO of free rows, every
-                 * bid sees the prices left by the previous one; the lone bidder always wins. */
-                int head = 0, tailp = nfree;                 /* circular queue in freel[0..n) */
-                int cnt = nfree;
+                /* Gauss-Seidel tail (what CTA 0 runs alone on the device): FIFO of free persons */
+                int head = 0, tailp = nfree % P, cnt = nfree;
                 while (cnt > 0) {
-                    int i = freel[head]; head = (head + 1) % n; --cnt;
-                    const int32_t *r = ROWP(i);
-                    int64_t b1 = INT64_MAX, b2 = INT64_MAX; int j1 = -1;
-                    for (int j = 0; j < n; ++j) {
-                        int64_t h = (int64_t)r[j] * S + price[j];
-                        if (h < b1) { b2 = b1; b1 = h; j1 = j; }
-                        else if (h < b2) b2 = h;
+                    const int i = freel[head]; head = (head + 1) % P; --cnt;
+                    int64_t b1, b2; int o1;
+                    SCAN(i, b1, b2, o1);
+                    const int64_t bid = lambda[o1] + GAP(b1, b2) + eps;
+                    const int t = minslot[o1];
+                    const int old = slot_owner[t];
+                    slot_owner[t] = i; slot_price[t] = bid; person_obj[i] = o1; person_slot[i] = t;
+                    if (old >= 0) {
+                        person_obj[old] = -1; person_slot[old] = -1;
+                        freel[tailp] = old; tailp = (tailp + 1) % P; ++cnt;
                     }
-                    price[j1] += (n > 1 ? b2 - b1 : 0) + eps;
-                    int old = colsol[j1];
-                    colsol[j1] = i; rowsol[i] = j1;
-                    if (old >= 0) { rowsol[old] = -1; freel[tailp % n] = old; tailp = (tailp + 1) % n; ++cnt; }
+                    REFRESH(o1);
                     ++st[2]; ++st[5];
                 }
                 nfree = 0;
@@ -97,44 +143,43 @@ int auction_model_i32(int n, const int32_t *cost, int64_t ld, const int32_t *row
             if (round_log && st[1] < round_cap) round_log[st[1]] = nfree;
             ++st[1]; st[2] += nfree;
             if (nfree <= 148) ++st[4];
-            int ntouched = 0;
+            /* bids: all computed against the prices of the round start (Jacobi) */
             for (int k = 0; k < nfree; ++k) {
-                int i = freel[k];
-                const int32_t *r = ROWP(i);
-                int64_t b1 = INT64_MAX, b2 = INT64_MAX; int j1 = -1;
-                for (int j = 0; j < n; ++j) {
-                    int64_t h = (int64_t)r[j] * S + price[j];
-                    if (h < b1) { b2 = b1; b1 = h; j1 = j; }
-                    else if (h < b2) b2 = h;
-                }
-                int64_t gamma = (n > 1 ? b2 - b1 : 0) + eps;
-                int64_t bp = price[j1] + gamma;
-                if (bidr[j1] < 0) { touched[ntouched++] = j1; bidp[j1] = bp; bidr[j1] = i; }
-                else if (bp > bidp[j1] || (bp == bidp[j1] && i < bidr[j1])) { bidp[j1] = bp; bidr[j1] = i; }
+                const int i = freel[k];
+                int64_t b1, b2; int o1;
+                SCAN(i, b1, b2, o1);
+                const int64_t bp = lambda[o1] + GAP(b1, b2) + eps;
+                kobj[k] = o1;
+                if (bidr[o1] < 0 || bp > bidp[o1] || (bp == bidp[o1] && i < bidr[o1])) { bidp[o1] = bp; bidr[o1] = i; }
             }
-            /* resolve: the winner of every touched column takes it at its bid
-             * price; the previous owner (if any) becomes free.  The next free
-             * list is losers + displaced owners; its order is irrelevant to a
-             * Jacobi round (all bids of a round see the same prices). */
+            /* resolve in record order (the device replays the records in this order): the winner of
+             * an object takes its cheapest slot at its bid, the slot's previous holder becomes free;
+             * a loser stays free.  The next free list keeps the record order. */
             int nnext = 0;
-            for (int t = 0; t < ntouched; ++t) {
-                int j = touched[t];
-                int w = bidr[j];
-                int old = colsol[j];
-                if (old >= 0) { rowsol[old] = -1; nextl[nnext++] = old; }
-                colsol[j] = w; rowsol[w] = j; price[j] = bidp[j];
-                bidr[j] = -1;
+            for (int k = 0; k < nfree; ++k) {
+                const int i = freel[k], o = kobj[k];
+                if (bidr[o] == i) {
+                    const int t = minslot[o], old = slot_owner[t];
+                    slot_owner[t] = i; slot_price[t] = bidp[o]; person_obj[i] = o; person_slot[i] = t;
+                    if (old >= 0) { person_obj[old] = -1; person_slot[old] = -1; nextl[nnext++] = old; }
+                } else {
+                    nextl[nnext++] = i;
+                }
             }
-            for (int k = 0; k < nfree; ++k) { int i = freel[k]; if (rowsol[i] < 0) nextl[nnext++] = i; }
+            for (int k = 0; k < nfree; ++k) {
+                const int o = kobj[k];
+                if (bidr[o] >= 0) { REFRESH(o); bidr[o] = -1; }
+            }
             int32_t *tmp = freel; freel = nextl; nextl = tmp; nfree = nnext;
         }
         if (eps == 1) break;
         eps = eps / theta; if (eps < 1) eps = 1;
     }
     int64_t tot = 0;
-    for (int i = 0; i < n; ++i) tot += ROWP(i)[rowsol[i]];
+    for (int i = 0; i < P; ++i) tot += m[(size_t)i * ld + person_obj[i]];
     if (total) *total = tot;
     if (stats) memcpy(stats, st, sizeof(st));
-    free(freel); free(nextl); free(bidp); free(bidr); free(touched);
+    free(soff); free(slot_price); free(minslot); free(person_slot); free(freel); free(nextl);
+    free(bidp); free(bidr); free(kobj);
     return 0;
 }

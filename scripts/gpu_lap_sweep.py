@@ -16,7 +16,7 @@ ref = None
 for T in tails:
     os.environ["CYB_LAP_TAIL"] = str(T)
     for rep in range(2):
-        res = eng.lap_solve(cost, n=n)
+        res = eng.lap_solve(cost, n_persons=n, n_objects=n)
     ms = eng.last_ms("lap")
     st_ = res.stats
     if ref is None: ref = res.total

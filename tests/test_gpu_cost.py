@@ -22,7 +22,8 @@ TOL = {"f16x3": 4, "f16": 400}
 def build(engine, sc, st, log_tpm=False, dtype=torch.float64):
     sc_d = engine.to_device(sc, dtype); st_d = engine.to_device(st, dtype)
     cost, cs_sc, cs_st = engine.cost_build(sc_d, st_d, log_tpm=log_tpm, return_colstats=True)
-    return cost[:, :sc.shape[1]].cpu().numpy(), cs_sc.cpu().numpy(), cs_st.cpu().numpy()
+    # the device matrix is cells x spots; compare in the reference's orientation (spots x cells)
+    return cost[:, :st.shape[1]].T.cpu().numpy(), cs_sc.cpu().numpy(), cs_st.cpu().numpy()
 
 
 @pytest.mark.parametrize("tag", ["a", "b", "c"])

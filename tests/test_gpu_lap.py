@@ -1,6 +1,6 @@
 """GPU: the LAP kernel (through the C ABI) against the CPU oracle.  Bit-exact bar: identical total
-cost; the permutation must be a valid optimal assignment (certificate: eps-complementary
-slackness <= 1 scaled unit, checked on the device and again on the host)."""
+cost; the assignment must be valid and optimal (certificate: eps-complementary slackness <= 1
+scaled unit, checked on the device), and the run deterministic."""
 import numpy as np
 import pytest
 import torch
@@ -12,28 +12,39 @@ from conftest import LAP_NAMES
 pytestmark = pytest.mark.gpu
 
 
-def solve_and_check(engine, cost_np, row_map_np=None, grid=0):
-    n = cost_np.shape[1] if row_map_np is None else len(row_map_np)
-    ld = (cost_np.shape[1] + 31) // 32 * 32
-    dev = torch.full((cost_np.shape[0], ld), 2 ** 30 - 1, dtype=torch.int32, device=engine.device)
-    dev[:, :cost_np.shape[1]] = torch.from_numpy(cost_np).to(engine.device)
-    rm = None if row_map_np is None else torch.from_numpy(row_map_np.astype(np.int32)).to(engine.device)
-    res = engine.lap_solve(dev, rm, n=n, grid=grid)
-    rowsol = res.rowsol.cpu().numpy(); colsol = res.colsol.cpu().numpy()
-    assert sorted(rowsol.tolist()) == list(range(n)), "rowsol is not a permutation"
-    assert np.array_equal(colsol[rowsol], np.arange(n)), "colsol is not the inverse of rowsol"
-    assert oracle.assignment_cost_i32(cost_np, rowsol, row_map_np) == res.total
-    cert = engine.lap_check(dev, res, rm)
-    assert cert["invalid_rows"] == 0 and cert["total"] == res.total
+def to_dev(engine, m):
+    ld = (m.shape[1] + 31) // 32 * 32
+    dev = torch.full((m.shape[0], ld), 2 ** 30 - 1, dtype=torch.int32, device=engine.device)
+    dev[:, :m.shape[1]] = torch.from_numpy(np.ascontiguousarray(m)).to(engine.device)
+    return dev
+
+
+def solve_and_check(engine, m, cap=None, grid=0):
+    """m: persons x objects.  Returns (LapResult, person_obj ndarray)."""
+    n_p, n_o = m.shape
+    dev = to_dev(engine, m)
+    res = engine.lap_solve(dev, cap, n_persons=n_p, n_objects=n_o, grid=grid)
+    po = res.person_obj.cpu().numpy(); so = res.slot_owner.cpu().numpy()
+    capv = np.ones(n_o, np.int64) if cap is None else np.asarray(cap)
+    assert po.min() >= 0 and po.max() < n_o
+    assert np.array_equal(np.bincount(po, minlength=n_o), capv), "capacities violated"
+    soff = np.concatenate([[0], np.cumsum(capv)])
+    assert sorted(so.tolist()) == list(range(n_p)), "slot_owner is not a permutation of the persons"
+    assert np.array_equal(np.repeat(np.arange(n_o), capv)[np.argsort(so)], po), "slot_owner inconsistent with person_obj"
+    assert int(m[np.arange(n_p), po].astype(np.int64).sum()) == res.total
+    cert = engine.lap_check(dev, res)
+    assert cert["invalid_rows"] == 0 and cert["capacity_mismatch"] == 0 and cert["total"] == res.total
     assert cert["max_violation"] <= 1, cert
-    return res, rowsol, colsol
+    return res, po
 
 
 @pytest.mark.parametrize("name", LAP_NAMES)
 def test_golden_instances(engine, lap_golden, name):
     cost = lap_golden[f"{name}_cost"]
-    res, rowsol, _ = solve_and_check(engine, cost)
+    res, po = solve_and_check(engine, cost)
     assert res.total == int(lap_golden[f"{name}_opt"])
+    res_t, _ = solve_and_check(engine, cost.T)               # either side may bid
+    assert res_t.total == res.total
 
 
 @pytest.mark.parametrize("n,high,seed", [(1, 10, 0), (2, 10, 1), (3, 5, 2), (31, 100, 3), (33, 2_000_000, 4),
@@ -41,27 +52,50 @@ def test_golden_instances(engine, lap_golden, name):
                                           (1023, 1000, 8), (2050, 2_000_000, 9)])
 def test_uniform_random_vs_oracle(engine, n, high, seed):
     cost = np.random.default_rng(seed).integers(-high, high, (n, n), dtype=np.int32)
-    res, _, _ = solve_and_check(engine, cost)
+    res, _ = solve_and_check(engine, cost)
     assert res.total == oracle.lapjv_i32(cost)[2][0]
 
 
 @pytest.mark.parametrize("grid", [1, 2, 7, 148])
 def test_result_independent_of_grid_size(engine, grid):
     cost = np.random.default_rng(11).integers(0, 10_000, (300, 300), dtype=np.int32)
-    ref, rowsol_ref, _ = solve_and_check(engine, cost, grid=0)
-    res, rowsol, _ = solve_and_check(engine, cost, grid=grid)
-    assert res.total == ref.total and np.array_equal(rowsol, rowsol_ref)      # deterministic tie-breaks
+    ref, po_ref = solve_and_check(engine, cost, grid=0)
+    res, po = solve_and_check(engine, cost, grid=grid)
+    assert res.total == ref.total and np.array_equal(po, po_ref)      # deterministic tie-breaks
 
 
-def test_row_map_expansion_cfg4_like(engine):
-    """Visium-like: S spots x cn cells per spot, rows resolved by index (LAS:63-66 never materialised)."""
-    from oracle import cost_oracle as co
-    sc, st, cn = syn.structured_counts(600, 100, 500, 6, seed=1004)
-    compact = co.cost_matrix_i32(co.normalize_data(sc), co.normalize_data(st))
-    row_map = np.repeat(np.arange(100, dtype=np.int32), 6)
-    res, _, _ = solve_and_check(engine, compact, row_map)
+def test_matches_cpu_model_of_the_device_algorithm(engine):
+    """Same tie-breaks as oracle/auction_model.c: identical assignment, not just identical total."""
+    rng = np.random.default_rng(3)
+    cap = rng.integers(0, 6, 70).astype(np.int32)
+    m = rng.integers(-1000, 1000, (int(cap.sum()), 70), dtype=np.int32)
+    res, po = solve_and_check(engine, m, cap)
+    po_model, so_model, tot_model, _, _, _ = oracle.auction_model(m, cap, tail_t=2)
+    assert res.total == tot_model and np.array_equal(po, po_model)
+    assert np.array_equal(res.slot_owner.cpu().numpy(), so_model)
+
+
+@pytest.mark.parametrize("n_obj,max_cap,seed", [(1, 7, 0), (5, 4, 1), (40, 6, 2), (333, 9, 3), (1000, 3, 4)])
+def test_capacitated_vs_expanded_oracle(engine, n_obj, max_cap, seed):
+    """Spots with cn cells each (incl. empty spots): optimum equals JV on the expanded matrix (LAS:63-66)."""
+    rng = np.random.default_rng(seed)
+    cap = rng.integers(0, max_cap + 1, n_obj).astype(np.int32)
+    cap[rng.integers(0, n_obj)] += 1
+    n = int(cap.sum())
+    compact = rng.integers(-50_000, 50_000, (n_obj, n), dtype=np.int32)        # spots x cells
+    res, po = solve_and_check(engine, np.ascontiguousarray(compact.T), cap)
+    row_map = np.repeat(np.arange(n_obj, dtype=np.int32), cap)
     assert res.total == oracle.lapjv_i32(compact, row_map)[2][0]
-    assert res.total == oracle.lapjv_i32(np.ascontiguousarray(compact[row_map]))[2][0]
+
+
+def test_visium_like_structured(engine):
+    """cfg4-shaped: S spots x 6 cells per spot on a correlation-built matrix."""
+    from oracle import cost_oracle as co
+    sc, st, cn = syn.structured_counts(1200, 200, 800, 6, seed=1004)
+    compact = co.cost_matrix_i32(co.normalize_data(sc), co.normalize_data(st))       # spots x cells
+    res, _ = solve_and_check(engine, np.ascontiguousarray(compact.T), cn.astype(np.int32))
+    row_map = np.repeat(np.arange(200, dtype=np.int32), 6)
+    assert res.total == oracle.lapjv_i32(compact, row_map)[2][0]
 
 
 def test_degenerate_inputs(engine):
@@ -69,14 +103,22 @@ def test_degenerate_inputs(engine):
                  np.tile(np.arange(40, dtype=np.int32), (40, 1)),            # identical rows
                  np.tile(np.arange(40, dtype=np.int32)[:, None], (1, 40)),   # identical columns
                  np.random.default_rng(1).integers(0, 2, (200, 200)).astype(np.int32)):
-        res, _, _ = solve_and_check(engine, cost)
+        res, _ = solve_and_check(engine, cost)
         assert res.total == oracle.lapjv_i32(cost)[2][0]
+    # one spot takes everything / duplicated cells (up-sampled, cytospace.py:278-281)
+    m = np.random.default_rng(2).integers(0, 100, (30, 1), dtype=np.int32)
+    res, po = solve_and_check(engine, m, np.array([30], np.int32))
+    assert res.total == int(m.sum()) and (po == 0).all()
+    base = np.random.default_rng(3).integers(-1000, 1000, (20, 60), dtype=np.int32)
+    dup = np.repeat(base, 3, axis=0)                                          # 60 persons, 3 copies each
+    res, _ = solve_and_check(engine, dup)
+    assert res.total == oracle.lapjv_i32(dup)[2][0]
 
 
 def test_extreme_cost_range(engine):
     lim = 2 ** 30 - 1
     cost = np.random.default_rng(5).integers(-lim, lim, (96, 96), dtype=np.int64).astype(np.int32)
-    res, _, _ = solve_and_check(engine, cost)
+    res, _ = solve_and_check(engine, cost)
     assert res.total == oracle.lapjv_i32(cost)[2][0]
 
 
@@ -85,20 +127,20 @@ def test_structured_cfg1_vs_oracle(engine):
     from oracle import cost_oracle as co
     sc, st, cn = syn.structured_counts(1000, 1000, 2000, 1, seed=1001)
     cost = co.cost_matrix_i32(co.normalize_data(sc), co.normalize_data(st))
-    res, _, _ = solve_and_check(engine, cost)
+    res, _ = solve_and_check(engine, np.ascontiguousarray(cost.T))
     assert res.total == oracle.lapjv_i32(cost)[2][0]
 
 
 def test_large_lap_properties_4k(engine):
     """Size-independent properties at a size the oracle still finishes quickly."""
     cost = syn.uniform_cost_i32(4096, seed=21)
-    res, rowsol, _ = solve_and_check(engine, cost)
+    res, _ = solve_and_check(engine, cost)
     assert res.total == oracle.lapjv_i32(cost)[2][0]
     # linearity: adding a row potential / column potential shifts the optimum by a known constant
     a = np.random.default_rng(1).integers(-1000, 1000, 4096).astype(np.int32)
     b = np.random.default_rng(2).integers(-1000, 1000, 4096).astype(np.int32)
     shifted = cost + a[:, None] + b[None, :]
-    res2, _, _ = solve_and_check(engine, shifted)
+    res2, _ = solve_and_check(engine, shifted)
     assert res2.total == res.total + int(a.sum()) + int(b.sum())
 
 
@@ -106,4 +148,7 @@ def test_lap_errors(engine):
     with pytest.raises(ValueError):
         engine.lap_solve(torch.zeros((4, 32), dtype=torch.float32, device=engine.device))
     with pytest.raises(ValueError):
-        engine.lap_solve(torch.zeros((4, 32), dtype=torch.int32, device=engine.device), n=40)
+        engine.lap_solve(torch.zeros((4, 32), dtype=torch.int32, device=engine.device), n_persons=40)
+    with pytest.raises(ValueError, match="square"):
+        engine.lap_solve(torch.zeros((4, 32), dtype=torch.int32, device=engine.device), np.array([1, 1]),
+                         n_persons=4, n_objects=2)

@@ -27,7 +27,7 @@ def test_solve_linear_assignment_problem_cfg1(engine):
     assert sorted(mapped) == list(range(1000))                     # cn == 1: a permutation of the spots
     spot_of_cell, res, cost = engine.assign(sc_n, st_n, cn)
     assert spot_of_cell.cpu().tolist() == mapped                   # deterministic
-    cost_np = cost[:, :1000].cpu().numpy()
+    cost_np = np.ascontiguousarray(cost[:, :1000].cpu().numpy())        # cn == 1: spots x cells on the device
     assert res.total == oracle_total_on(cost_np)
     # against the float64 reference formulation: the GPU assignment's float64 cost is within
     # n * 4e-6 of the float64 optimum (quantisation + fp16x3 tolerance)
@@ -45,7 +45,7 @@ def test_visium_like_repeated_spots(engine):
     assert np.array_equal(np.bincount(mapped, minlength=150), cn)   # every spot gets exactly cn cells
     _, res, cost = engine.assign(sc_n, st_n, cn)
     row_map = np.repeat(np.arange(150, dtype=np.int32), 6)
-    assert res.total == oracle_total_on(cost[:, :900].cpu().numpy(), row_map)
+    assert res.total == oracle_total_on(np.ascontiguousarray(cost[:, :150].T.cpu().numpy()), row_map)
 
 
 def test_uneven_capacities_and_empty_spots(engine):

@@ -26,8 +26,8 @@ def test_size_queries_without_gpu():
     assert lib.cyb_operand_k(20000, lib.CYB_PREC_F16) == 20032
     assert lib.cyb_operand_k(20000, lib.CYB_PREC_F16X3) == 3 * 20032
     assert lib.cyb_operand_k(64, lib.CYB_PREC_F16) == 64
-    assert lib.cyb_lap_workspace_bytes(1000) >= 1000 * 48
-    assert lib.cyb_lap_workspace_bytes(0) > 0
+    assert lib.cyb_lap_workspace_bytes(1000, 1000) >= 1000 * 48
+    assert lib.cyb_lap_workspace_bytes(0, 0) > 0
     need = lib.cyb_cost_build_workspace_bytes(2000, 1000, 1000, lib.CYB_PREC_F16X3)
     assert need >= 2 * 1000 * 3 * 2048 * 2
 
@@ -35,12 +35,15 @@ def test_size_queries_without_gpu():
 def test_native_argument_errors_without_gpu():
     """Argument validation happens before any CUDA call, so it is checkable on CPU."""
     lib, ffi = _native.load(), _native.ffi()
-    rc = lib.cyb_lap_solve_i32(ffi.NULL, 8, 8, ffi.NULL, ffi.NULL, ffi.NULL, ffi.NULL, ffi.NULL, ffi.NULL,
+    rc = lib.cyb_lap_solve_i32(ffi.NULL, 8, 8, 8, ffi.NULL, ffi.NULL, ffi.NULL, ffi.NULL, ffi.NULL, ffi.NULL,
                                ffi.NULL, 0, 0, ffi.NULL)
     assert rc == lib.CYB_ERR_INVALID and b"null" in ffi.string(lib.cyb_last_error())
-    rc = lib.cyb_lap_solve_i32(ffi.NULL, 8, 0, ffi.NULL, ffi.NULL, ffi.NULL, ffi.NULL, ffi.NULL, ffi.NULL,
+    rc = lib.cyb_lap_solve_i32(ffi.NULL, 8, 0, 0, ffi.NULL, ffi.NULL, ffi.NULL, ffi.NULL, ffi.NULL, ffi.NULL,
                                ffi.NULL, 0, 0, ffi.NULL)
     assert rc == lib.CYB_ERR_INVALID
+    rc = lib.cyb_lap_solve_i32(ffi.NULL, 8, 8, 4, ffi.NULL, ffi.NULL, ffi.NULL, ffi.NULL, ffi.NULL, ffi.NULL,
+                               ffi.NULL, 0, 0, ffi.NULL)
+    assert rc == lib.CYB_ERR_INVALID and b"square" in ffi.string(lib.cyb_last_error())
     rc = lib.cyb_cost_gemm_i32(ffi.cast("void *", 16), ffi.cast("void *", 16), 8, 8, 70, 1.0,
                                ffi.cast("int32_t *", 16), 8, ffi.NULL)
     assert rc == lib.CYB_ERR_INVALID           # k not a multiple of 64

@@ -37,8 +37,10 @@ def test_f64_restatement_and_auction_model(lap_golden, name):
     opt = int(lap_golden[f"{name}_opt"])
     _, colsol, (total, _, _) = oracle.lapjv_f64(cost.astype(np.float64))
     assert int(round(total)) == opt
-    rs, cs, tot, price, stats, _ = oracle.auction_model(cost)
-    assert tot == opt and sorted(rs.tolist()) == list(range(cost.shape[0]))
+    for tail in (0, 2):
+        po, so, tot, lam, stats, _ = oracle.auction_model(cost, tail_t=tail)       # persons = rows
+        assert tot == opt and sorted(po.tolist()) == list(range(cost.shape[0]))
+        assert np.array_equal(so[po], np.arange(cost.shape[0]))
 
 
 @settings(max_examples=60, deadline=None)
@@ -51,6 +53,30 @@ def test_jv_total_equals_scipy_property(n, seed, high):
     assert total == int(cost[ri, ci].astype(np.int64).sum())
     check_solution(cost, rowsol, colsol, total, u, v)
     assert oracle.auction_model(cost)[2] == total
+
+
+@settings(max_examples=80, deadline=None)
+@given(st.integers(1, 10), st.integers(0, 2 ** 31 - 1), st.sampled_from([2, 10, 1000, 2_000_000]), st.sampled_from([0, 2, 64]))
+def test_capacitated_auction_model_equals_expanded_jv(n_obj, seed, high, tail):
+    """The device algorithm (capacitated objects = spots with cn cells, transposed matrix) reaches the
+    optimum of the reference's expanded LAP (LAS:63-66) -- including empty spots (cn == 0)."""
+    rng = np.random.default_rng(seed)
+    cap = rng.integers(0, 5, n_obj).astype(np.int32)
+    if cap.sum() == 0:
+        cap[0] = 1
+    n = int(cap.sum())
+    compact = rng.integers(-high, high, (n_obj, n), dtype=np.int32)           # spots x cells (reference orientation)
+    row_map = np.repeat(np.arange(n_obj, dtype=np.int32), cap)
+    want = oracle.lapjv_i32(compact, row_map)[2][0]
+    po, so, tot, lam, stats, _ = oracle.auction_model(np.ascontiguousarray(compact.T), cap, tail_t=tail)
+    assert tot == want
+    assert np.array_equal(np.bincount(po, minlength=n_obj), cap)
+    soff = np.concatenate([[0], np.cumsum(cap)])
+    for o in range(n_obj):
+        assert sorted(so[soff[o]:soff[o + 1]].tolist()) == sorted(np.nonzero(po == o)[0].tolist())
+    # eps-CS certificate with eps = 1 in units of 1/(n+1)
+    h = (compact.T.astype(object) - int(compact.min())) * (n + 1) + np.array([int(x) for x in lam], dtype=object)[None, :]
+    assert max(h[i, po[i]] - min(h[i]) for i in range(n)) <= 1
 
 
 def test_jv_row_map_equals_materialised_expansion():
