@@ -50,6 +50,7 @@
 // HBM traffic: each bid reads one row (O*4 bytes) once; prices, holders, lists
 // and bid words live in shared memory / L2.
 
+#include <algorithm>
 #include <climits>
 #include <cstdint>
 #include <cstdlib>
@@ -66,6 +67,8 @@ constexpr long long kBidLimit = 1ll << 45;                     // 46-bit bid fie
 constexpr int kTheta = 8;
 constexpr int kEps0Div = 4;
 constexpr int kTailMax = 64;                                   // capacity of the tail FIFO
+constexpr int kListK = 64;                                     // candidate-list capacity per person
+constexpr unsigned kGenMask = 0x3FFF;                          // 14-bit generation tag above the 18-bit object index
 
 struct LapParams {
     const int32_t *cost;     // M: persons x objects
@@ -89,6 +92,15 @@ struct LapParams {
     int qcap;
     long long max_rounds;
     int tail_t;              // rounds with <= tail_t bidders are finished by CTA 0 alone
+    // candidate lists (tail accelerator): per person a header {bound, gen<<32 | n} and kListK entries
+    // (object | gen << 18, cost).  Every object NOT in the list had value >= bound when the list was
+    // built; prices never decrease, so that stays true and a list evaluation whose best two values are
+    // < bound returns exactly what a full row scan would.
+    longlong2 *lst_hdr;
+    int2 *lst_ent;
+    int use_lists;
+    int sweepers;            // CTAs that rebuild lists during a tail (<= G-1)
+    int smem_owner;          // 1: CTA 0 keeps the holder of every object in shared memory during a tail (unit capacities)
 };
 
 struct Best {
@@ -96,10 +108,17 @@ struct Best {
     int j1;
 };
 
-__device__ __forceinline__ int4 ld_stream(const int4 *p) {
+// Row data is streamed: no L1 allocation, and L2 lines marked evict-first so that the matrix
+// stream does not push the (hot, small) prices / holders / candidate lists out of L2.
+__device__ __forceinline__ unsigned long long l2_policy_evict_first() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ int4 ld_stream(const int4 *p, unsigned long long pol) {
     int4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.s32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(pol));
     return r;
 }
 
@@ -162,13 +181,14 @@ __device__ __forceinline__ Best scan_row(const int32_t *__restrict__ r, int n, i
                                          long long *red_b1, long long *red_b2, int *red_j) {
     Best s{LLONG_MAX, LLONG_MAX, -1};
     const int t = threadIdx.x;
+    const unsigned long long pol = l2_policy_evict_first();
     int jtail = 0;
     if (vec_ok) {
         const int4 *r4 = reinterpret_cast<const int4 *>(r);
         const int n4 = n >> 2;
 #pragma unroll 4
         for (int q = t; q < n4; q += kThreads) {
-            const int4 c = ld_stream(r4 + q);
+            const int4 c = ld_stream(r4 + q, pol);
             const int j = q << 2;
             long long p0, p1, p2, p3;
             if (SMEMP) {
@@ -231,6 +251,127 @@ __device__ __forceinline__ void cheapest_slot(const LapParams &P, int o, int t_n
     }
 }
 
+// Sweeper side: rebuild person i's candidate list from one CTA-wide pass over its row.  Each
+// thread keeps the best / second-best value of ITS columns; bound = the smallest per-thread
+// second-best; the list = the per-thread bests below bound.  Any other object is either some
+// thread's non-best (value >= that thread's second-best >= bound) or a best >= bound.  Prices may be
+// stale (lower than current): the bound is then merely weaker, never wrong.
+template <bool SMEMP>
+__device__ __forceinline__ void build_list(const LapParams &P, int i, const int32_t *__restrict__ r, int n, int cmin,
+                                           long long S, const long long *__restrict__ price, bool vec_ok,
+                                           long long *red_b2, int *wcnt) {
+    Best s{LLONG_MAX, LLONG_MAX, -1};
+    const int t = threadIdx.x;
+    const unsigned long long pol = l2_policy_evict_first();
+    int jtail = 0;
+    if (vec_ok) {
+        const int4 *r4 = reinterpret_cast<const int4 *>(r);
+        const int n4 = n >> 2;
+#pragma unroll 4
+        for (int q = t; q < n4; q += kThreads) {
+            const int4 c = ld_stream(r4 + q, pol);
+            const int j = q << 2;
+            long long p0, p1, p2, p3;
+            if (SMEMP) {
+                const longlong2 a = *reinterpret_cast<const longlong2 *>(price + j);
+                const longlong2 b = *reinterpret_cast<const longlong2 *>(price + j + 2);
+                p0 = a.x; p1 = a.y; p2 = b.x; p3 = b.y;
+            } else {
+                const longlong2 a = __ldcg(reinterpret_cast<const longlong2 *>(price + j));
+                const longlong2 b = __ldcg(reinterpret_cast<const longlong2 *>(price + j + 2));
+                p0 = a.x; p1 = a.y; p2 = b.x; p3 = b.y;
+            }
+            upd(s, (long long)(c.x - cmin) * S + p0, j);
+            upd(s, (long long)(c.y - cmin) * S + p1, j + 1);
+            upd(s, (long long)(c.z - cmin) * S + p2, j + 2);
+            upd(s, (long long)(c.w - cmin) * S + p3, j + 3);
+        }
+        jtail = n4 << 2;
+    }
+    for (int j = jtail + t; j < n; j += kThreads) {
+        const long long p = SMEMP ? price[j] : __ldcg(price + j);
+        upd(s, (long long)(__ldg(r + j) - cmin) * S + p, j);
+    }
+    long long m = s.b2;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, d));
+    if ((t & 31) == 0) red_b2[t >> 5] = m;
+    __syncthreads();
+    m = red_b2[t & 31];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, d));
+    const long long bound = m;
+    const bool q = s.j1 >= 0 && s.b1 < bound;
+    int total;
+    const int pos = block_excl_count(q, wcnt, total);              // two __syncthreads inside
+    const unsigned gen = ((unsigned)((unsigned long long)__ldcg(&P.lst_hdr[i].y) >> 32) + 1u) & kGenMask;
+    if (total <= kListK) {
+        if (q) P.lst_ent[(long long)i * kListK + pos] = make_int2(s.j1 | (int)(gen << kPersonBits), __ldg(r + s.j1));
+        __threadfence();
+    }
+    __syncthreads();
+    if (t == 0) {
+        longlong2 h;
+        h.x = bound;
+        h.y = (long long)(((unsigned long long)gen << 32) | (unsigned long long)(total <= kListK ? total : 0));
+        P.lst_hdr[i] = h;
+    }
+}
+
+// Leader side (one warp): evaluate person i's list against the current prices.  Returns true with
+// the exact (b1, j1, b2) of a full scan in every lane when the result is certified, false otherwise
+// (no list, torn list, or the second-best candidate is not below the bound).
+template <bool SMEMP>
+__device__ __forceinline__ bool list_try(const LapParams &P, int i, int cmin, long long S,
+                                         const long long *__restrict__ price, Best &out) {
+    const int lane = threadIdx.x & 31;
+    // header and entries are fetched together (one L2 round trip); entries beyond n are ignored
+    const int2 *e = P.lst_ent + (long long)i * kListK;
+    int2 v[kListK / 32];
+#pragma unroll
+    for (int k = 0; k < kListK / 32; ++k) v[k] = __ldcg(e + lane + 32 * k);
+    const longlong2 h = __ldcg(&P.lst_hdr[i]);
+    const int n = (int)((unsigned long long)h.y & 0xFFFFFFFFull);
+    const unsigned gen = (unsigned)((unsigned long long)h.y >> 32);
+    if (n < 2) return false;
+    bool ok = true;
+    // Values are compared as 64-bit keys (value << 18 | object): lexicographic (value, object) order,
+    // valid while every value is < 2^46 (guaranteed when the scaled cost range is < 2^45, see `pack_ok`).
+    unsigned long long k1 = ~0ull, k2 = ~0ull;
+#pragma unroll
+    for (int k = 0; k < kListK / 32; ++k) {
+        const int q = lane + 32 * k;
+        if (q < n) {
+            const int o = v[k].x & (int)kPersonMask;
+            ok = ok && ((unsigned)v[k].x >> kPersonBits) == gen && o < P.O;
+            const long long p = SMEMP ? price[ok ? o : 0] : __ldcg(price + (ok ? o : 0));
+            const long long hv = (long long)(v[k].y - cmin) * S + p;
+            ok = ok && hv >= 0 && hv < (1ll << 46);
+            const unsigned long long key = ((unsigned long long)hv << kPersonBits) | (unsigned)o;
+            if (key < k1) { k2 = k1; k1 = key; }
+            else if (key < k2) k2 = key;
+        }
+    }
+    if (!__all_sync(0xffffffffu, ok)) return false;
+    // warp minimum of a 64-bit key with two 32-bit REDUX steps (high word, then low word among the
+    // lanes that hold the minimal high word)
+    auto warp_min64 = [](unsigned long long key) -> unsigned long long {
+        const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+        const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
+        const unsigned mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xFFFFFFFFu);
+        return ((unsigned long long)mhi << 32) | mlo;
+    };
+    const unsigned long long w1 = warp_min64(k1);
+    const unsigned long long w2 = warp_min64(k1 == w1 ? k2 : k1);      // keys are unique (distinct objects)
+    if (w2 == ~0ull) return false;
+    Best s;
+    s.b1 = (long long)(w1 >> kPersonBits); s.j1 = (int)(w1 & kPersonMask);
+    s.b2 = (long long)(w2 >> kPersonBits);
+    if (!(s.b2 < h.x)) return false;
+    out = s;
+    return true;
+}
+
 template <bool SMEMP>
 __global__ void __launch_bounds__(kThreads, 1) lap_auction_kernel(const LapParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -238,9 +379,10 @@ __global__ void __launch_bounds__(kThreads, 1) lap_auction_kernel(const LapParam
     long long *sprice = reinterpret_cast<long long *>(smem_raw);
     size_t off = SMEMP ? ((size_t)no * 8 + 15) / 16 * 16 : 0;
     int *myq = reinterpret_cast<int *>(smem_raw + off);
+    int *sowner = myq + ((P.qcap + 3) & ~3);          // only used by CTA 0 when P.smem_owner
     __shared__ long long red_b1[32], red_b2[32];
     __shared__ int red_j[32], wcnt[32];
-    __shared__ int tq[kTailMax], tq_head, tq_cnt, tq_status;
+    __shared__ int tq[kTailMax], tq_head, tq_cnt, tq_status, sw_stop;
 
     const int G = gridDim.x, b = blockIdx.x, t = threadIdx.x;
     const long long S = (long long)np + 1;
@@ -269,6 +411,7 @@ __global__ void __launch_bounds__(kThreads, 1) lap_auction_kernel(const LapParam
         if ((t & 31) == 0 && lmin <= lmax) { atomicMin(P.gmm + 0, lmin); atomicMax(P.gmm + 1, lmax); }
         for (int i = b * kThreads + t; i < np; i += G * kThreads) {
             P.slot_price[i] = 0; P.slot_owner[i] = -1; P.person_obj[i] = -1; P.person_slot[i] = -1;
+            P.lst_hdr[i] = make_longlong2(LLONG_MIN, 0);       // no list yet
         }
         for (int o = b * kThreads + t; o < no; o += G * kThreads) {
             P.lambda[o] = capacity(o) > 0 ? 0 : kInf;          // a spot that takes no cell is priced out
@@ -282,11 +425,14 @@ __global__ void __launch_bounds__(kThreads, 1) lap_auction_kernel(const LapParam
     long long eps = ((long long)cmax - (long long)cmin) * S / kEps0Div;
     if (eps < 1) eps = 1;
 
-    long long rounds = 0, bids = 0, passes = 0, phases = 0, rounds1 = 0, maxF = 0, tail_bids = 0, tails = 0;
+    long long rounds = 0, bids = 0, passes = 0, phases = 0, rounds1 = 0, maxF = 0, tail_bids = 0, tails = 0, list_hits = 0;
     int status = 0;
     int cur = 0;             // buffer of the current round; the previous round used (cur + 2) % 3
     int prevF = 0;           // records of the previous round (their bid words are cleared in this resolve)
     const int tail_t = min(P.tail_t, kTailMax);
+    // candidate-list keys pack (value << 18 | object): needs every value < 2^46, i.e. scaled costs < 2^45
+    // (prices are bounded by kBidLimit = 2^45 already)
+    const bool use_lists = P.use_lists && G > 1 && ((long long)cmax - (long long)cmin + 1) * S < (1ll << 45);
 
     for (;;) {
         ++phases;
@@ -354,24 +500,24 @@ __global__ void __launch_bounds__(kThreads, 1) lap_auction_kernel(const LapParam
                 if (b == 0) {
                     if (t < F) tq[t] = __ldcg(P.list[cur] + t);
                     if (t == 0) { tq_head = 0; tq_cnt = F; tq_status = 0; }
+                    if (P.smem_owner) for (int o = t; o < no; o += kThreads) sowner[o] = __ldcg(P.slot_owner + o);
                     __syncthreads();
                     while (tq_cnt > 0 && tq_status == 0) {
-                        const int i = tq[tq_head];
-                        const Best s = scan_row<SMEMP>(rowptr(i), no, cmin, S, price_rd, vec_ok, red_b1, red_b2, red_j);
-                        ++tail_bids;
-                        if (t == 0) {
+                        // one bid: thread 0 books the result `s` of person i's scan (list or full row)
+                        auto book = [&](int i, const Best &s) {
                             const int o = s.j1;
                             const long long lam = SMEMP ? sprice[o] : __ldcg(P.lambda + o);
                             const long long bid = lam + (s.b2 < kInf / 2 ? s.b2 - s.b1 : 0) + eps;
                             if (bid >= kBidLimit) tq_status = CYB_ERR_OVERFLOW;
                             if (tail_bids + rounds > P.max_rounds) tq_status = CYB_ERR_NOT_CONVERGED;
-                            const int slot = __ldcg(P.minslot + o);
-                            const int prev = __ldcg(P.slot_owner + slot);
+                            const int slot = P.soff ? __ldcg(P.minslot + o) : o;
+                            const int prev = P.smem_owner ? sowner[o] : __ldcg(P.slot_owner + slot);
+                            if (P.smem_owner) sowner[o] = i;
                             P.slot_owner[slot] = i; P.slot_price[slot] = bid;
                             P.person_obj[i] = o; P.person_slot[i] = slot;
-                            int ms; long long mp;
-                            cheapest_slot(P, o, slot, bid, ms, mp);
-                            P.minslot[o] = ms; P.lambda[o] = mp;
+                            long long mp = bid;
+                            if (P.soff) { int ms; cheapest_slot(P, o, slot, bid, ms, mp); P.minslot[o] = ms; }
+                            P.lambda[o] = mp;
                             if (SMEMP) sprice[o] = mp;
                             int head = tq_head + 1; if (head == kTailMax) head = 0;
                             int cnt = tq_cnt - 1;
@@ -381,10 +527,57 @@ __global__ void __launch_bounds__(kThreads, 1) lap_auction_kernel(const LapParam
                                 tq[tail] = prev; ++cnt;
                             }
                             tq_head = head; tq_cnt = cnt;
+                        };
+                        if (use_lists) {
+                            // warp 0 alone serves bids from the candidate lists the sweeper CTAs keep
+                            // fresh, until one cannot be certified; the other warps wait at the barrier
+                            if (t < 32) {
+                                while (tq_cnt > 0 && tq_status == 0) {
+                                    const int i = tq[tq_head];
+                                    Best s;
+                                    if (!list_try<SMEMP>(P, i, cmin, S, price_rd, s)) break;
+                                    ++list_hits;
+                                    ++tail_bids;
+                                    if (t == 0) book(i, s);
+                                    __syncwarp();
+                                }
+                            }
+                            __syncthreads();
+                            if (!(tq_cnt > 0 && tq_status == 0)) break;
                         }
+                        const int i = tq[tq_head];
+                        const Best s = scan_row<SMEMP>(rowptr(i), no, cmin, S, price_rd, vec_ok, red_b1, red_b2, red_j);
+                        ++tail_bids;
+                        if (t == 0) book(i, s);
                         __syncthreads();
                     }
-                    if (t == 0 && tq_status) atomicExch(P.gmm + 2, tq_status);
+                    if (t == 0) {
+                        if (tq_status) atomicExch(P.gmm + 2, tq_status);
+                        __threadfence();
+                        asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(P.gmm + 3), "r"((int)tails) : "memory");
+                    }
+                } else if (use_lists && b <= P.sweepers) {
+                    // ---- sweepers: while CTA 0 runs the tail, the idle CTAs keep re-deriving candidate
+                    // lists (person i belongs to CTA 1 + i mod (G-1)) against the prices CTA 0 publishes.
+                    // Purely speculative: a list only ever short-cuts a scan whose result it reproduces
+                    // exactly, so neither timing nor staleness can change the assignment.
+                    bool stop = false;
+                    while (!stop) {
+                        if (SMEMP) {
+                            for (int o = t; o < no; o += kThreads) sprice[o] = __ldcg(P.lambda + o);
+                            __syncthreads();
+                        }
+                        for (int i = b - 1; i < np; i += P.sweepers) {
+                            if (t == 0) {
+                                int v;
+                                asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(P.gmm + 3) : "memory");
+                                sw_stop = (v >= (int)tails);
+                            }
+                            __syncthreads();
+                            if (sw_stop) { stop = true; break; }
+                            build_list<SMEMP>(P, i, rowptr(i), no, cmin, S, price_rd, vec_ok, red_b2, wcnt);
+                        }
+                    }
                 }
                 F = 0;
                 break;
@@ -491,7 +684,7 @@ __global__ void __launch_bounds__(kThreads, 1) lap_auction_kernel(const LapParam
         P.stats[0] = status; P.stats[1] = phases; P.stats[2] = rounds; P.stats[3] = bids;
         P.stats[4] = passes; P.stats[5] = cmin; P.stats[6] = cmax; P.stats[7] = S;
         P.stats[8] = G; P.stats[9] = SMEMP ? 1 : 0; P.stats[10] = rounds1; P.stats[11] = maxF;
-        P.stats[12] = (phases - 1) * (long long)np; P.stats[13] = tail_bids; P.stats[14] = tails; P.stats[15] = 0;
+        P.stats[12] = (phases - 1) * (long long)np; P.stats[13] = tail_bids; P.stats[14] = tails; P.stats[15] = list_hits;
     }
 }
 
@@ -512,6 +705,7 @@ __global__ void __launch_bounds__(kChkThreads) lap_rowmin_kernel(
     for (int j = threadIdx.x; j < nc; j += kChkThreads) sp[j] = price[c0 + j];
     __syncthreads();
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const unsigned long long pol = l2_policy_evict_first();
     const int r0 = blockIdx.y * rows_per_cta;
     const int r1 = min(np, r0 + rows_per_cta);
     const bool vec_ok = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(cost) & 15) == 0);
@@ -524,7 +718,7 @@ __global__ void __launch_bounds__(kChkThreads) lap_rowmin_kernel(
             const int n4 = nc >> 2;
 #pragma unroll 4
             for (int q = lane; q < n4; q += 32) {
-                const int4 c = ld_stream(r4 + q);
+                const int4 c = ld_stream(r4 + q, pol);
                 const longlong2 a = *reinterpret_cast<const longlong2 *>(sp + 4 * q);
                 const longlong2 bb = *reinterpret_cast<const longlong2 *>(sp + 4 * q + 2);
                 m = min(m, (long long)c.x * S + a.x);
@@ -581,7 +775,7 @@ __global__ void lap_check_capacity_kernel(const int32_t *__restrict__ soff, int 
 }
 
 struct WsLayout {
-    size_t list[3], rec[3], bidw[3], flag, slot_price, person_slot, minslot, rowmin, count, small, total;
+    size_t list[3], rec[3], bidw[3], flag, slot_price, person_slot, minslot, rowmin, count, lst_hdr, lst_ent, small, total;
 };
 
 WsLayout ws_layout(int64_t np, int64_t no) {
@@ -597,6 +791,8 @@ WsLayout ws_layout(int64_t np, int64_t no) {
     L.minslot = take((size_t)no * 4);
     L.rowmin = take((size_t)np * 8);
     L.count = take((size_t)no * 4);
+    L.lst_hdr = take((size_t)np * 16);
+    L.lst_ent = take((size_t)np * kListK * 8);
     L.small = take(256);
     L.total = o;
     return L;
@@ -664,25 +860,36 @@ extern "C" int cyb_lap_solve_i32(const int32_t *cost_dev, int64_t ld, int64_t n_
     P.gmm = reinterpret_cast<int *>(ws + L.small + 16);
     P.qcap = (int)((np + G - 1) / G);
     P.max_rounds = 2000ll * np + 100000;
-    P.tail_t = 2;
+    P.lst_hdr = reinterpret_cast<longlong2 *>(ws + L.lst_hdr);
+    P.lst_ent = reinterpret_cast<int2 *>(ws + L.lst_ent);
+    P.tail_t = 8;
+    P.use_lists = 1;
     if (const char *e = getenv("CYB_LAP_TAIL")) P.tail_t = atoi(e);
+    if (const char *e = getenv("CYB_LAP_LISTS")) P.use_lists = atoi(e);
 
     // small block: barrier counter, cmin = INT_MAX, cmax = INT_MIN, status = 0
-    const int init[8] = {0, 0, 0, 0, INT_MAX, INT_MIN, 0, 0};
+    const int init[8] = {0, 0, 0, 0, INT_MAX, INT_MIN, 0, 0};      // gmm[3] = tails finished
     CYB_CUDA_CHECK(cudaMemcpyAsync(ws + L.small, init, sizeof(init), cudaMemcpyHostToDevice, stream));
     CYB_CUDA_CHECK(cudaMemsetAsync(total_dev, 0, sizeof(int64_t), stream));
 
     const size_t q_bytes = cyb::align_up((size_t)P.qcap * 4, 16);
     const size_t smem_with_price = cyb::align_up((size_t)no * 8, 16) + q_bytes;
-    const size_t static_smem = 32 * 8 * 2 + 32 * 4 * 2 + kTailMax * 4 + 128;
+    const size_t static_smem = 32 * 8 * 2 + 32 * 4 * 2 + kTailMax * 4 + 160;
     const bool smemp = smem_with_price + static_smem <= (size_t)max_smem;
-    const size_t dyn = smemp ? smem_with_price : q_bytes;
+    size_t dyn = smemp ? smem_with_price : q_bytes;
+    const size_t owner_bytes = cyb::align_up((size_t)no * 4, 16);
+    P.smem_owner = (!slot_offset_dev && dyn + owner_bytes + static_smem <= (size_t)max_smem) ? 1 : 0;
+    if (P.smem_owner) dyn += owner_bytes;
+
     const void *fn = smemp ? (const void *)lap_auction_kernel<true> : (const void *)lap_auction_kernel<false>;
     CYB_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
     int occ = 0;
     CYB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kThreads, dyn));
     if (occ < 1) return cyb::set_error(CYB_ERR_UNSUPPORTED, "lap kernel does not fit on an SM (smem %zu)", dyn);
     if (G > occ * sms) G = occ * sms;
+    P.sweepers = G - 1;
+    if (const char *e = getenv("CYB_LAP_SWEEPERS")) P.sweepers = std::max(1, std::min(G - 1, atoi(e)));
+    if (G < 2) P.use_lists = 0;
     void *args[] = {(void *)&P};
     CYB_CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(G), dim3(kThreads), args, dyn, stream));
     CYB_CUDA_CHECK(cudaGetLastError());

@@ -23,7 +23,7 @@ from . import _native
 COST_SCALE = 10 ** 6           # integer scale of the correlation distance; precedent cytospace.py:337
 PRECISIONS = {"f16": 0, "f16x3": 1}
 STAT_NAMES = ("status", "phases", "rounds", "bids", "passes", "cost_min", "cost_max", "scale",
-              "grid", "smem_prices", "rounds_le1", "max_bidders", "phase_scans", "tail_bids", "tails")
+              "grid", "smem_prices", "rounds_le1", "max_bidders", "phase_scans", "tail_bids", "tails", "list_hits")
 
 
 def _round_up(x: int, a: int) -> int:

@@ -69,7 +69,7 @@ extern "C" {
  *  [10] rounds with <= 1 bidder [11] max bidders in a round
  *  [12] row scans at phase starts (rows whose pair was re-checked)
  *  [13] bids made in Gauss-Seidel tails (one CTA, no grid barrier)  [14] tails run
- *  [15] reserved */
+ *  [15] tail bids served from a candidate list (no row scan) */
 
 int         cyb_abi_version(void);
 const char *cyb_last_error(void);

@@ -28,6 +28,13 @@
 #include <string.h>
 
 #define AUCTION_INF ((int64_t)1 << 60)
+/* candidate-list experiment (tail only): groups of columns as the device scan assigns them to threads */
+int64_t auction_list_hits = 0, auction_list_miss = 0;
+int auction_list_groups = 0;       /* 0 = lists off; else number of groups (32 = warps, 1024 = threads) */
+int auction_list_cap = 64;
+int auction_list_refresh = 0;   /* >0: every R tail bids all persons' lists are rebuilt at current prices (idle-CTA sweep model) */
+#define LIST_MAX 1024
+typedef struct { int n; int64_t bound; int32_t obj[LIST_MAX]; } cand_t;
 #define GAP(b1, b2) (((b2) >= AUCTION_INF / 2) ? 0 : (b2) - (b1))   /* no alternative object: bid eps */
 
 /* stats[0]=phases, [1]=rounds, [2]=bids (row scans), [3]=full-matrix passes,
@@ -57,6 +64,8 @@ int auction_model_i32(int P, int O, const int32_t *m, int64_t ld, const int32_t 
     int64_t *bidp = (int64_t *)malloc(sizeof(int64_t) * (size_t)O);
     int32_t *bidr = (int32_t *)malloc(sizeof(int32_t) * (size_t)O);
     int32_t *kobj = (int32_t *)malloc(sizeof(int32_t) * (size_t)P);
+    cand_t *lists = auction_list_groups ? (cand_t *)calloc((size_t)P, sizeof(cand_t)) : NULL;
+    int64_t gb1[1024], gb2[1024]; int gj[1024];
     /* an object without capacity (a spot that takes no cell, cytospace.py:686-694) is priced out */
     for (int o = 0; o < O; ++o) { lambda[o] = (soff[o + 1] > soff[o]) ? 0 : AUCTION_INF; minslot[o] = soff[o]; bidr[o] = -1; }
     for (int t = 0; t < P; ++t) slot_owner[t] = -1;
@@ -125,7 +134,77 @@ int auction_model_i32(int P, int O, const int32_t *m, int64_t ld, const int32_t 
                 while (cnt > 0) {
                     const int i = freel[head]; head = (head + 1) % P; --cnt;
                     int64_t b1, b2; int o1;
-                    SCAN(i, b1, b2, o1);
+                    int done = 0;
+                    if (auction_list_groups > 0 && lists && auction_list_refresh > 0 && (st[5] % auction_list_refresh) == 0) {
+                        const int Gn = auction_list_groups;
+                        for (int p_ = 0; p_ < P; ++p_) {
+                            const int32_t *r_ = m + (size_t)p_ * ld;
+                            for (int g = 0; g < Gn; ++g) { gb1[g] = INT64_MAX; gb2[g] = INT64_MAX; gj[g] = -1; }
+                            for (int o_ = 0; o_ < O; ++o_) {
+                                const int g = (Gn == 32) ? (((o_ >> 2) % 1024) >> 5) : ((o_ >> 2) % Gn);
+                                const int64_t h_ = (int64_t)(r_[o_] - cmin) * S + lambda[o_];
+                                if (h_ < gb1[g]) { gb2[g] = gb1[g]; gb1[g] = h_; gj[g] = o_; }
+                                else if (h_ < gb2[g]) gb2[g] = h_;
+                            }
+                            int64_t bound = INT64_MAX;
+                            for (int g = 0; g < Gn; ++g) if (gb2[g] < bound) bound = gb2[g];
+                            int cntq = 0;
+                            for (int g = 0; g < Gn; ++g) if (gj[g] >= 0 && gb1[g] < bound) ++cntq;
+                            lists[p_].n = 0; lists[p_].bound = bound;
+                            if (cntq <= auction_list_cap && cntq <= LIST_MAX)
+                                for (int g = 0; g < Gn; ++g) if (gj[g] >= 0 && gb1[g] < bound) lists[p_].obj[lists[p_].n++] = gj[g];
+                        }
+                    }
+                    if (auction_list_groups && lists && lists[i].n > 0) {
+                        const int32_t *r_ = m + (size_t)i * ld;
+                        b1 = INT64_MAX; b2 = INT64_MAX; o1 = -1;
+                        for (int q = 0; q < lists[i].n; ++q) {
+                            const int o_ = lists[i].obj[q];
+                            const int64_t h_ = (int64_t)(r_[o_] - cmin) * S + lambda[o_];
+                            if (h_ < b1 || (h_ == b1 && o_ < o1)) { b2 = b1; b1 = h_; o1 = o_; }
+                            else if (h_ < b2) b2 = h_;
+                        }
+                        if (b2 < lists[i].bound) { done = 1; ++auction_list_hits; }
+                    }
+                    if (!done) {
+                        SCAN(i, b1, b2, o1);
+                        if (auction_list_groups && lists) {
+                            ++auction_list_miss;
+                            const int32_t *r_ = m + (size_t)i * ld;
+                            if (auction_list_groups < 0) {
+                                /* exact top-K (K = -groups <= LIST_MAX): bound = (K+1)-th smallest value */
+                                const int K = -auction_list_groups;
+                                int64_t hv[LIST_MAX + 1]; int ho[LIST_MAX + 1]; int nn = 0;
+                                for (int o_ = 0; o_ < O; ++o_) {
+                                    const int64_t h_ = (int64_t)(r_[o_] - cmin) * S + lambda[o_];
+                                    if (nn <= K || h_ < hv[nn - 1]) {
+                                        int p_ = nn < K + 1 ? nn++ : nn - 1;
+                                        while (p_ > 0 && hv[p_ - 1] > h_) { hv[p_] = hv[p_ - 1]; ho[p_] = ho[p_ - 1]; --p_; }
+                                        hv[p_] = h_; ho[p_] = o_;
+                                    }
+                                }
+                                lists[i].n = 0; lists[i].bound = nn > K ? hv[K] : INT64_MAX;
+                                for (int q = 0; q < (nn > K ? K : nn); ++q) lists[i].obj[lists[i].n++] = ho[q];
+                            } else {
+                            /* rebuild: per-group best / second best */
+                            const int Gn = auction_list_groups;
+                            for (int g = 0; g < Gn; ++g) { gb1[g] = INT64_MAX; gb2[g] = INT64_MAX; gj[g] = -1; }
+                            for (int o_ = 0; o_ < O; ++o_) {
+                                const int g = (Gn == 32) ? (((o_ >> 2) % 1024) >> 5) : ((o_ >> 2) % Gn);
+                                const int64_t h_ = (int64_t)(r_[o_] - cmin) * S + lambda[o_];
+                                if (h_ < gb1[g]) { gb2[g] = gb1[g]; gb1[g] = h_; gj[g] = o_; }
+                                else if (h_ < gb2[g]) gb2[g] = h_;
+                            }
+                            int64_t bound = INT64_MAX;
+                            for (int g = 0; g < Gn; ++g) if (gb2[g] < bound) bound = gb2[g];
+                            int cntq = 0;
+                            for (int g = 0; g < Gn; ++g) if (gj[g] >= 0 && gb1[g] < bound) ++cntq;
+                            lists[i].n = 0; lists[i].bound = bound;
+                            if (cntq <= auction_list_cap && cntq <= LIST_MAX)
+                                for (int g = 0; g < Gn; ++g) if (gj[g] >= 0 && gb1[g] < bound) lists[i].obj[lists[i].n++] = gj[g];
+                            }
+                        }
+                    }
                     const int64_t bid = lambda[o1] + GAP(b1, b2) + eps;
                     const int t = minslot[o1];
                     const int old = slot_owner[t];
@@ -180,6 +259,6 @@ int auction_model_i32(int P, int O, const int32_t *m, int64_t ld, const int32_t 
     if (total) *total = tot;
     if (stats) memcpy(stats, st, sizeof(st));
     free(soff); free(slot_price); free(minslot); free(person_slot); free(freel); free(nextl);
-    free(bidp); free(bidr); free(kobj);
+    free(bidp); free(bidr); free(kobj); free(lists);
     return 0;
 }

@@ -69,7 +69,12 @@ def test_matches_cpu_model_of_the_device_algorithm(engine):
     rng = np.random.default_rng(3)
     cap = rng.integers(0, 6, 70).astype(np.int32)
     m = rng.integers(-1000, 1000, (int(cap.sum()), 70), dtype=np.int32)
-    res, po = solve_and_check(engine, m, cap)
+    import os
+    os.environ["CYB_LAP_TAIL"] = "2"                   # same Jacobi / Gauss-Seidel switch point as the model run
+    try:
+        res, po = solve_and_check(engine, m, cap)
+    finally:
+        del os.environ["CYB_LAP_TAIL"]
     po_model, so_model, tot_model, _, _, _ = oracle.auction_model(m, cap, tail_t=2)
     assert res.total == tot_model and np.array_equal(po, po_model)
     assert np.array_equal(res.slot_owner.cpu().numpy(), so_model)
