@@ -67,7 +67,7 @@ constexpr long long kBidLimit = 1ll << 45;                     // 46-bit bid fie
 constexpr int kTheta = 8;
 constexpr int kEps0Div = 4;
 constexpr int kTailMax = 64;                                   // capacity of the tail FIFO
-constexpr int kListK = 64;                                     // candidate-list capacity per person
+constexpr int kListK = 128;                                    // candidate-list capacity per person
 constexpr unsigned kGenMask = 0x3FFF;                          // 14-bit generation tag above the 18-bit object index
 
 struct LapParams {
@@ -318,6 +318,15 @@ __device__ __forceinline__ void build_list(const LapParams &P, int i, const int3
     }
 }
 
+// Warp minimum of a 64-bit key with two 32-bit REDUX steps (high word, then low word among the lanes
+// that hold the minimal high word).
+__device__ __forceinline__ unsigned long long warp_min64(unsigned long long key) {
+    const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+    const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
+    const unsigned mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xFFFFFFFFu);
+    return ((unsigned long long)mhi << 32) | mlo;
+}
+
 // Leader side (one warp): evaluate person i's list against the current prices.  Returns true with
 // the exact (b1, j1, b2) of a full scan in every lane when the result is certified, false otherwise
 // (no list, torn list, or the second-best candidate is not below the bound).
@@ -325,14 +334,17 @@ template <bool SMEMP>
 __device__ __forceinline__ bool list_try(const LapParams &P, int i, int cmin, long long S,
                                          const long long *__restrict__ price, Best &out) {
     const int lane = threadIdx.x & 31;
-    // header and entries are fetched together (one L2 round trip); entries beyond n are ignored
+    // header and the first 64 entries are fetched together (one L2 round trip); the rare longer list
+    // costs a second trip; entries beyond n are ignored
     const int2 *e = P.lst_ent + (long long)i * kListK;
     int2 v[kListK / 32];
 #pragma unroll
-    for (int k = 0; k < kListK / 32; ++k) v[k] = __ldcg(e + lane + 32 * k);
+    for (int k = 0; k < 2; ++k) v[k] = __ldcg(e + lane + 32 * k);
     const longlong2 h = __ldcg(&P.lst_hdr[i]);
     const int n = (int)((unsigned long long)h.y & 0xFFFFFFFFull);
     const unsigned gen = (unsigned)((unsigned long long)h.y >> 32);
+#pragma unroll
+    for (int k = 2; k < kListK / 32; ++k) v[k] = (n > 64) ? __ldcg(e + lane + 32 * k) : make_int2(0, 0);
     if (n < 2) return false;
     bool ok = true;
     // Values are compared as 64-bit keys (value << 18 | object): lexicographic (value, object) order,
@@ -353,14 +365,6 @@ __device__ __forceinline__ bool list_try(const LapParams &P, int i, int cmin, lo
         }
     }
     if (!__all_sync(0xffffffffu, ok)) return false;
-    // warp minimum of a 64-bit key with two 32-bit REDUX steps (high word, then low word among the
-    // lanes that hold the minimal high word)
-    auto warp_min64 = [](unsigned long long key) -> unsigned long long {
-        const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
-        const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
-        const unsigned mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xFFFFFFFFu);
-        return ((unsigned long long)mhi << 32) | mlo;
-    };
     const unsigned long long w1 = warp_min64(k1);
     const unsigned long long w2 = warp_min64(k1 == w1 ? k2 : k1);      // keys are unique (distinct objects)
     if (w2 == ~0ull) return false;
@@ -504,19 +508,15 @@ __global__ void __launch_bounds__(kThreads, 1) lap_auction_kernel(const LapParam
                     __syncthreads();
                     while (tq_cnt > 0 && tq_status == 0) {
                         // one bid: thread 0 books the result `s` of person i's scan (list or full row)
-                        auto book = [&](int i, const Best &s) {
-                            const int o = s.j1;
-                            const long long lam = SMEMP ? sprice[o] : __ldcg(P.lambda + o);
-                            const long long bid = lam + (s.b2 < kInf / 2 ? s.b2 - s.b1 : 0) + eps;
+                        // commit one bid (one thread): person i takes `slot` of object o at price `bid`,
+                        // evicting `prev`; (ms, mp) = the object's cheapest slot / price afterwards
+                        auto commit = [&](int i, int o, long long bid, int slot, int prev, int ms, long long mp) {
                             if (bid >= kBidLimit) tq_status = CYB_ERR_OVERFLOW;
                             if (tail_bids + rounds > P.max_rounds) tq_status = CYB_ERR_NOT_CONVERGED;
-                            const int slot = P.soff ? __ldcg(P.minslot + o) : o;
-                            const int prev = P.smem_owner ? sowner[o] : __ldcg(P.slot_owner + slot);
                             if (P.smem_owner) sowner[o] = i;
                             P.slot_owner[slot] = i; P.slot_price[slot] = bid;
                             P.person_obj[i] = o; P.person_slot[i] = slot;
-                            long long mp = bid;
-                            if (P.soff) { int ms; cheapest_slot(P, o, slot, bid, ms, mp); P.minslot[o] = ms; }
+                            if (P.soff) P.minslot[o] = ms;
                             P.lambda[o] = mp;
                             if (SMEMP) sprice[o] = mp;
                             int head = tq_head + 1; if (head == kTailMax) head = 0;
@@ -528,6 +528,40 @@ __global__ void __launch_bounds__(kThreads, 1) lap_auction_kernel(const LapParam
                             }
                             tq_head = head; tq_cnt = cnt;
                         };
+                        // thread-0 version (after a full row scan)
+                        auto book = [&](int i, const Best &s) {
+                            const int o = s.j1;
+                            const long long lam = SMEMP ? sprice[o] : __ldcg(P.lambda + o);
+                            const long long bid = lam + (s.b2 < kInf / 2 ? s.b2 - s.b1 : 0) + eps;
+                            const int slot = P.soff ? __ldcg(P.minslot + o) : o;
+                            const int prev = P.smem_owner ? sowner[o] : __ldcg(P.slot_owner + slot);
+                            long long mp = bid; int ms = slot;
+                            if (P.soff) cheapest_slot(P, o, slot, bid, ms, mp);
+                            commit(i, o, bid, slot, prev, ms, mp);
+                        };
+                        // warp version (after a list hit, every lane holds `s`): the slots of a capacitated
+                        // object are inspected by the lanes in parallel -- one L2 round trip instead of four
+                        auto book_warp = [&](int i, const Best &s) {
+                            const int o = s.j1, lane = t & 31;
+                            const long long lam = SMEMP ? sprice[o] : __ldcg(P.lambda + o);
+                            const long long bid = lam + (s.b2 < kInf / 2 ? s.b2 - s.b1 : 0) + eps;
+                            if (!P.soff) {
+                                if (lane == 0) commit(i, o, bid, o, P.smem_owner ? sowner[o] : __ldcg(P.slot_owner + o), o, bid);
+                                return;
+                            }
+                            const int s0 = __ldg(P.soff + o), s1 = __ldg(P.soff + o + 1);
+                            if (s1 - s0 > 32) { if (lane == 0) book(i, s); return; }
+                            const int tl = s0 + lane;
+                            long long p = 0; int w = -1;
+                            if (tl < s1) { p = __ldcg(P.slot_price + tl); w = __ldcg(P.slot_owner + tl); }
+                            // cheapest slot, lowest index on ties (slot prices < 2^45)
+                            const unsigned long long k1 = warp_min64(tl < s1 ? (((unsigned long long)p << 5) | lane) : ~0ull);
+                            const int tlane = (int)(k1 & 31);
+                            const int prev = __shfl_sync(0xffffffffu, w, tlane);
+                            const unsigned long long k2 =
+                                warp_min64(tl < s1 ? (((unsigned long long)(lane == tlane ? bid : p) << 5) | lane) : ~0ull);
+                            if (lane == 0) commit(i, o, bid, s0 + tlane, prev, s0 + (int)(k2 & 31), (long long)(k2 >> 5));
+                        };
                         if (use_lists) {
                             // warp 0 alone serves bids from the candidate lists the sweeper CTAs keep
                             // fresh, until one cannot be certified; the other warps wait at the barrier
@@ -538,7 +572,7 @@ __global__ void __launch_bounds__(kThreads, 1) lap_auction_kernel(const LapParam
                                     if (!list_try<SMEMP>(P, i, cmin, S, price_rd, s)) break;
                                     ++list_hits;
                                     ++tail_bids;
-                                    if (t == 0) book(i, s);
+                                    book_warp(i, s);
                                     __syncwarp();
                                 }
                             }
