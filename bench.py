@@ -44,6 +44,9 @@ WORKLOADS = {
                  desc="Visium-shaped 30k cells x 5k spots (6 cells/spot) x 30k genes"),
     "chunk25k": dict(n_cells=25000, n_spots=25000, n_genes=20000, cps=1, seed=1005,
                      desc="one 25k x 25k x 20k-gene sub-LAP of the 200k chunked problem (cfg5)"),
+    "cfg5": dict(n_cells=25000, n_spots=25000, n_genes=20000, cps=1, seed=1005, chunks=8,
+                 desc="synthetic 200k cells x 200k spots chunked into 8 sub-LAPs of 25k (--single-cell -noss 25000), "
+                      "strong scaling over the ranks"),
 }
 METRIC = "cell-spot assignments/sec"
 UNIT = "assignments/s"
@@ -207,31 +210,75 @@ def run_b200(args, wl):
     eng = AssignmentEngine(device=dev, precision=args.precision)
     eng.profile = True
     n_cells, n_spots, n_genes, cps = wl["n_cells"], wl["n_spots"], wl["n_genes"], wl["cps"]
+    n_chunks = wl.get("chunks", 0)          # cfg5: a fixed number of independent sub-LAPs dealt to the ranks
+    strong = n_chunks > 0
+    my_chunks = [c for c in range(n_chunks) if c % world == rank] if strong else [rank]
+    in_dtype = torch.float32 if strong else torch.float64      # cfg5 keeps 8 chunks resident: float32 inputs
 
     # ---- synthetic inputs (sampled on the device, normalised like CYT:398-399) -- not timed
-    sc_raw, st_raw, cn = syn.structured_counts_torch(n_cells, n_spots, n_genes, cps, seed=wl["seed"] + 17 * rank,
-                                                     device=dev)
-    sc_dev = syn.normalize_data_torch(sc_raw); del sc_raw
-    st_dev = syn.normalize_data_torch(st_raw); del st_raw
-    sc_host = sc_dev.cpu().pin_memory()
-    st_host = st_dev.cpu().pin_memory()
-    h2d = sc_host.numel() * 8 + st_host.numel() * 8
-    d2h = n_cells * 8
-    gathered = [torch.empty(n_cells, dtype=torch.int64, device=dev) for _ in range(world)] if world > 1 else None
+    units = []
+    for c in my_chunks:
+        sc_raw, st_raw, cn = syn.structured_counts_torch(n_cells, n_spots, n_genes, cps, seed=wl["seed"] + 17 * c,
+                                                         device=dev)
+        sc_dev = syn.normalize_data_torch(sc_raw).to(in_dtype); del sc_raw
+        st_dev = syn.normalize_data_torch(st_raw).to(in_dtype); del st_raw
+        units.append((sc_dev, st_dev, cn))
+    esz = 4 if strong else 8
+    # pinned host image of one unit (e2e re-sends it for every unit: same bytes over PCIe)
+    sc_host = units[0][0].cpu().pin_memory()
+    st_host = units[0][1].cpu().pin_memory()
+    h2d = (sc_host.numel() + st_host.numel()) * esz * len(units)
+    d2h = n_cells * 8 * len(units)
+    n_out = n_cells * max(1, len(units))
+    gathered = [torch.empty(n_out, dtype=torch.int64, device=dev) for _ in range(world)] if world > 1 else None
+    even = (not strong) or (n_chunks % world == 0)
+
+    def finish(spots):
+        if world > 1 and even:
+            dist.all_gather(gathered, torch.cat(spots) if len(spots) > 1 else spots[0])   # gather of assignment indices
 
     def step_resident():
-        spot, res, cost = eng.assign(sc_dev, st_dev, cn)
-        if world > 1:
-            dist.all_gather(gathered, spot)
+        spots = []
+        for sc_d, st_d, cn in units:
+            spot, res, cost = eng.assign(sc_d, st_d, cn)
+            spots.append(spot)
+        finish(spots)
         return spot, res, cost
 
+    # e2e: double-buffered uploads on a copy stream -- the H2D of unit k+1 overlaps the solve of unit k
+    copy_stream = torch.cuda.Stream(device=dev)
+    bufs = [(torch.empty_like(units[0][0]), torch.empty_like(units[0][1])) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    freed = [torch.cuda.Event() for _ in range(2)]
+    state = {"k": 0, "primed": False}
+
+    def upload(slot):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(freed[slot])
+            bufs[slot][0].copy_(sc_host, non_blocking=True)
+            bufs[slot][1].copy_(st_host, non_blocking=True)
+            ready[slot].record(copy_stream)
+
     def step_e2e():
-        sc_dev.copy_(sc_host, non_blocking=True)
-        st_dev.copy_(st_host, non_blocking=True)
-        spot, res, cost = eng.assign(sc_dev, st_dev, cn)
-        if world > 1:
-            dist.all_gather(gathered, spot)
-        return spot.cpu(), res, cost
+        cur_stream = torch.cuda.current_stream(dev)
+        spots, outs = [], None
+        for u in range(len(units)):
+            k = state["k"]
+            if not state["primed"]:
+                for sl in range(2):
+                    freed[sl].record(cur_stream)
+                upload(k % 2)
+                state["primed"] = True
+            cur_stream.wait_event(ready[k % 2])
+            upload((k + 1) % 2)                         # next unit's inputs, overlapping this solve
+            spot, res, cost = eng.assign(bufs[k % 2][0], bufs[k % 2][1], units[u][2])
+            freed[k % 2].record(cur_stream)
+            spots.append(spot)
+            state["k"] = k + 1
+            outs = (spot, res, cost)
+        finish(spots)
+        host = [sp.cpu() for sp in spots]               # D2H of the result
+        return host[-1], outs[1], outs[2]
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -262,46 +309,67 @@ def run_b200(args, wl):
     tot_ms, (spot, res, cost), lap_ms, cost_ms = timed(step_resident, args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
     e2e_ms, _, _, _ = timed(step_e2e, args.steps, min(args.warmup, 1))
+    # certificate = one coalesced read of the whole cost matrix: the row-scan bandwidth probe, and a
+    # full-size optimality proof of the last solve
+    for _ in range(3):
+        cert = eng.lap_check(cost, res)
+    check_ms = eng.last_ms("check")
 
     if rank == 0:
         hbm, tf_burst, tf_sus, peak_src = measured_peaks()
         ms_per_step = tot_ms / args.steps
-        value = world * n_cells / (ms_per_step / 1e3)
-        e2e_value = world * n_cells / (e2e_ms / args.steps / 1e3)
-        n = n_cells
-        n_obj = int(res.price.numel())               # a scan reads one bidder's row: n_obj int32
-        scans = res.row_scans + n                    # bids + phase-start re-checks + the min/max pass
+        total_cells = (n_chunks if strong else world) * n_cells
+        value = total_cells / (ms_per_step / 1e3)
+        e2e_value = total_cells / (e2e_ms / args.steps / 1e3)
+        n_per, n_obj = int(res.person_obj.numel()), int(res.price.numel())
+        # logical row scans of one solve: every bid scans one bidder's row (n_obj int32); bids served from a
+        # candidate list are counted too (the list is a cache of that scan) and reported separately
+        scans = res.row_scans + n_per                # + the min/max pass over every row
         lap_bytes = scans * n_obj * 4
         ach = lap_bytes / (lap_ms / 1e3) / 1e9
         kop = n_genes if args.precision == "f16" else 3 * n_genes
         gemm_flop_alg = 2.0 * n_spots * n_cells * n_genes
+        scan_bytes = n_per * n_obj * 4
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong" if strong else "weak",
             "vs_baseline": None, "dtype": "int32/int64 LAP; fp16(hi/lo split)->fp32 cost GEMM",
             "data": "synthetic",
             "config": {"workload": f"{args.workload}: {wl['desc']}", "n_cells": n_cells, "n_spots": n_spots,
                        "n_genes": n_genes, "cells_per_spot": cps, "precision": args.precision,
-                       "l2": "inputs larger than L2 (expression matrices %.1f GB, cost matrix %.2f GB)"
-                             % (h2d / 1e9, n_spots * n_cells * 4 / 1e9),
-                       "per_rank": "each rank solves its own independent sub-problem" if world > 1 else "single GPU"},
+                       "input_dtype": str(in_dtype).replace("torch.", ""),
+                       "l2": "inputs larger than L2 (expression matrices %.1f GB, cost matrix %.2f GB per sub-problem)"
+                             % ((sc_host.numel() + st_host.numel()) * esz / 1e9, n_spots * n_cells * 4 / 1e9),
+                       "per_rank": (f"{n_chunks} independent sub-LAPs dealt round-robin to {world} rank(s)" if strong else
+                                    ("each rank solves its own independent sub-problem" if world > 1 else "single GPU")),
+                       "e2e": "double-buffered pinned H2D on a copy stream overlaps the previous solve"},
             "roofline": {"kernel": "lap_auction_kernel", "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s",
                          "frac": ach / hbm, "traffic": None, "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)",
-                         "row_scans": scans, "bytes_per_scan": n_obj * 4, "kernel_ms": lap_ms},
+                         "row_scans": scans, "bytes_per_scan": n_obj * 4, "kernel_ms": lap_ms,
+                         "scans_served_from_candidate_lists": int(res.stats["list_hits"]),
+                         "note": "latency-bound: sequential price-war chains; see DESIGN.md 4.3"},
+            "roofline_row_scan": {"kernel": "lap_rowmin_kernel (certificate: one pass over the cost matrix)",
+                                  "bound": "hbm", "bytes": scan_bytes, "ms": check_ms,
+                                  "achieved": scan_bytes / (check_ms / 1e3) / 1e9, "peak": hbm, "unit": "GB/s",
+                                  "frac": scan_bytes / (check_ms / 1e3) / 1e9 / hbm,
+                                  "note": "ms covers memsets + rowmin + finish kernels"},
             "roofline_cost_build": {"bound": "tensor", "algorithmic_flop": gemm_flop_alg, "ms": cost_ms,
                                     "achieved": gemm_flop_alg / (cost_ms / 1e3) / 1e12, "peak": tf_burst,
                                     "unit": "TFLOP/s", "frac": gemm_flop_alg / (cost_ms / 1e3) / 1e12 / tf_burst,
                                     "executed_flop": 2.0 * n_spots * n_cells * kop,
+                                    "executed_frac": 2.0 * n_spots * n_cells * kop / (cost_ms / 1e3) / 1e12 / tf_burst,
                                     "note": "ms covers standardise pre-pass + GEMM; f16x3 executes 3x the algorithmic flop"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / args.steps},
-            "gpu_launches": args.steps * 8,
+            "gpu_launches": args.steps * 8 * len(units),
             "clocks": clocks,
-            "lap_stats": {k: res.stats[k] for k in ("phases", "rounds", "bids", "tail_bids", "tails", "rounds_le1",
+            "certificate": cert,
+            "lap_stats": {k: res.stats[k] for k in ("phases", "rounds", "bids", "tail_bids", "tails", "list_hits",
                                                     "max_bidders", "grid", "smem_prices")},
             "total_cost": res.total, "lap_ms": lap_ms, "cost_build_ms": cost_ms,
         }
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not strong and not args.no_cpu_baseline:
             row_map = None if cps == 1 else np.repeat(np.arange(n_spots, dtype=np.int32), cn)
             # the oracle takes the reference's orientation (spots x cells)
             cost_np = np.ascontiguousarray((cost[:, :n_cells] if cps == 1 else cost[:, :n_spots].T).cpu().numpy())
