@@ -52,6 +52,15 @@ METRIC = "cell-spot assignments/sec"
 UNIT = "assignments/s"
 
 
+def ncu_traffic(workload, kernel):
+    """DRAM bytes per launch measured once with `ncu --set full` (profiles/ncu_traffic.json), or None."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        return json.load(open(p)).get(workload, {}).get(kernel)
+    except (OSError, ValueError):
+        return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -345,7 +354,7 @@ def run_b200(args, wl):
                                     ("each rank solves its own independent sub-problem" if world > 1 else "single GPU")),
                        "e2e": "double-buffered pinned H2D on a copy stream overlaps the previous solve"},
             "roofline": {"kernel": "lap_auction_kernel", "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s",
-                         "frac": ach / hbm, "traffic": None, "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)",
+                         "frac": ach / hbm, "traffic": ncu_traffic(args.workload, "lap_auction_kernel"), "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)",
                          "row_scans": scans, "bytes_per_scan": n_obj * 4, "kernel_ms": lap_ms,
                          "scans_served_from_candidate_lists": int(res.stats["list_hits"]),
                          "note": "latency-bound: sequential price-war chains; see DESIGN.md 4.3"},
