@@ -20,7 +20,7 @@
 // highest bid of a round wins (lowest person on ties) and evicts the slot's
 // holder.  Invariant (eps-CS): an assigned person's C[i,o] + (own slot price) is
 // within eps of its best alternative object, and lambda[o] <= own slot price.
-// eps is divided by 8 per phase down to 1; at a phase start a pair is kept iff
+// eps is divided by 4 per phase down to 1; at a phase start a pair is kept iff
 // C[i,o] + lambda[o] <= alt + eps, and its slot price is clamped down to
 // alt + eps - C[i,o] (never below lambda[o], so object prices never decrease).
 // With the factor P+1 on the costs, eps = 1 leaves the total < P+1 scaled units
@@ -64,7 +64,7 @@ constexpr int kPersonBits = 18;                                // P < 2^18
 constexpr unsigned long long kPersonMask = (1ull << kPersonBits) - 1;
 constexpr long long kInf = 1ll << 60;                          // price of an object without capacity
 constexpr long long kBidLimit = 1ll << 45;                     // 46-bit bid field
-constexpr int kTheta = 8;
+constexpr int kTheta = 4;
 constexpr int kEps0Div = 4;
 constexpr int kTailMax = 64;                                   // capacity of the tail FIFO
 constexpr int kListK = 128;                                    // candidate-list capacity per person
@@ -100,6 +100,7 @@ struct LapParams {
     int2 *lst_ent;
     int use_lists;
     int sweepers;            // CTAs that rebuild lists during a tail (<= G-1)
+    int theta, eps0_div;     // eps schedule: eps0 = range*(P+1)/eps0_div, eps /= theta per phase
     int smem_owner;          // 1: CTA 0 keeps the holder of every object in shared memory during a tail (unit capacities)
 };
 
@@ -426,7 +427,7 @@ __global__ void __launch_bounds__(kThreads, 1) lap_auction_kernel(const LapParam
     }
     grid_barrier(P.bar, bar_target, G);
     const int cmin = __ldcg(P.gmm + 0), cmax = __ldcg(P.gmm + 1);
-    long long eps = ((long long)cmax - (long long)cmin) * S / kEps0Div;
+    long long eps = ((long long)cmax - (long long)cmin) * S / P.eps0_div;
     if (eps < 1) eps = 1;
 
     long long rounds = 0, bids = 0, passes = 0, phases = 0, rounds1 = 0, maxF = 0, tail_bids = 0, tails = 0, list_hits = 0;
@@ -699,7 +700,7 @@ __global__ void __launch_bounds__(kThreads, 1) lap_auction_kernel(const LapParam
             }
         }
         if (eps == 1) break;
-        eps /= kTheta;
+        eps /= P.theta;
         if (eps < 1) eps = 1;
     }
 
@@ -898,6 +899,9 @@ extern "C" int cyb_lap_solve_i32(const int32_t *cost_dev, int64_t ld, int64_t n_
     P.lst_ent = reinterpret_cast<int2 *>(ws + L.lst_ent);
     P.tail_t = 8;
     P.use_lists = 1;
+    P.theta = kTheta; P.eps0_div = kEps0Div;
+    if (const char *e = getenv("CYB_LAP_THETA")) P.theta = std::max(2, atoi(e));
+    if (const char *e = getenv("CYB_LAP_EPS0")) P.eps0_div = std::max(1, atoi(e));
     if (const char *e = getenv("CYB_LAP_TAIL")) P.tail_t = atoi(e);
     if (const char *e = getenv("CYB_LAP_LISTS")) P.use_lists = atoi(e);
 

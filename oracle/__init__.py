@@ -136,7 +136,7 @@ def min_reduced_cost_i32(cost, u, v, row_map=None) -> int:
                                               _ptr(v, ctypes.c_int64)))
 
 
-def auction_model(m, cap=None, theta=8, eps0_div=4, tail_t=0, round_cap=0, variant=1):
+def auction_model(m, cap=None, theta=4, eps0_div=4, tail_t=0, round_cap=0, variant=1):
     """Sequential model of the device auction.  ``m`` is persons x objects (cells x spots: the
     TRANSPOSE of the reference's cost), ``cap`` the object capacities (None: all 1).
     Returns (person_obj, slot_owner, total, lambda, stats, round_log)."""
