@@ -328,28 +328,42 @@ __device__ __forceinline__ unsigned long long warp_min64(unsigned long long key)
     return ((unsigned long long)mhi << 32) | mlo;
 }
 
-// Leader side (one warp): evaluate person i's list against the current prices.  Returns true with
-// the exact (b1, j1, b2) of a full scan in every lane when the result is certified, false otherwise
-// (no list, torn list, or the second-best candidate is not below the bound).
-template <bool SMEMP>
-__device__ __forceinline__ bool list_try(const LapParams &P, int i, int cmin, long long S,
-                                         const long long *__restrict__ price, Best &out) {
+// Leader side (one warp).  A list is FETCHED (header + first 64 entries: one L2 round trip, issued
+// as early as the next bidder is known so that it overlaps the current bid's bookkeeping) and later
+// EVALUATED against the current prices.
+struct ListRegs {
+    longlong2 h;
+    int2 v0, v1;
+};
+
+__device__ __forceinline__ ListRegs list_fetch(const LapParams &P, int i) {
     const int lane = threadIdx.x & 31;
-    // header and the first 64 entries are fetched together (one L2 round trip); the rare longer list
-    // costs a second trip; entries beyond n are ignored
     const int2 *e = P.lst_ent + (long long)i * kListK;
-    int2 v[kListK / 32];
-#pragma unroll
-    for (int k = 0; k < 2; ++k) v[k] = __ldcg(e + lane + 32 * k);
-    const longlong2 h = __ldcg(&P.lst_hdr[i]);
+    ListRegs r;
+    r.v0 = __ldcg(e + lane);
+    r.v1 = __ldcg(e + lane + 32);
+    r.h = __ldcg(&P.lst_hdr[i]);
+    return r;
+}
+
+// Returns true with the exact (b1, j1, b2) of a full scan in every lane when the result is certified,
+// false otherwise (no list, torn list, or the second-best candidate is not below the bound).
+template <bool SMEMP>
+__device__ __forceinline__ bool list_eval(const LapParams &P, int i, const ListRegs &r, int cmin, long long S,
+                                          const long long *__restrict__ price, Best &out) {
+    const int lane = threadIdx.x & 31;
+    const longlong2 h = r.h;
     const int n = (int)((unsigned long long)h.y & 0xFFFFFFFFull);
     const unsigned gen = (unsigned)((unsigned long long)h.y >> 32);
+    int2 v[kListK / 32];
+    v[0] = r.v0; v[1] = r.v1;
+    const int2 *e = P.lst_ent + (long long)i * kListK;
 #pragma unroll
-    for (int k = 2; k < kListK / 32; ++k) v[k] = (n > 64) ? __ldcg(e + lane + 32 * k) : make_int2(0, 0);
+    for (int k = 2; k < kListK / 32; ++k) v[k] = (n > 64) ? __ldcg(e + lane + 32 * k) : make_int2(0, 0);   // rare second trip
     if (n < 2) return false;
     bool ok = true;
     // Values are compared as 64-bit keys (value << 18 | object): lexicographic (value, object) order,
-    // valid while every value is < 2^46 (guaranteed when the scaled cost range is < 2^45, see `pack_ok`).
+    // valid while every value is < 2^46 (guaranteed when the scaled cost range is < 2^45).
     unsigned long long k1 = ~0ull, k2 = ~0ull;
 #pragma unroll
     for (int k = 0; k < kListK / 32; ++k) {
@@ -542,16 +556,24 @@ __global__ void __launch_bounds__(kThreads, 1) lap_auction_kernel(const LapParam
                         };
                         // warp version (after a list hit, every lane holds `s`): the slots of a capacitated
                         // object are inspected by the lanes in parallel -- one L2 round trip instead of four
-                        auto book_warp = [&](int i, const Best &s) {
+                        auto book_warp = [&](int i, const Best &s) -> int {
                             const int o = s.j1, lane = t & 31;
                             const long long lam = SMEMP ? sprice[o] : __ldcg(P.lambda + o);
                             const long long bid = lam + (s.b2 < kInf / 2 ? s.b2 - s.b1 : 0) + eps;
                             if (!P.soff) {
-                                if (lane == 0) commit(i, o, bid, o, P.smem_owner ? sowner[o] : __ldcg(P.slot_owner + o), o, bid);
-                                return;
+                                const int prev = P.smem_owner ? sowner[o] : __ldcg(P.slot_owner + o);   // uniform address
+                                __syncwarp();
+                                if (lane == 0) commit(i, o, bid, o, prev, o, bid);
+                                return prev;
                             }
                             const int s0 = __ldg(P.soff + o), s1 = __ldg(P.soff + o + 1);
-                            if (s1 - s0 > 32) { if (lane == 0) book(i, s); return; }
+                            if (s1 - s0 > 32) {
+                                const int slot = __ldcg(P.minslot + o);
+                                const int prev = __ldcg(P.slot_owner + slot);
+                                __syncwarp();
+                                if (lane == 0) book(i, s);
+                                return prev;
+                            }
                             const int tl = s0 + lane;
                             long long p = 0; int w = -1;
                             if (tl < s1) { p = __ldcg(P.slot_price + tl); w = __ldcg(P.slot_owner + tl); }
@@ -562,19 +584,36 @@ __global__ void __launch_bounds__(kThreads, 1) lap_auction_kernel(const LapParam
                             const unsigned long long k2 =
                                 warp_min64(tl < s1 ? (((unsigned long long)(lane == tlane ? bid : p) << 5) | lane) : ~0ull);
                             if (lane == 0) commit(i, o, bid, s0 + tlane, prev, s0 + (int)(k2 & 31), (long long)(k2 >> 5));
+                            return prev;
                         };
                         if (use_lists) {
                             // warp 0 alone serves bids from the candidate lists the sweeper CTAs keep
                             // fresh, until one cannot be certified; the other warps wait at the barrier
                             if (t < 32) {
+                                int i = tq[tq_head];
+                                ListRegs lr = list_fetch(P, i);
                                 while (tq_cnt > 0 && tq_status == 0) {
-                                    const int i = tq[tq_head];
+                                    // the next bidder is the second FIFO entry when there is one, otherwise the
+                                    // person this bid evicts: fetch its list as early as it is known
+                                    int nxt = -1;
+                                    ListRegs ln;
+                                    if (tq_cnt > 1) {
+                                        int h2 = tq_head + 1; if (h2 == kTailMax) h2 = 0;
+                                        nxt = tq[h2];
+                                        ln = list_fetch(P, nxt);
+                                    }
                                     Best s;
-                                    if (!list_try<SMEMP>(P, i, cmin, S, price_rd, s)) break;
+                                    if (!list_eval<SMEMP>(P, i, lr, cmin, S, price_rd, s)) break;
                                     ++list_hits;
                                     ++tail_bids;
-                                    book_warp(i, s);
+                                    const int prev = book_warp(i, s);
                                     __syncwarp();
+                                    if (nxt < 0) {
+                                        if (prev < 0) break;                  // queue is empty now
+                                        nxt = prev;
+                                        ln = list_fetch(P, nxt);
+                                    }
+                                    i = nxt; lr = ln;
                                 }
                             }
                             __syncthreads();
