@@ -78,12 +78,13 @@ def _dist_state(group=None):
     return None, 0, 1
 
 
-def solve_chunks(engine, sc_np, st_np, plan: list[Chunk], log_tpm: bool = False, group=None):
+def solve_chunks(engine, sc_np, st_np, plan: list[Chunk], log_tpm: bool = False, group=None, **assign_kw):
     """Solve every chunk; returns ``mapped_st_index`` (list of int per cell, chunk-local spot index
     as in cytospace.py:455-459) for each chunk, on every rank.
 
     Single process: chunks run back to back on ``engine``.  With a process group: rank 0 passes the
-    matrices (other ranks may pass ``None``), chunks are dealt by ``assign_ranks``."""
+    matrices (other ranks may pass ``None``), chunks are dealt by ``assign_ranks``.
+    ``assign_kw`` (``metric=``, ``cspr_seed=``) goes to ``engine.assign`` unchanged (rank 0's values)."""
     dist, rank, world = _dist_state(group)
     if world == 1:
         out = []
@@ -91,10 +92,10 @@ def solve_chunks(engine, sc_np, st_np, plan: list[Chunk], log_tpm: bool = False,
             sc = sc_np[:, ch.sc_index] if len(ch.sc_index) != sc_np.shape[1] or not _is_arange(ch.sc_index) else sc_np
             st = st_np if ch.st_index is None else st_np[:, ch.st_index]
             spot_of_cell, _, _ = engine.assign(np.ascontiguousarray(sc), np.ascontiguousarray(st), ch.cn,
-                                               log_tpm=log_tpm)
+                                               log_tpm=log_tpm, **assign_kw)
             out.append(spot_of_cell.cpu().numpy().tolist())
         return out
-    return _solve_chunks_distributed(dist, rank, world, engine, sc_np, st_np, plan, log_tpm, group)
+    return _solve_chunks_distributed(dist, rank, world, engine, sc_np, st_np, plan, log_tpm, group, assign_kw)
 
 
 def _is_arange(idx) -> bool:
@@ -102,14 +103,14 @@ def _is_arange(idx) -> bool:
     return idx.size > 0 and idx[0] == 0 and np.array_equal(idx, np.arange(idx.size))
 
 
-def _solve_chunks_distributed(dist, rank, world, engine, sc_np, st_np, plan, log_tpm, group):
+def _solve_chunks_distributed(dist, rank, world, engine, sc_np, st_np, plan, log_tpm, group, assign_kw):
     dev = engine.device
     # plan and shapes travel as one small object broadcast (host metadata, not the data path)
     meta = [None]
     if rank == 0:
-        meta[0] = (plan, int(sc_np.shape[0]), int(st_np.shape[1]), str(sc_np.dtype))
+        meta[0] = (plan, int(sc_np.shape[0]), int(st_np.shape[1]), str(sc_np.dtype), dict(assign_kw))
     dist.broadcast_object_list(meta, src=0, group=group)
-    plan, n_genes, n_spots, dt = meta[0]
+    plan, n_genes, n_spots, dt, assign_kw = meta[0]
     tdt = torch.float64 if dt == "float64" else torch.float32
     owner = assign_ranks([c.n for c in plan], world)
     shared_st = any(c.st_index is None for c in plan)
@@ -155,7 +156,8 @@ def _solve_chunks_distributed(dist, rank, world, engine, sc_np, st_np, plan, log
         if owner[ch.idx] != rank:
             continue
         sc_blk, st_blk = mine.pop(ch.idx)
-        spot_of_cell, _, _ = engine.assign(sc_blk, st_all if st_blk is None else st_blk, ch.cn, log_tpm=log_tpm)
+        spot_of_cell, _, _ = engine.assign(sc_blk, st_all if st_blk is None else st_blk, ch.cn, log_tpm=log_tpm,
+                                           **assign_kw)
         results[ch.idx] = spot_of_cell.to(torch.int32)
 
     # one all-gather of the assignment indices (padded to the largest per-rank total)

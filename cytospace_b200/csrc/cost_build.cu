@@ -271,10 +271,20 @@ __device__ __forceinline__ TileCoord tile_coord(int t, int mblocks, int nblocks)
     return tc;
 }
 
+// EPI 0: cost = rint(neg_scale * acc)                                  (correlation metrics)
+// EPI 1: Euclidean distance from the SAME standardised operands.  With a = mu_a + sd_a * z_a,
+//        b = mu_b + sd_b * z_b and sum_g z = 0:  a.b = G (mu_a mu_b + sd_a sd_b r),  r = acc / G, so
+//            |a - b|^2 = G [ (mu_a - mu_b)^2 + (sd_a - sd_b)^2 + 2 sd_a sd_b (1 - r) ]
+//        -- three non-negative terms, no cancellation of the large norms, and the GEMM keeps its
+//        mixed-sign products (an un-centred a.b accumulates only positive products, and the tensor
+//        core's truncating fp32 accumulate then biases it: measured 1e-4 relative on the distance).
+//        cost = rint(scale * sqrt(.)); the epilogue runs in float64; stat_* = [mean | sd] per column.
+template <int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 cost_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  int n_spots, int n_cells, int num_kb, float neg_scale, int32_t *__restrict__ cost,
-                 long long ld_cost) {
+                 long long ld_cost, const double *__restrict__ stat_a, const double *__restrict__ stat_b,
+                 double n_genes_d, int32_t *__restrict__ bad) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)kStages * kStageBytes);
@@ -386,21 +396,32 @@ cost_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             const int col0 = tc.n * BN + cg * 64;
             if (row < n_spots) {
                 int32_t *out_row = cost + (long long)row * ld_cost + col0;
+                const double mu_a = (EPI == 1) ? stat_a[row] : 0.0, sd_a = (EPI == 1) ? stat_a[n_spots + row] : 0.0;
+                int nbad = 0;
+                auto quant = [&](int q) -> int {
+                    if (EPI == 0) return __float2int_rn(neg_scale * sum[q]);
+                    const int col = min(col0 + q, n_cells - 1);
+                    const double mu_b = __ldg(stat_b + col), sd_b = __ldg(stat_b + n_cells + col);
+                    const double dm = mu_a - mu_b, ds = sd_a - sd_b;
+                    const double one_minus_r = fmax(1.0 - (double)sum[q] / n_genes_d, 0.0);
+                    const double d2 = n_genes_d * (dm * dm + ds * ds + 2.0 * sd_a * sd_b * one_minus_r);
+                    double v = (double)neg_scale * sqrt(d2);
+                    if (!(v < 1073741823.0)) { v = 1073741823.0; ++nbad; }
+                    return __double2int_rn(v);
+                };
                 if (vec_ok && col0 + 64 <= n_cells) {
 #pragma unroll
                     for (int q = 0; q < 64; q += 4) {
                         int4 o;
-                        o.x = __float2int_rn(neg_scale * sum[q]);
-                        o.y = __float2int_rn(neg_scale * sum[q + 1]);
-                        o.z = __float2int_rn(neg_scale * sum[q + 2]);
-                        o.w = __float2int_rn(neg_scale * sum[q + 3]);
+                        o.x = quant(q); o.y = quant(q + 1); o.z = quant(q + 2); o.w = quant(q + 3);
                         *reinterpret_cast<int4 *>(out_row + q) = o;
                     }
                 } else {
 #pragma unroll
                     for (int q = 0; q < 64; ++q)
-                        if (col0 + q < n_cells) out_row[q] = __float2int_rn(neg_scale * sum[q]);
+                        if (col0 + q < n_cells) out_row[q] = quant(q);
                 }
+                if (EPI == 1 && nbad && bad) atomicAdd(bad, nbad);
             }
         }
     }
@@ -524,8 +545,27 @@ extern "C" int cyb_standardise(const void *x_dev, int x_dtype, int64_t n_genes, 
     return cyb::set_error(CYB_ERR_INVALID, "cyb_standardise: unknown dtype %d", x_dtype);
 }
 
-extern "C" int cyb_cost_gemm_i32(const void *zst_dev, const void *zsc_dev, int64_t n_spots, int64_t n_cells,
-                                 int64_t k, float scale, int32_t *cost_dev, int64_t ld_cost, void *stream_v) {
+// fac[c] = 1e6 / colsum(x[:, c]) -- the TPM factor of normalize_data (common.py:144), shared with metrics.cu
+int cyb_internal_tpm_factors(const void *x_dev, int x_dtype, int64_t n_genes, int64_t n_cols, int64_t ld_x,
+                             double *fac_dev, double *partial_dev, cudaStream_t stream) {
+    const int splits = (int)std::min<int64_t>(kStatSplit, std::max<int64_t>(1, n_genes / 64));
+    const dim3 sgrid((unsigned)((n_cols + kStatCols - 1) / kStatCols), (unsigned)splits);
+    if (x_dtype == CYB_F64)
+        colsum_kernel<double, 0><<<sgrid, kStatCols * kStatRows, 0, stream>>>(
+            static_cast<const double *>(x_dev), ld_x, (int)n_genes, (int)n_cols, nullptr, partial_dev);
+    else
+        colsum_kernel<float, 0><<<sgrid, kStatCols * kStatRows, 0, stream>>>(
+            static_cast<const float *>(x_dev), ld_x, (int)n_genes, (int)n_cols, nullptr, partial_dev);
+    colstat_finalize_kernel<0><<<(int)((n_cols + 255) / 256), 256, 0, stream>>>(
+        partial_dev, (int)n_cols, (int)n_genes, splits, fac_dev, nullptr, nullptr, nullptr, nullptr);
+    CYB_CUDA_CHECK(cudaGetLastError());
+    return CYB_OK;
+}
+
+namespace {
+int gemm_launch(const void *zst_dev, const void *zsc_dev, int64_t n_spots, int64_t n_cells, int64_t k, float scale,
+                int32_t *cost_dev, int64_t ld_cost, const double *stat_a, const double *stat_b, double n_genes,
+                int32_t *bad_dev, void *stream_v) {
     // (local names: "spots" = rows of the output / operand A, "cells" = columns / operand B)
     cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
     if (!zst_dev || !zsc_dev || !cost_dev)
@@ -546,24 +586,63 @@ extern "C" int cyb_cost_gemm_i32(const void *zst_dev, const void *zsc_dev, int64
     CUtensorMap map_a, map_b;
     if (int rc = make_operand_map(enc, &map_a, zst_dev, n_spots, k, BM)) return rc;
     if (int rc = make_operand_map(enc, &map_b, zsc_dev, n_cells, k, BN)) return rc;
-    CYB_CUDA_CHECK(cudaFuncSetAttribute(cost_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
     const int64_t mblocks = (n_spots + BM - 1) / BM, nblocks = (n_cells + BN - 1) / BN;
     const int grid = (int)std::min<int64_t>(sms, mblocks * nblocks);
-    cost_gemm_kernel<<<grid, kGemmThreads, kGemmSmem, stream>>>(map_a, map_b, (int)n_spots, (int)n_cells,
-                                                                (int)(k / BK), -scale, cost_dev, ld_cost);
+    if (stat_a) {
+        CYB_CUDA_CHECK(cudaFuncSetAttribute(cost_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
+        cost_gemm_kernel<1><<<grid, kGemmThreads, kGemmSmem, stream>>>(map_a, map_b, (int)n_spots, (int)n_cells,
+                                                                       (int)(k / BK), scale, cost_dev, ld_cost,
+                                                                       stat_a, stat_b, n_genes, bad_dev);
+    } else {
+        CYB_CUDA_CHECK(cudaFuncSetAttribute(cost_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
+        cost_gemm_kernel<0><<<grid, kGemmThreads, kGemmSmem, stream>>>(map_a, map_b, (int)n_spots, (int)n_cells,
+                                                                       (int)(k / BK), -scale, cost_dev, ld_cost,
+                                                                       nullptr, nullptr, 0.0, nullptr);
+    }
     CYB_CUDA_CHECK(cudaGetLastError());
     return CYB_OK;
 }
+}  // namespace
+
+extern "C" int cyb_cost_gemm_i32(const void *za_dev, const void *zb_dev, int64_t n_a, int64_t n_b, int64_t k,
+                                 float scale, int32_t *cost_dev, int64_t ld_cost, void *stream) {
+    return gemm_launch(za_dev, zb_dev, n_a, n_b, k, scale, cost_dev, ld_cost, nullptr, nullptr, 0.0, nullptr, stream);
+}
+
+extern "C" int cyb_cost_gemm_euclid_i32(const void *za_dev, const void *zb_dev, int64_t n_a, int64_t n_b, int64_t k,
+                                        int64_t n_genes, float scale, const double *colstat_a_dev,
+                                        const double *colstat_b_dev, int32_t *cost_dev, int64_t ld_cost,
+                                        int32_t *bad_dev, void *stream) {
+    if (!colstat_a_dev || !colstat_b_dev)
+        return cyb::set_error(CYB_ERR_INVALID, "cyb_cost_gemm_euclid_i32: null pointer argument");
+    if (n_genes <= 0) return cyb::set_error(CYB_ERR_INVALID, "cyb_cost_gemm_euclid_i32: n_genes must be positive");
+    return gemm_launch(za_dev, zb_dev, n_a, n_b, k, scale, cost_dev, ld_cost, colstat_a_dev, colstat_b_dev,
+                       (double)n_genes, bad_dev, stream);
+}
+
+extern "C" size_t cyb_rank_workspace_bytes(int64_t n_genes, int64_t n_cols);
+extern "C" int cyb_rank_columns(const void *x_dev, int x_dtype, int64_t n_genes, int64_t n_cols, int64_t ld_x,
+                                int log_tpm, float *rank_dev, int64_t ld_rank, void *workspace_dev,
+                                size_t workspace_bytes, void *stream);
 
 namespace {
-struct BuildLayout { size_t za, zb, std_ws, total; };
-BuildLayout build_layout(int64_t n_genes, int64_t n_a, int64_t n_b, int precision) {
+struct BuildLayout { size_t za, zb, std_ws, norm_a, norm_b, rank_a, rank_b, rank_ws, total; };
+BuildLayout build_layout(int64_t n_genes, int64_t n_a, int64_t n_b, int precision, int metric) {
     BuildLayout L; size_t o = 0;
     auto take = [&](size_t b) { size_t r = o; o = cyb::align_up(o + b, 1024); return r; };
     const size_t kop = (size_t)cyb_operand_k(n_genes, precision);
     L.za = take((size_t)n_a * kop * 2);
     L.zb = take((size_t)n_b * kop * 2);
     L.std_ws = take(std_layout(std::max(n_a, n_b)).total);
+    L.norm_a = L.norm_b = L.rank_a = L.rank_b = L.rank_ws = 0;
+    if (metric == CYB_METRIC_EUCLIDEAN) {
+        L.norm_a = take((size_t)n_a * 16);      // [mean | sd] per column
+        L.norm_b = take((size_t)n_b * 16);
+    } else if (metric == CYB_METRIC_SPEARMAN) {
+        L.rank_a = take((size_t)n_genes * cyb::align_up((size_t)n_a, 32) * 4);
+        L.rank_b = take((size_t)n_genes * cyb::align_up((size_t)n_b, 32) * 4);
+        L.rank_ws = take(cyb_rank_workspace_bytes(n_genes, std::max(n_a, n_b)));
+    }
     L.total = o;
     return L;
 }
@@ -571,7 +650,60 @@ BuildLayout build_layout(int64_t n_genes, int64_t n_a, int64_t n_b, int precisio
 
 extern "C" size_t cyb_cost_build_workspace_bytes(int64_t n_genes, int64_t n_a, int64_t n_b, int precision) {
     if (n_genes <= 0 || n_a <= 0 || n_b <= 0) return 1024;
-    return build_layout(n_genes, n_a, n_b, precision).total;
+    return build_layout(n_genes, n_a, n_b, precision, CYB_METRIC_PEARSON).total;
+}
+
+extern "C" size_t cyb_cost_build_metric_workspace_bytes(int metric, int64_t n_genes, int64_t n_a, int64_t n_b,
+                                                        int precision) {
+    if (n_genes <= 0 || n_a <= 0 || n_b <= 0) return 1024;
+    return build_layout(n_genes, n_a, n_b, precision, metric).total;
+}
+
+extern "C" int cyb_cost_build(int metric, const void *a_dev, const void *b_dev, int x_dtype, int64_t n_genes,
+                              int64_t n_a, int64_t n_b, int64_t ld_a, int64_t ld_b, int log_tpm_flag, int precision,
+                              double cost_scale, int32_t *cost_dev, int64_t ld_cost, int32_t *bad_dev,
+                              void *workspace_dev, size_t workspace_bytes, void *stream) {
+    if (metric == CYB_METRIC_PEARSON)
+        return cyb_cost_build_pearson(a_dev, b_dev, x_dtype, n_genes, n_a, n_b, ld_a, ld_b, log_tpm_flag, precision,
+                                      cost_scale, cost_dev, ld_cost, nullptr, nullptr, bad_dev, workspace_dev,
+                                      workspace_bytes, stream);
+    if (metric != CYB_METRIC_SPEARMAN && metric != CYB_METRIC_EUCLIDEAN)
+        return cyb::set_error(CYB_ERR_INVALID, "cyb_cost_build: unknown metric %d", metric);
+    if (!workspace_dev) return cyb::set_error(CYB_ERR_INVALID, "cyb_cost_build: null workspace");
+    if (n_genes <= 0 || n_a <= 0 || n_b <= 0) return cyb::set_error(CYB_ERR_INVALID, "cyb_cost_build: empty problem");
+    const BuildLayout L = build_layout(n_genes, n_a, n_b, precision, metric);
+    if (workspace_bytes < L.total)
+        return cyb::set_error(CYB_ERR_WORKSPACE, "cyb_cost_build: workspace %zu < required %zu", workspace_bytes, L.total);
+    if (reinterpret_cast<uintptr_t>(workspace_dev) & 1023)
+        return cyb::set_error(CYB_ERR_INVALID, "cyb_cost_build: workspace must be 1024-byte aligned");
+    char *ws = static_cast<char *>(workspace_dev);
+    const size_t std_bytes = std_layout(std::max(n_a, n_b)).total;
+    const int64_t kop = cyb_operand_k(n_genes, precision);
+    if (metric == CYB_METRIC_EUCLIDEAN) {
+        // cdist(.., 'euclidean') (linear_assignment_solvers.py:51,59) from the standardised operands of
+        // the Pearson build plus the column means / sigmas (a constant column is fine here: z = 0)
+        double *sa = reinterpret_cast<double *>(ws + L.norm_a), *sb = reinterpret_cast<double *>(ws + L.norm_b);
+        if (int rc = cyb_standardise(a_dev, x_dtype, n_genes, n_a, ld_a, log_tpm_flag, precision, 0, ws + L.za, sa,
+                                     nullptr, ws + L.std_ws, std_bytes, stream)) return rc;
+        if (int rc = cyb_standardise(b_dev, x_dtype, n_genes, n_b, ld_b, log_tpm_flag, precision, 1, ws + L.zb, sb,
+                                     nullptr, ws + L.std_ws, std_bytes, stream)) return rc;
+        return cyb_cost_gemm_euclid_i32(ws + L.za, ws + L.zb, n_a, n_b, kop, n_genes, (float)cost_scale, sa, sb,
+                                        cost_dev, ld_cost, bad_dev, stream);
+    }
+    // Spearman (common.py:202-215): Pearson of the per-column average ranks
+    float *ra = reinterpret_cast<float *>(ws + L.rank_a), *rb = reinterpret_cast<float *>(ws + L.rank_b);
+    const int64_t lda_r = (int64_t)cyb::align_up((size_t)n_a, 32), ldb_r = (int64_t)cyb::align_up((size_t)n_b, 32);
+    const size_t rank_bytes = cyb_rank_workspace_bytes(n_genes, std::max(n_a, n_b));
+    if (int rc = cyb_rank_columns(a_dev, x_dtype, n_genes, n_a, ld_a, log_tpm_flag, ra, lda_r, ws + L.rank_ws,
+                                  rank_bytes, stream)) return rc;
+    if (int rc = cyb_rank_columns(b_dev, x_dtype, n_genes, n_b, ld_b, log_tpm_flag, rb, ldb_r, ws + L.rank_ws,
+                                  rank_bytes, stream)) return rc;
+    if (int rc = cyb_standardise(ra, CYB_F32, n_genes, n_a, lda_r, 0, precision, 0, ws + L.za, nullptr, bad_dev,
+                                 ws + L.std_ws, std_bytes, stream)) return rc;
+    if (int rc = cyb_standardise(rb, CYB_F32, n_genes, n_b, ldb_r, 0, precision, 1, ws + L.zb, nullptr, bad_dev,
+                                 ws + L.std_ws, std_bytes, stream)) return rc;
+    return cyb_cost_gemm_i32(ws + L.za, ws + L.zb, n_a, n_b, kop, (float)(cost_scale / (double)n_genes), cost_dev,
+                             ld_cost, stream);
 }
 
 extern "C" int cyb_cost_build_pearson(const void *a_dev, const void *b_dev, int x_dtype, int64_t n_genes,
@@ -582,14 +714,14 @@ extern "C" int cyb_cost_build_pearson(const void *a_dev, const void *b_dev, int 
     if (!workspace_dev) return cyb::set_error(CYB_ERR_INVALID, "cyb_cost_build_pearson: null workspace");
     if (n_genes <= 0 || n_a <= 0 || n_b <= 0)
         return cyb::set_error(CYB_ERR_INVALID, "cyb_cost_build_pearson: empty problem");
-    const BuildLayout L = build_layout(n_genes, n_a, n_b, precision);
+    const BuildLayout L = build_layout(n_genes, n_a, n_b, precision, CYB_METRIC_PEARSON);
     if (workspace_bytes < L.total)
         return cyb::set_error(CYB_ERR_WORKSPACE, "cyb_cost_build_pearson: workspace %zu < required %zu",
                               workspace_bytes, L.total);
     if (reinterpret_cast<uintptr_t>(workspace_dev) & 1023)
         return cyb::set_error(CYB_ERR_INVALID, "cyb_cost_build_pearson: workspace must be 1024-byte aligned");
     char *ws = static_cast<char *>(workspace_dev);
-    const size_t std_bytes = L.total - L.std_ws;
+    const size_t std_bytes = std_layout(std::max(n_a, n_b)).total;
     // matrix a supplies the rows of the output (GEMM operand A), matrix b the columns (operand B)
     if (int rc = cyb_standardise(a_dev, x_dtype, n_genes, n_a, ld_a, log_tpm_flag, precision, 0, ws + L.za,
                                  colstat_a_dev, zero_var_dev, ws + L.std_ws, std_bytes, stream)) return rc;

@@ -101,7 +101,8 @@ struct LapParams {
     int use_lists;
     int sweepers;            // CTAs that rebuild lists during a tail (<= G-1)
     int theta, eps0_div;     // eps schedule: eps0 = range*(P+1)/eps0_div, eps /= theta per phase
-    int smem_owner;          // 1: CTA 0 keeps the holder of every object in shared memory during a tail (unit capacities)
+    int early_stop;          // a phase with eps > 1 ends once <= early_stop persons are free (they bid again next phase)
+    int smem_owner;          // 1: every CTA keeps a replica of slot_owner (and minslot) in shared memory
 };
 
 struct Best {
@@ -398,7 +399,8 @@ __global__ void __launch_bounds__(kThreads, 1) lap_auction_kernel(const LapParam
     long long *sprice = reinterpret_cast<long long *>(smem_raw);
     size_t off = SMEMP ? ((size_t)no * 8 + 15) / 16 * 16 : 0;
     int *myq = reinterpret_cast<int *>(smem_raw + off);
-    int *sowner = myq + ((P.qcap + 3) & ~3);          // only used by CTA 0 when P.smem_owner
+    int *sowner = myq + ((P.qcap + 3) & ~3);          // [P] replica of slot_owner, only when P.smem_owner
+    int *sminslot = sowner + ((np + 3) & ~3);         // [O] replica of minslot, only when P.smem_owner && P.soff
     __shared__ long long red_b1[32], red_b2[32];
     __shared__ int red_j[32], wcnt[32];
     __shared__ int tq[kTailMax], tq_head, tq_cnt, tq_status, sw_stop;
@@ -438,6 +440,10 @@ __global__ void __launch_bounds__(kThreads, 1) lap_auction_kernel(const LapParam
             P.bidw[0][o] = 0ull; P.bidw[1][o] = 0ull; P.bidw[2][o] = 0ull;
         }
         if (SMEMP) for (int o = t; o < no; o += kThreads) sprice[o] = capacity(o) > 0 ? 0 : kInf;
+        if (P.smem_owner) {
+            for (int k = t; k < np; k += kThreads) sowner[k] = -1;
+            if (P.soff) for (int o = t; o < no; o += kThreads) sminslot[o] = __ldg(P.soff + o);
+        }
     }
     grid_barrier(P.bar, bar_target, G);
     const int cmin = __ldcg(P.gmm + 0), cmax = __ldcg(P.gmm + 1);
@@ -487,6 +493,7 @@ __global__ void __launch_bounds__(kThreads, 1) lap_auction_kernel(const LapParam
             const int f = (i < np) ? (phases == 1 ? 1 : __ldcg(P.flag + i)) : 0;
             if (f >= 2) {
                 P.slot_owner[f - 2] = -1;                    // identical write from every CTA; price stays
+                if (P.smem_owner) sowner[f - 2] = -1;
                 if (i % G == b) { P.person_obj[i] = -1; P.person_slot[i] = -1; }
             }
             int tot;
@@ -501,6 +508,7 @@ __global__ void __launch_bounds__(kThreads, 1) lap_auction_kernel(const LapParam
                     int ms; long long mp;
                     cheapest_slot(P, o, -1, 0, ms, mp);
                     P.minslot[o] = ms;                       // identical write from every CTA
+                    if (P.smem_owner) sminslot[o] = ms;
                 }
             }
         }
@@ -509,6 +517,11 @@ __global__ void __launch_bounds__(kThreads, 1) lap_auction_kernel(const LapParam
         // ---- bidding rounds --------------------------------------------------
         bool ran_tail = false;
         while (F > 0) {
+            // Incomplete phases (Bertsekas): eps-CS holds for every assigned pair whether or not the
+            // phase assigns everybody, so a phase with eps > 1 stops as soon as only a handful of
+            // persons are still fighting a price war; they re-enter the next phase's free list
+            // (person_obj == -1).  Only the eps == 1 phase has to run to completion.
+            if (eps > 1 && F <= P.early_stop) { F = 0; break; }
             if (F <= tail_t) {
                 // ---- Gauss-Seidel tail: few bidders left, a grid barrier per round would cost more
                 // than the bids.  CTA 0 alone drains a FIFO of free persons; every bid sees the
@@ -519,7 +532,6 @@ __global__ void __launch_bounds__(kThreads, 1) lap_auction_kernel(const LapParam
                 if (b == 0) {
                     if (t < F) tq[t] = __ldcg(P.list[cur] + t);
                     if (t == 0) { tq_head = 0; tq_cnt = F; tq_status = 0; }
-                    if (P.smem_owner) for (int o = t; o < no; o += kThreads) sowner[o] = __ldcg(P.slot_owner + o);
                     __syncthreads();
                     while (tq_cnt > 0 && tq_status == 0) {
                         // one bid: thread 0 books the result `s` of person i's scan (list or full row)
@@ -528,7 +540,7 @@ __global__ void __launch_bounds__(kThreads, 1) lap_auction_kernel(const LapParam
                         auto commit = [&](int i, int o, long long bid, int slot, int prev, int ms, long long mp) {
                             if (bid >= kBidLimit) tq_status = CYB_ERR_OVERFLOW;
                             if (tail_bids + rounds > P.max_rounds) tq_status = CYB_ERR_NOT_CONVERGED;
-                            if (P.smem_owner) sowner[o] = i;
+                            if (P.smem_owner) { sowner[slot] = i; if (P.soff) sminslot[o] = ms; }
                             P.slot_owner[slot] = i; P.slot_price[slot] = bid;
                             P.person_obj[i] = o; P.person_slot[i] = slot;
                             if (P.soff) P.minslot[o] = ms;
@@ -548,8 +560,8 @@ __global__ void __launch_bounds__(kThreads, 1) lap_auction_kernel(const LapParam
                             const int o = s.j1;
                             const long long lam = SMEMP ? sprice[o] : __ldcg(P.lambda + o);
                             const long long bid = lam + (s.b2 < kInf / 2 ? s.b2 - s.b1 : 0) + eps;
-                            const int slot = P.soff ? __ldcg(P.minslot + o) : o;
-                            const int prev = P.smem_owner ? sowner[o] : __ldcg(P.slot_owner + slot);
+                            const int slot = P.soff ? (P.smem_owner ? sminslot[o] : __ldcg(P.minslot + o)) : o;
+                            const int prev = P.smem_owner ? sowner[slot] : __ldcg(P.slot_owner + slot);
                             long long mp = bid; int ms = slot;
                             if (P.soff) cheapest_slot(P, o, slot, bid, ms, mp);
                             commit(i, o, bid, slot, prev, ms, mp);
@@ -669,17 +681,17 @@ __global__ void __launch_bounds__(kThreads, 1) lap_auction_kernel(const LapParam
                     const long long lam = SMEMP ? sprice[o] : __ldcg(P.lambda + o);
                     const long long bid = lam + (s.b2 < kInf / 2 ? s.b2 - s.b1 : 0) + eps;
                     if (bid >= kBidLimit) atomicExch(P.gmm + 2, CYB_ERR_OVERFLOW);
-                    const int slot = __ldcg(P.minslot + o);
-                    const int prev = __ldcg(P.slot_owner + slot);
+                    const int slot = P.soff ? (P.smem_owner ? sminslot[o] : __ldcg(P.minslot + o)) : o;
+                    const int prev = P.smem_owner ? sowner[slot] : __ldcg(P.slot_owner + slot);
                     P.rec[cur][q * G + b] = make_int4(o, slot, prev, 0);
                     atomicMax(P.bidw[cur] + o,
                               ((unsigned long long)bid << kPersonBits) | (kPersonMask - (unsigned long long)i));
                 }
             }
             grid_barrier(P.bar, bar_target, G);
-            status = __ldcg(P.gmm + 2);
-            if (status) break;
             // ---- resolve: every CTA replays every record ----------------------
+            // (the error flag is checked after the replay so that its load overlaps the record loads)
+            status = __ldcg(P.gmm + 2);
             const int nxt = cur == 2 ? 0 : cur + 1, prv = cur == 0 ? 2 : cur - 1;
             // clear the bid words of the previous round (their next use is two rounds ahead)
             for (int k = b * kThreads + t; k < prevF; k += G * kThreads)
@@ -700,6 +712,7 @@ __global__ void __launch_bounds__(kThreads, 1) lap_auction_kernel(const LapParam
                         int ms; long long mp;
                         cheapest_slot(P, rc.x, rc.y, bid, ms, mp);
                         P.minslot[rc.x] = ms;
+                        if (P.smem_owner) { sowner[rc.y] = i; if (P.soff) sminslot[rc.x] = ms; }
                         if (SMEMP) { sprice[rc.x] = mp; if (mine) P.lambda[rc.x] = mp; }
                         else P.lambda[rc.x] = mp;
                         if (mine) {
@@ -720,6 +733,7 @@ __global__ void __launch_bounds__(kThreads, 1) lap_auction_kernel(const LapParam
             F = Fn;
             cur = nxt;
             __syncthreads();
+            if (status) break;
         }
         if (status) break;
         grid_barrier(P.bar, bar_target, G);        // state of the last resolve / the tail becomes visible
@@ -733,10 +747,14 @@ __global__ void __launch_bounds__(kThreads, 1) lap_auction_kernel(const LapParam
         if (ran_tail) {
             status = __ldcg(P.gmm + 2);
             if (status) break;
-            if (SMEMP) {                            // pick up the prices CTA 0 moved during the tail
-                for (int o = t; o < no; o += kThreads) sprice[o] = __ldcg(P.lambda + o);
-                __syncthreads();
+            if (eps > 1 && b != 0) {                // pick up what CTA 0 moved during the tail
+                if (SMEMP) for (int o = t; o < no; o += kThreads) sprice[o] = __ldcg(P.lambda + o);
+                if (P.smem_owner) {
+                    for (int k = t; k < np; k += kThreads) sowner[k] = __ldcg(P.slot_owner + k);
+                    if (P.soff) for (int o = t; o < no; o += kThreads) sminslot[o] = __ldcg(P.minslot + o);
+                }
             }
+            __syncthreads();
         }
         if (eps == 1) break;
         eps /= P.theta;
@@ -937,11 +955,13 @@ extern "C" int cyb_lap_solve_i32(const int32_t *cost_dev, int64_t ld, int64_t n_
     P.lst_hdr = reinterpret_cast<longlong2 *>(ws + L.lst_hdr);
     P.lst_ent = reinterpret_cast<int2 *>(ws + L.lst_ent);
     P.tail_t = 8;
+    P.early_stop = 0;      // measured: postponed price wars get longer at smaller eps
     P.use_lists = 1;
     P.theta = kTheta; P.eps0_div = kEps0Div;
     if (const char *e = getenv("CYB_LAP_THETA")) P.theta = std::max(2, atoi(e));
     if (const char *e = getenv("CYB_LAP_EPS0")) P.eps0_div = std::max(1, atoi(e));
     if (const char *e = getenv("CYB_LAP_TAIL")) P.tail_t = atoi(e);
+    if (const char *e = getenv("CYB_LAP_EARLY")) P.early_stop = std::max(0, atoi(e));
     if (const char *e = getenv("CYB_LAP_LISTS")) P.use_lists = atoi(e);
 
     // small block: barrier counter, cmin = INT_MAX, cmax = INT_MIN, status = 0
@@ -954,8 +974,9 @@ extern "C" int cyb_lap_solve_i32(const int32_t *cost_dev, int64_t ld, int64_t n_
     const size_t static_smem = 32 * 8 * 2 + 32 * 4 * 2 + kTailMax * 4 + 160;
     const bool smemp = smem_with_price + static_smem <= (size_t)max_smem;
     size_t dyn = smemp ? smem_with_price : q_bytes;
-    const size_t owner_bytes = cyb::align_up((size_t)no * 4, 16);
-    P.smem_owner = (!slot_offset_dev && dyn + owner_bytes + static_smem <= (size_t)max_smem) ? 1 : 0;
+    const size_t owner_bytes = cyb::align_up((size_t)np * 4, 16) + (slot_offset_dev ? cyb::align_up((size_t)no * 4, 16) : 0);
+    P.smem_owner = (dyn + owner_bytes + static_smem <= (size_t)max_smem) ? 1 : 0;
+    if (const char *e = getenv("CYB_LAP_SMEM_OWNER")) P.smem_owner = P.smem_owner && atoi(e);
     if (P.smem_owner) dyn += owner_bytes;
 
     const void *fn = smemp ? (const void *)lap_auction_kernel<true> : (const void *)lap_auction_kernel<false>;

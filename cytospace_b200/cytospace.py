@@ -15,35 +15,35 @@ import time
 import numpy as np
 
 from . import chunking
-from .linear_assignment_solvers import SOLVER_METHODS, get_engine
+from .linear_assignment_solvers import DISTANCE_METRICS, SOLVER_METHODS, get_engine
 
-_GPU_METHODS = ("lapjv", "lapjv_compat", "lapjv_b200")
+_GPU_METHODS = SOLVER_METHODS
 
 
 def solve_linear_assignment_problem(scRNA_norm_data, st_norm_data, cell_number_to_node_assignment,
                                     solver_method, solver, seed, distance_metric, process_idx=None):
-    """cytospace.py:304-351 for ``solver_method`` in {lapjv, lapjv_compat, lapjv_b200}.
+    """cytospace.py:304-351 for ``solver_method`` in {lapjv, lapjv_compat, lapjv_b200, lap_CSPR} and
+    ``distance_metric`` in {Pearson_correlation, Spearman_correlation, Euclidean}.
 
     Parameters as the reference: normalised genes x cells arrays, cell count per spot, the
     solver name, the solver callable (ignored: cost build and solve are fused on the device),
     ``seed`` (accepted for signature parity; the integer path breaks ties by index instead of
-    the reference's 1e-16 * U(0,1) noise, cytospace.py:325-327), the distance metric and a
-    ``process_idx`` returned as is.
+    the reference's 1e-16 * U(0,1) noise, cytospace.py:325-327; the lap_CSPR path uses it to seed
+    its integer tie noise, cytospace.py:336-337, drawn from a counter-based hash instead of
+    MT19937), the distance metric and a ``process_idx`` returned as is.
     Returns ``(mapped_st_index: List[int] of length n_cells, process_idx)`` -- element c is the
     column index in ``st_norm_data`` of the spot that cell c is mapped to."""
     if solver_method not in _GPU_METHODS:
-        if solver_method == "lap_CSPR":
-            raise NotImplementedError("lap_CSPR is not on the accelerated path (SURVEY section 8(f) #4)")
         raise ValueError("Invalid solver_method provided")
-    if distance_metric != "Pearson_correlation":
-        raise NotImplementedError(f"distance metric {distance_metric} is not on the accelerated path; "
-                                  "use Pearson_correlation")
+    if distance_metric not in DISTANCE_METRICS:
+        raise ValueError(f"Invalid distance_metric provided: {distance_metric}")
     eng = get_engine()
     print("Building cost matrix ...")
     print("Solving linear assignment problem ...")
     t0 = time.perf_counter()
     spot_of_cell, res, _ = eng.assign(np.asarray(scRNA_norm_data), np.asarray(st_norm_data),
-                                      cell_number_to_node_assignment)
+                                      cell_number_to_node_assignment, metric=distance_metric,
+                                      cspr_seed=(seed if solver_method == "lap_CSPR" else None))
     mapped_st_index = spot_of_cell.cpu().numpy().tolist()
     print(f"Time to build cost matrix and solve linear assignment problem: "
           f"{round(time.perf_counter() - t0, 2)} seconds")
@@ -96,8 +96,8 @@ def apply_linear_assignment(scRNA_data, st_data, coordinates_data, cell_number_t
         raise ValueError("index_st_list and subsampled_cell_number_to_node_assignment_list cannot both be specified")
     if solver_method not in _GPU_METHODS:
         raise ValueError("Invalid solver_method provided")
-    if distance_metric != "Pearson_correlation":
-        raise NotImplementedError(f"distance metric {distance_metric} is not on the accelerated path")
+    if distance_metric not in DISTANCE_METRICS:
+        raise ValueError(f"Invalid distance_metric provided: {distance_metric}")
     sc_np = scRNA_data.to_numpy()
     st_np = st_data.to_numpy()
     cn = np.asarray(cell_number_to_node_assignment)
@@ -105,7 +105,12 @@ def apply_linear_assignment(scRNA_data, st_data, coordinates_data, cell_number_t
                                 subsampled_cell_number_to_node_assignment_list)
     if len(plan) > 1:
         print(f"Number of required processors: {len(plan)}")
-    mapped = chunking.solve_chunks(get_engine(), sc_np, st_np, plan, log_tpm=True)
+    assign_kw = {}
+    if distance_metric != "Pearson_correlation":
+        assign_kw["metric"] = distance_metric
+    if solver_method == "lap_CSPR":
+        assign_kw["cspr_seed"] = seed
+    mapped = chunking.solve_chunks(get_engine(), sc_np, st_np, plan, log_tpm=True, **assign_kw)
     locations, cell_ids = [], []
     for chunk, mapped_st_index in zip(plan, mapped):
         coords = coordinates_data if chunk.st_index is None else coordinates_data.iloc[chunk.st_index]

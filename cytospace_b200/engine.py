@@ -22,6 +22,8 @@ from . import _native
 
 COST_SCALE = 10 ** 6           # integer scale of the correlation distance; precedent cytospace.py:337
 PRECISIONS = {"f16": 0, "f16x3": 1}
+#: ``--distance-metric`` values (argument_parser.py:72-74) -> CYB_METRIC_*
+METRICS = {"Pearson_correlation": 0, "Spearman_correlation": 1, "Euclidean": 2}
 STAT_NAMES = ("status", "phases", "rounds", "bids", "passes", "cost_min", "cost_max", "scale",
               "grid", "smem_prices", "rounds_le1", "max_bidders", "phase_scans", "tail_bids", "tails", "list_hits")
 
@@ -113,9 +115,12 @@ class AssignmentEngine:
 
     # --------------------------------------------------------------- cost build
     def cost_build(self, sc: torch.Tensor, st: torch.Tensor, log_tpm: bool = False, out: torch.Tensor | None = None,
-                   return_colstats: bool = False, check_variance: bool = True, layout: str = "cells_x_spots"):
-        """Integer cost ``rint(-cost_scale * pearson)`` as int32, row-major with ld = columns rounded
-        up to 32.  ``layout="cells_x_spots"`` ([N, ld]: the TRANSPOSE of the reference's ``cost``, a
+                   return_colstats: bool = False, check_variance: bool = True, layout: str = "cells_x_spots",
+                   metric: str = "Pearson_correlation"):
+        """Integer cost as int32, row-major with ld = columns rounded up to 32:
+        ``rint(-cost_scale * r)`` for the Pearson / Spearman correlation r, ``rint(cost_scale * d)`` for
+        the Euclidean distance d (linear_assignment_solvers.py:46-59).
+        ``layout="cells_x_spots"`` ([N, ld]: the TRANSPOSE of the reference's ``cost``, a
         cell's row contiguous) or ``"spots_x_cells"`` ([S, ld]: the reference's own orientation).
 
         sc [G x N], st [G x S]: float64 / float32 device tensors, genes x cells row-major -- the
@@ -140,6 +145,10 @@ class AssignmentEngine:
         if G == 0 or N == 0 or S == 0:
             raise ValueError("empty expression matrix")
         prec = PRECISIONS[self.precision]
+        if metric not in METRICS:
+            raise ValueError(f"distance_metric must be one of {sorted(METRICS)}")
+        if return_colstats and metric != "Pearson_correlation":
+            raise ValueError("column statistics are only returned for Pearson_correlation")
         if layout not in ("cells_x_spots", "spots_x_cells"):
             raise ValueError("layout must be 'cells_x_spots' or 'spots_x_cells'")
         rows, cols = (N, S) if layout == "cells_x_spots" else (S, N)
@@ -148,7 +157,7 @@ class AssignmentEngine:
             out = torch.empty((rows, ld), dtype=torch.int32, device=self.device)
         elif out.shape[0] < rows or out.stride(0) < cols or out.dtype != torch.int32:
             raise ValueError("bad `out` buffer")
-        ws_bytes = self.lib.cyb_cost_build_workspace_bytes(G, N, S, prec)
+        ws_bytes = self.lib.cyb_cost_build_metric_workspace_bytes(METRICS[metric], G, N, S, prec)
         ws = self._workspace("cost", ws_bytes + 1024)
         off = (-ws.data_ptr()) % 1024
         colstat_sc = torch.empty((2, N), dtype=torch.float64, device=self.device) if return_colstats else None
@@ -159,14 +168,22 @@ class AssignmentEngine:
         # the library builds cost[first, second]; the first matrix supplies the rows
         a, b, na, nb, csa, csb = (sc, st, N, S, colstat_sc, colstat_st) if layout == "cells_x_spots" \
             else (st, sc, S, N, colstat_st, colstat_sc)
-        _native.check(self.lib.cyb_cost_build_pearson(
-            _native.ptr("void *", a), _native.ptr("void *", b), dt, G, na, nb, a.stride(0), b.stride(0),
-            int(bool(log_tpm)), prec, self.cost_scale, _native.ptr("int32_t *", out), out.stride(0),
-            _native.ptr("double *", csa), _native.ptr("double *", csb),
-            _native.ptr("int32_t *", zero_var), self.ffi.cast("void *", ws.data_ptr() + off), ws_bytes,
-            self._stream()))
+        if metric == "Pearson_correlation":
+            _native.check(self.lib.cyb_cost_build_pearson(
+                _native.ptr("void *", a), _native.ptr("void *", b), dt, G, na, nb, a.stride(0), b.stride(0),
+                int(bool(log_tpm)), prec, self.cost_scale, _native.ptr("int32_t *", out), out.stride(0),
+                _native.ptr("double *", csa), _native.ptr("double *", csb),
+                _native.ptr("int32_t *", zero_var), self.ffi.cast("void *", ws.data_ptr() + off), ws_bytes,
+                self._stream()))
+        else:
+            _native.check(self.lib.cyb_cost_build(
+                METRICS[metric], _native.ptr("void *", a), _native.ptr("void *", b), dt, G, na, nb, a.stride(0),
+                b.stride(0), int(bool(log_tpm)), prec, self.cost_scale, _native.ptr("int32_t *", out), out.stride(0),
+                _native.ptr("int32_t *", zero_var), self.ffi.cast("void *", ws.data_ptr() + off), ws_bytes,
+                self._stream()))
         self._mark("cost", 1)
         self._zero_var = zero_var
+        self._zero_var_metric = metric
         if check_variance:
             self.check_zero_variance()
         if return_colstats:
@@ -176,9 +193,45 @@ class AssignmentEngine:
     def check_zero_variance(self):
         """Raises if the last cost build met a zero-variance column (one small D2H read)."""
         nz = int(self._zero_var.item())
+        if nz and getattr(self, "_zero_var_metric", "") == "Euclidean":
+            raise ValueError(f"{nz} distance(s) cannot be represented (cost_scale * distance >= 2^30)")
         if nz:
-            raise ValueError(f"{nz} cell/spot column(s) have zero variance: Pearson correlation undefined "
+            raise ValueError(f"{nz} cell/spot column(s) have zero variance: correlation undefined "
                              "(the reference would hand NaN costs to the solver)")
+
+    def rank_columns(self, x: torch.Tensor, log_tpm: bool = False) -> torch.Tensor:
+        """``pd.DataFrame(x).rank().values`` (common.py:207-208) for a [G x n] float64 / float32 device
+        matrix: float32 [G x n] average ranks."""
+        if x.dim() != 2 or not x.is_cuda or x.dtype not in (torch.float64, torch.float32):
+            raise ValueError("rank_columns takes a 2-D float64/float32 device matrix")
+        if x.stride(1) != 1:
+            x = x.contiguous()
+        G, n = x.shape
+        out = torch.empty((G, n), dtype=torch.float32, device=self.device)
+        ws_bytes = self.lib.cyb_rank_workspace_bytes(G, n)
+        ws = self._workspace("rank", ws_bytes + 256)
+        off = (-ws.data_ptr()) % 256
+        dt = self.lib.CYB_F64 if x.dtype == torch.float64 else self.lib.CYB_F32
+        self._mark("rank", 0)
+        _native.check(self.lib.cyb_rank_columns(_native.ptr("void *", x), dt, G, n, x.stride(0), int(bool(log_tpm)),
+                                                _native.ptr("float *", out), out.stride(0),
+                                                self.ffi.cast("void *", ws.data_ptr() + off), ws_bytes, self._stream()))
+        self._mark("rank", 1)
+        return out
+
+    def expand_with_noise(self, cost: torch.Tensor, n_cols: int, row_map, seed: int, noise_lo: int = 1,
+                          noise_span: int = 10) -> torch.Tensor:
+        """``cost[location_repeat, :]`` (linear_assignment_solvers.py:63-66) plus the integer tie noise
+        of the lap_CSPR path (cytospace.py:337-340): int32 [n_slots x ld]."""
+        rm = torch.as_tensor(np.asarray(row_map), dtype=torch.int32).to(self.device)
+        n_rows = int(rm.numel())
+        ld = _round_up(n_cols, 32)
+        out = torch.empty((n_rows, ld), dtype=torch.int32, device=self.device)
+        _native.check(self.lib.cyb_expand_rows_noise_i32(
+            _native.ptr("int32_t *", cost), cost.stride(0), n_rows, n_cols, _native.ptr("int32_t *", rm),
+            int(seed) & ((1 << 64) - 1), int(noise_lo), int(noise_span), _native.ptr("int32_t *", out), ld,
+            self._stream()))
+        return out
 
     def quantise(self, cost_f64: torch.Tensor, scale: float) -> torch.Tensor:
         """int32 ``rint(scale * cost)`` of a float64 device matrix (entry P2)."""
@@ -267,8 +320,13 @@ class AssignmentEngine:
         return {"max_violation": v, "total": t, "invalid_rows": bad, "capacity_mismatch": badcap}
 
     # --------------------------------------------------------------- whole path
-    def assign(self, sc, st, cell_number_to_node_assignment, log_tpm: bool = False):
+    def assign(self, sc, st, cell_number_to_node_assignment, log_tpm: bool = False,
+               metric: str = "Pearson_correlation", cspr_seed: int | None = None):
         """cost build + LAP + ``location_repeat[assignment]`` (cytospace.py:319-331).
+
+        ``cspr_seed`` not None selects the integerised lap_CSPR formulation (cytospace.py:334-347):
+        the slot expansion is materialised with per-(slot, cell) integer noise in [1, 10] and solved
+        as a square LAP (slots bid for cells).
 
         Returns ``(spot_of_cell int64 device tensor [N], LapResult, cost int32 device matrix)``; the
         matrix is persons x objects of the solve: spots x cells when every spot takes one cell, cells x
@@ -285,17 +343,27 @@ class AssignmentEngine:
         if n != N:
             raise ValueError(f"the assignment must be square: sum(cell_number_to_node_assignment)={n} "
                              f"but {N} cells were given")
-        if (cn == 1).all():
+        if cspr_seed is not None:
+            compact = self.cost_build(sc, st, log_tpm=log_tpm, check_variance=False, layout="spots_x_cells",
+                                      metric=metric)
+            location_repeat = np.repeat(np.arange(S), cn)
+            cost = self.expand_with_noise(compact, N, location_repeat, cspr_seed)
+            res = self.lap_solve(cost, None, n_persons=N, n_objects=N)
+            lr = torch.from_numpy(location_repeat).to(self.device)
+            spot_of_cell = lr[res.slot_owner.long()]
+        elif (cn == 1).all():
             # square LAP: the spots bid for the cells (the reference's own orientation).  Either side
             # may bid; measured on B200 the noisier side (the cells) makes the better OBJECTS -- larger
             # gaps between a bidder's best and second-best object, shorter price wars.
-            cost = self.cost_build(sc, st, log_tpm=log_tpm, check_variance=False, layout="spots_x_cells")
+            cost = self.cost_build(sc, st, log_tpm=log_tpm, check_variance=False, layout="spots_x_cells",
+                                   metric=metric)
             res = self.lap_solve(cost, None, n_persons=S, n_objects=N)
             spot_of_cell = res.slot_owner.long()
         else:
             # location_repeat (linear_assignment_solvers.py:63-65) becomes the spots' capacities:
             # the cells bid for spots that hold cn[s] cells each
-            cost = self.cost_build(sc, st, log_tpm=log_tpm, check_variance=False, layout="cells_x_spots")
+            cost = self.cost_build(sc, st, log_tpm=log_tpm, check_variance=False, layout="cells_x_spots",
+                                   metric=metric)
             res = self.lap_solve(cost, cn, n_persons=N, n_objects=S)
             spot_of_cell = res.person_obj.long()
         self.check_zero_variance()                   # one sync, after the solve

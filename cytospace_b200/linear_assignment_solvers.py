@@ -1,5 +1,5 @@
 """Host-side mirror of ``cytospace/linear_assignment_solvers/linear_assignment_solvers.py``
-for the lapjv / Pearson branch: same function names, argument meaning and error behaviour,
+(every solver method and distance metric): same function names, argument meaning and error behaviour,
 with the arithmetic done by the sm_100a kernels behind the C ABI.
 """
 from __future__ import annotations
@@ -14,7 +14,8 @@ from .engine import AssignmentEngine, COST_SCALE
 #: ``--solver-method`` values served here.  ``lapjv`` / ``lapjv_compat`` are the reference's own
 #: names (argument_parser.py:69-71); ``lapjv_b200`` is the new value a maintainer adds to that
 #: ``choices`` list to route cost build + solve through this package.
-SOLVER_METHODS = ("lapjv", "lapjv_compat", "lapjv_b200")
+SOLVER_METHODS = ("lapjv", "lapjv_compat", "lapjv_b200", "lap_CSPR")
+DISTANCE_METRICS = ("Pearson_correlation", "Spearman_correlation", "Euclidean")
 
 _engine = None
 
@@ -52,23 +53,21 @@ def call_solver(solver, solver_method, cost_scaled):
 
 def calculate_cost(expressions_tpm_scRNA_log, expressions_tpm_st_log, cell_number_to_node_assignment,
                    solver_method, distance_metric):
-    """linear_assignment_solvers.py:42-69 for the non-CSPR Pearson branch (:53-55, :63-66).
+    """linear_assignment_solvers.py:42-69, all three metrics (:46-59) and the slot expansion (:63-66).
 
     Compatibility form: returns ``(distance_repeat float64 [n x N], location_repeat int [n])`` on
     the host like the reference, where ``distance_repeat`` is the device-built integer matrix
-    divided by the integer scale (so it is quantised to 1e-6).  The fast path
+    divided by the integer scale (so it is quantised to 1e-6).  ``solver_method`` only selects the
+    reference's branch (:46 vs :53); both build the same matrix.  The fast path
     (``cytospace.solve_linear_assignment_problem``) never materialises this expansion."""
-    if solver_method == "lap_CSPR":
-        raise NotImplementedError("lap_CSPR is not on the accelerated path (SURVEY section 8(f) #4)")
-    if distance_metric != "Pearson_correlation":
-        raise NotImplementedError(f"distance metric {distance_metric} is not on the accelerated path "
-                                  "(SURVEY section 8(f) #3); use Pearson_correlation")
+    if distance_metric not in DISTANCE_METRICS:
+        raise ValueError(f"Invalid distance_metric provided: {distance_metric}")
     print("Building cost matrix ...")
     t0 = time.perf_counter()
     eng = get_engine()
     sc = eng.to_device(np.asarray(expressions_tpm_scRNA_log, dtype=np.float64))
     st = eng.to_device(np.asarray(expressions_tpm_st_log, dtype=np.float64))
-    cost_i32 = eng.cost_build(sc, st)                      # cells x spots on the device
+    cost_i32 = eng.cost_build(sc, st, metric=distance_metric)                      # cells x spots on the device
     n_spots = st.shape[1]
     cost = cost_i32[:, :n_spots].T.cpu().numpy().astype(np.float64) / COST_SCALE    # spots x cells like the reference
     location_repeat = np.repeat(np.arange(len(cell_number_to_node_assignment)),

@@ -25,6 +25,14 @@
  *       <- lapjv.lapjv(cost) as called by call_solver,
  *          linear_assignment_solvers.py:34-40 (third-party lapjv==1.3.14) from
  *          solve_linear_assignment_problem, cytospace/cytospace.py:323-332
+ *   cyb_rank_columns / cyb_cost_gemm_euclid_i32 / cyb_cost_build
+ *       <- the other two `--distance-metric` values (argument_parser.py:72-74):
+ *          matrix_correlation_spearman, cytospace/common/common.py:202-215
+ *          (pd.DataFrame(v).rank() then the Pearson formula) and
+ *          scipy cdist(.., 'euclidean'), linear_assignment_solvers.py:51,59
+ *   cyb_expand_rows_noise_i32
+ *       <- the integerised lap_CSPR matrix, cytospace/cytospace.py:334-340:
+ *          int(1e6 * cost[location_repeat, :] + 10 * U(0,1) + 1)
  *   cyb_lap_check_i32
  *       <- no reference counterpart: on-device optimality certificate
  *          (eps-complementary slackness of the returned prices)
@@ -39,7 +47,7 @@
 extern "C" {
 #endif
 
-#define CYB_ABI_VERSION 3
+#define CYB_ABI_VERSION 4
 
 /* status codes */
 #define CYB_OK                 0
@@ -53,6 +61,11 @@ extern "C" {
 /* input element types of the expression matrices */
 #define CYB_F64 0
 #define CYB_F32 1
+
+/* distance metrics (--distance-metric, argument_parser.py:72-74) */
+#define CYB_METRIC_PEARSON   0
+#define CYB_METRIC_SPEARMAN  1
+#define CYB_METRIC_EUCLIDEAN 2
 
 /* operand precision of the correlation GEMM (fp16 operands, fp32 accumulate) */
 #define CYB_PREC_F16    0   /* one fp16 pass                                         */
@@ -131,6 +144,60 @@ int cyb_cost_build_pearson(const void *a_dev, const void *b_dev, int x_dtype,
                            double *colstat_a_dev, double *colstat_b_dev,
                            int32_t *zero_var_dev, void *workspace_dev,
                            size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------- Spearman / Euclidean / lap_CSPR */
+
+/* Bytes of scratch cyb_rank_columns needs. */
+size_t cyb_rank_workspace_bytes(int64_t n_genes, int64_t n_cols);
+
+/* Per-column average ranks, `pd.DataFrame(x).rank().values` (common.py:207-208; method
+ * "average", ascending, 1-based; ties are exact ties of the float64 values, NaN counts as 0):
+ *   rank[g, c] = #{g': x[g',c] < x[g,c]} + (#{g': x[g',c] == x[g,c]} + 1) / 2
+ *   x_dev     [n_genes x n_cols] row-major, float64 or float32, leading dimension ld_x
+ *   log_tpm   1: rank normalize_data(x) (common.py:142-147) instead of x
+ *   rank_dev  float32 [n_genes x ld_rank] out (exact: ranks are multiples of 0.5 below 2^24)
+ * One CTA per column: the column is sorted in shared memory (bitonic network on
+ * order-preserving 64-bit keys), every element binary-searches its tie group.            */
+int cyb_rank_columns(const void *x_dev, int x_dtype, int64_t n_genes, int64_t n_cols,
+                     int64_t ld_x, int log_tpm, float *rank_dev, int64_t ld_rank,
+                     void *workspace_dev, size_t workspace_bytes, void *stream);
+
+/* Euclidean distance from the standardised operands of cyb_standardise and its colstat output
+ * ([mean | sigma] per column):  with r = (1/n_genes) * sum_k za[a,k] * zb[b,k],
+ *   |a - b|^2 = n_genes * ((mu_a - mu_b)^2 + (sd_a - sd_b)^2 + 2 sd_a sd_b (1 - r))
+ *   cost[a, b] = rint(scale * sqrt(.))
+ * -- the same tcgen05 GEMM as cyb_cost_gemm_i32 with a float64 epilogue; no cancellation of the
+ * large norms.  bad_dev int32[1] is incremented per entry >= 2^30 (clamped).               */
+int cyb_cost_gemm_euclid_i32(const void *za_dev, const void *zb_dev, int64_t n_a, int64_t n_b,
+                             int64_t k, int64_t n_genes, float scale, const double *colstat_a_dev,
+                             const double *colstat_b_dev, int32_t *cost_dev, int64_t ld_cost,
+                             int32_t *bad_dev, void *stream);
+
+/* Bytes of device workspace cyb_cost_build needs for `metric`. */
+size_t cyb_cost_build_metric_workspace_bytes(int metric, int64_t n_genes, int64_t n_a, int64_t n_b,
+                                             int precision);
+
+/* calculate_cost (linear_assignment_solvers.py:42-59) for any --distance-metric:
+ *   CYB_METRIC_PEARSON    cost = rint(-cost_scale * pearson(a_i, b_j))
+ *   CYB_METRIC_SPEARMAN   cost = rint(-cost_scale * pearson(rank(a_i), rank(b_j)))
+ *   CYB_METRIC_EUCLIDEAN  cost = rint( cost_scale * ||a_i - b_j||_2)
+ * Arguments as cyb_cost_build_pearson.  bad_dev int32[1] is incremented per zero-variance
+ * column (correlations) or per unrepresentable entry (Euclidean).                         */
+int cyb_cost_build(int metric, const void *a_dev, const void *b_dev, int x_dtype,
+                   int64_t n_genes, int64_t n_a, int64_t n_b, int64_t ld_a, int64_t ld_b,
+                   int log_tpm, int precision, double cost_scale, int32_t *cost_dev,
+                   int64_t ld_cost, int32_t *bad_dev, void *workspace_dev,
+                   size_t workspace_bytes, void *stream);
+
+/* out[i, j] = cost[row_map[i], j] + noise_lo + floor(noise_span * U(seed, i, j))  (int32):
+ * the slot expansion cost[location_repeat, :] (linear_assignment_solvers.py:63-66) with the
+ * integer tie noise of the lap_CSPR path (cytospace.py:337-340: + 10 * rand + 1, i.e.
+ * noise_lo = 1, noise_span = 10).  U is a counter-based hash (splitmix64 of seed, i, j), not
+ * the reference's MT19937 stream.  row_map_dev NULL: identity; noise_span 0: no noise.     */
+int cyb_expand_rows_noise_i32(const int32_t *cost_dev, int64_t ld, int64_t n_rows_out,
+                              int64_t n_cols, const int32_t *row_map_dev, uint64_t seed,
+                              int noise_lo, int noise_span, int32_t *out_dev, int64_t ld_out,
+                              void *stream);
 
 /* out[i, j] = rint(scale * in[i, j]) as int32 (entry P2: an n_rows x n_cols float64
  * cost matrix built by the reference itself).  bad_dev int32[1] is incremented by

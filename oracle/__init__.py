@@ -136,7 +136,7 @@ def min_reduced_cost_i32(cost, u, v, row_map=None) -> int:
                                               _ptr(v, ctypes.c_int64)))
 
 
-def auction_model(m, cap=None, theta=4, eps0_div=4, tail_t=0, round_cap=0, variant=1):
+def auction_model(m, cap=None, theta=4, eps0_div=4, tail_t=0, round_cap=0, variant=1, early_stop=0):
     """Sequential model of the device auction.  ``m`` is persons x objects (cells x spots: the
     TRANSPOSE of the reference's cost), ``cap`` the object capacities (None: all 1).
     Returns (person_obj, slot_owner, total, lambda, stats, round_log)."""
@@ -149,6 +149,7 @@ def auction_model(m, cap=None, theta=4, eps0_div=4, tail_t=0, round_cap=0, varia
     person_obj = np.empty(P, np.int32); slot_owner = np.empty(P, np.int32)
     lam = np.zeros(O, np.int64); total = np.zeros(1, np.int64); stats = np.zeros(6, np.int64)
     rlog = np.zeros(max(round_cap, 1), np.int32)
+    ctypes.c_int.in_dll(lib, "auction_early_stop").value = int(early_stop)     # device knob CYB_LAP_EARLY (default 0)
     rc = lib.auction_model_i32(P, O, _ptr(m, ctypes.c_int32), m.shape[1], _ptr(capa, ctypes.c_int32),
                                _ptr(person_obj, ctypes.c_int32), _ptr(slot_owner, ctypes.c_int32),
                                _ptr(lam, ctypes.c_int64), _ptr(total, ctypes.c_int64),

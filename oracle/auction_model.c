@@ -32,6 +32,8 @@
 int64_t auction_list_hits = 0, auction_list_miss = 0;
 int auction_list_groups = 0;       /* 0 = lists off; else number of groups (32 = warps, 1024 = threads) */
 int auction_list_cap = 64;
+int auction_early_stop = 0;     /* >0: a phase with eps > 1 ends as soon as <= this many persons are free; they carry over */
+int64_t auction_phase_log[64][4];   /* per phase: free at start, rounds, bids, tail bids */
 int auction_list_refresh = 0;   /* >0: every R tail bids all persons' lists are rebuilt at current prices (idle-CTA sweep model) */
 #define LIST_MAX 1024
 typedef struct { int n; int64_t bound; int32_t obj[LIST_MAX]; } cand_t;
@@ -127,7 +129,10 @@ int auction_model_i32(int P, int O, const int32_t *m, int64_t ld, const int32_t 
             }
         }
         if (st[0] > 1 && variant) for (int o = 0; o < O; ++o) if (soff[o + 1] > soff[o]) REFRESH(o);
+        const int64_t ph_r0 = st[1], ph_b0 = st[2], ph_t0 = st[5];
+        if (st[0] <= 64) auction_phase_log[st[0] - 1][0] = nfree;
         while (nfree > 0) {
+            if (eps > 1 && nfree <= auction_early_stop) break;    /* the free persons bid again in the next phase */
             if (nfree <= tail_t) {
                 /* Gauss-Seidel tail (what CTA 0 runs alone on the device): FIFO of free persons */
                 int head = 0, tailp = nfree % P, cnt = nfree;
@@ -250,6 +255,10 @@ int auction_model_i32(int P, int O, const int32_t *m, int64_t ld, const int32_t 
                 if (bidr[o] >= 0) { REFRESH(o); bidr[o] = -1; }
             }
             int32_t *tmp = freel; freel = nextl; nextl = tmp; nfree = nnext;
+        }
+        if (st[0] <= 64) {
+            auction_phase_log[st[0] - 1][1] = st[1] - ph_r0; auction_phase_log[st[0] - 1][2] = st[2] - ph_b0;
+            auction_phase_log[st[0] - 1][3] = st[5] - ph_t0;
         }
         if (eps == 1) break;
         eps = eps / theta; if (eps < 1) eps = 1;

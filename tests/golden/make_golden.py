@@ -5,7 +5,12 @@
    four absent third-party modules stubbed): normalize_data (common.py:142-147),
    matrix_correlation_pearson (common.py:190-199), calculate_cost
    (linear_assignment_solvers.py:42-69) and partition_indices (cytospace.py:150-209) on small
-   seeded inputs.
+   seeded inputs; the Spearman / Euclidean branches of calculate_cost (common.py:202-215,
+   linear_assignment_solvers.py:51,59); and the reference's own solve_linear_assignment_problem
+   (cytospace.py:304-351) run END TO END for every metric and for both solver branches, with the
+   absent third-party solvers replaced by SciPy's linear_sum_assignment behind their call
+   conventions (a `lapjv.lapjv`-shaped callable; a recording fake of
+   ortools.graph.pywrapgraph.LinearSumAssignment) -> mapped_st_index vectors.
 2. lap_golden.npz  -- small integer LAP instances with their optimal total from
    scipy.optimize.linear_sum_assignment (independent implementation) and the permutation of the
    repo's JV restatement (oracle/lapjv_oracle.c) so the restatement itself cannot drift.
@@ -47,6 +52,52 @@ def import_reference():
     return normalize_data, matrix_correlation_pearson, calculate_cost, partition_indices
 
 
+def scipy_lapjv(cost):
+    """A callable with the `lapjv.lapjv` return convention backed by SciPy."""
+    from scipy.optimize import linear_sum_assignment
+    ri, ci = linear_sum_assignment(cost)
+    row_ind = np.empty(len(ri), np.int32); col_ind = np.empty(len(ri), np.int32)
+    row_ind[ri] = ci; col_ind[ci] = ri
+    return row_ind, col_ind, (float(cost[ri, ci].sum()), None, None)
+
+
+class FakeLinearSumAssignment:
+    """Records the arcs match_solution adds (linear_assignment_solvers.py:72-96) and solves them with
+    SciPy; a skipped arc (integer cost exactly 0, :79) is forbidden, as in ortools."""
+    OPTIMAL, INFEASIBLE, POSSIBLE_OVERFLOW = 0, 1, 2
+    last = None
+
+    def __init__(self):
+        self.arcs = {}
+        FakeLinearSumAssignment.last = self
+
+    def AddArcWithCost(self, worker, task, cost):
+        self.arcs[(worker, task)] = cost
+
+    def Solve(self):
+        from scipy.optimize import linear_sum_assignment
+        n = 1 + max(max(w for w, _ in self.arcs), max(t for _, t in self.arcs))
+        big = 2 ** 40
+        m = np.full((n, n), big, dtype=np.int64)
+        for (w, t), c in self.arcs.items():
+            m[w, t] = c
+        ri, ci = linear_sum_assignment(m)
+        self.n, self.mate, self.m = n, ci, m
+        return self.OPTIMAL if (m[ri, ci] < big).all() else self.INFEASIBLE
+
+    def NumNodes(self):
+        return self.n
+
+    def RightMate(self, i):
+        return int(self.mate[i])
+
+    def AssignmentCost(self, i):
+        return int(self.m[i, self.mate[i]])
+
+    def OptimalCost(self):
+        return int(sum(self.AssignmentCost(i) for i in range(self.n)))
+
+
 def main():
     from cytospace_b200 import synthetic as syn
     import oracle
@@ -66,6 +117,23 @@ def main():
         out[f"{tag}_sc"] = sc; out[f"{tag}_st"] = st; out[f"{tag}_cn"] = cn
         out[f"{tag}_sc_norm"] = sc_n; out[f"{tag}_st_norm"] = st_n
         out[f"{tag}_corr"] = corr; out[f"{tag}_distance_repeat"] = dist_rep; out[f"{tag}_location_repeat"] = loc_rep
+        # the other metrics and the reference's own solve, end to end
+        import cytospace.linear_assignment_solvers.linear_assignment_solvers as las
+        from cytospace.cytospace import solve_linear_assignment_problem
+        las.pywrapgraph.LinearSumAssignment = FakeLinearSumAssignment
+        for metric, key in (("Pearson_correlation", "pearson"), ("Spearman_correlation", "spearman"),
+                            ("Euclidean", "euclid")):
+            with contextlib.redirect_stdout(io.StringIO()):
+                d_rep, _ = calculate_cost(sc_n, st_n, cn, "lapjv", metric)
+                d_cspr, _ = calculate_cost(sc_n, st_n, cn, "lap_CSPR", metric)
+                mapped, _ = solve_linear_assignment_problem(sc_n, st_n, cn, "lapjv", scipy_lapjv, 1, metric)
+                mapped_cspr, _ = solve_linear_assignment_problem(sc_n, st_n, cn, "lap_CSPR", None, 1, metric)
+            assert np.array_equal(d_rep, d_cspr)          # both branches build the same matrix
+            out[f"{tag}_{key}_distance_repeat"] = d_rep
+            out[f"{tag}_{key}_mapped"] = np.asarray(mapped, dtype=np.int64)
+            out[f"{tag}_{key}_mapped_cspr"] = np.asarray(mapped_cspr, dtype=np.int64)
+            if key == "pearson":      # the integer matrix the reference handed to the solver (cells x slots)
+                out[f"{tag}_cspr_int"] = FakeLinearSumAssignment.last.m.copy()
     # --- partition_indices (no shuffle, and shuffle under a fixed global seed)
     p1 = partition_indices(np.arange(1800), split_by_category_list=np.array([500, 1000, 300]),
                            split_by_interval_int=400, shuffle=False)

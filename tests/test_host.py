@@ -115,10 +115,38 @@ def test_assign_ranks_balances_and_is_deterministic():
 def test_solver_surface_mirrors_reference():
     from cytospace_b200 import linear_assignment_solvers as las
     with pytest.raises(NotImplementedError, match="not a supported solver"):
-        las.import_solver("lap_CSPR")
+        las.import_solver("lap_CSPR")                                # LAS:20-22: only the two lapjv names import
     assert callable(las.import_solver("lapjv")) and callable(las.import_solver("lapjv_compat"))
     assert las.call_solver(lambda c: (0, "y_lapjv", 1), "lapjv", None) == "y_lapjv"
     assert las.call_solver(lambda c: (0, 1, "y_lap"), "lapjv_compat", None) == "y_lap"
     from cytospace_b200.cytospace import solve_linear_assignment_problem
     with pytest.raises(ValueError, match="Invalid solver_method"):
         solve_linear_assignment_problem(None, None, None, "bogus", None, 1, "Pearson_correlation")
+    with pytest.raises(ValueError, match="Invalid distance_metric"):
+        solve_linear_assignment_problem(None, None, None, "lapjv", None, 1, "Manhattan")
+    assert set(las.DISTANCE_METRICS) == {"Pearson_correlation", "Spearman_correlation", "Euclidean"}
+    assert "lap_CSPR" in las.SOLVER_METHODS
+
+
+def test_metric_entry_points_validate_arguments_without_gpu():
+    lib, ffi = _native.load(), _native.ffi()
+    assert lib.cyb_rank_workspace_bytes(20000, 10000) >= 10000 * 8
+    assert lib.cyb_rank_workspace_bytes(40000, 100) > lib.cyb_rank_workspace_bytes(20000, 100)   # multi-run scratch
+    pe = lib.cyb_cost_build_metric_workspace_bytes(lib.CYB_METRIC_PEARSON, 2000, 1000, 1000, lib.CYB_PREC_F16X3)
+    assert pe == lib.cyb_cost_build_workspace_bytes(2000, 1000, 1000, lib.CYB_PREC_F16X3)
+    sp = lib.cyb_cost_build_metric_workspace_bytes(lib.CYB_METRIC_SPEARMAN, 2000, 1000, 1000, lib.CYB_PREC_F16X3)
+    assert sp >= pe + 2 * 2000 * 1000 * 4                              # float32 rank matrices
+    assert lib.cyb_cost_build_metric_workspace_bytes(lib.CYB_METRIC_EUCLIDEAN, 2000, 1000, 1000, lib.CYB_PREC_F16X3) > pe
+    rc = lib.cyb_rank_columns(ffi.NULL, lib.CYB_F64, 10, 10, 10, 0, ffi.NULL, 10, ffi.NULL, 0, ffi.NULL)
+    assert rc == lib.CYB_ERR_INVALID and b"null" in ffi.string(lib.cyb_last_error())
+    p16 = ffi.cast("void *", 256)
+    rc = lib.cyb_rank_columns(p16, 7, 10, 10, 10, 0, ffi.cast("float *", 256), 10, p16, 1 << 20, ffi.NULL)
+    assert rc == lib.CYB_ERR_INVALID and b"dtype" in ffi.string(lib.cyb_last_error())
+    rc = lib.cyb_cost_build(9, p16, p16, lib.CYB_F64, 10, 10, 10, 10, 10, 0, lib.CYB_PREC_F16, 1e6,
+                            ffi.cast("int32_t *", 256), 32, ffi.NULL, p16, 1 << 30, ffi.NULL)
+    assert rc == lib.CYB_ERR_INVALID and b"metric" in ffi.string(lib.cyb_last_error())
+    rc = lib.cyb_expand_rows_noise_i32(ffi.NULL, 8, 8, 8, ffi.NULL, 1, 1, 10, ffi.NULL, 8, ffi.NULL)
+    assert rc == lib.CYB_ERR_INVALID
+    rc = lib.cyb_cost_gemm_euclid_i32(p16, p16, 8, 8, 64, 100, 1.0, ffi.NULL, ffi.NULL, ffi.cast("int32_t *", 256), 8,
+                                      ffi.NULL, ffi.NULL)
+    assert rc == lib.CYB_ERR_INVALID

@@ -122,3 +122,80 @@ def test_cost_oracle_errors_and_degenerate():
     assert np.all(n[:, 0] == 0) and np.all(np.isfinite(n))       # all-zero column -> zeros (common.py:143-146)
     r = co.matrix_correlation_pearson(n, n)
     assert np.isnan(r[0, 1]) and abs(r[1, 1] - 1) < 1e-12         # sigma == 0 -> NaN (common.py:196-197)
+
+
+# ---- Spearman / Euclidean / lap_CSPR -------------------------------------------
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+@pytest.mark.parametrize("metric,key", [("Pearson_correlation", "pearson"), ("Spearman_correlation", "spearman"),
+                                        ("Euclidean", "euclid")])
+def test_metric_oracle_matches_reference_calculate_cost(cost_golden, tag, metric, key):
+    """Golden = the reference's calculate_cost for every --distance-metric (LAS:46-59)."""
+    g = cost_golden
+    dist_rep, loc_rep = co.calculate_cost(g[f"{tag}_sc_norm"], g[f"{tag}_st_norm"], g[f"{tag}_cn"], metric)
+    np.testing.assert_allclose(dist_rep, g[f"{tag}_{key}_distance_repeat"], rtol=0, atol=1e-10)
+    assert np.array_equal(loc_rep, g[f"{tag}_location_repeat"])
+
+
+def test_average_ranks_restatement_equals_pandas():
+    import pandas as pd
+    rng = np.random.default_rng(5)
+    x = rng.poisson(0.4, (300, 17)).astype(np.float64)         # heavy ties
+    x[:, 3] = 2.5                                              # constant column
+    x[::7, 5] = -0.0
+    assert np.array_equal(co.average_ranks(x), pd.DataFrame(x).rank().values)
+    y = rng.normal(size=(64, 5))
+    assert np.array_equal(co.average_ranks(y), pd.DataFrame(y).rank().values)
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+@pytest.mark.parametrize("key,metric", [("pearson", "Pearson_correlation"), ("spearman", "Spearman_correlation"),
+                                        ("euclid", "Euclidean")])
+def test_oracle_solve_equals_reference_solve_end_to_end(cost_golden, tag, key, metric):
+    """Golden `mapped` = the reference's own solve_linear_assignment_problem (CYT:304-351) with SciPy
+    behind the lapjv convention.  The restated float64 JV on the reference's formulation
+    (distance_repeat + 1e-16 * rand, CYT:325-327) reaches the same total cost."""
+    g = cost_golden
+    dist_rep, loc_rep = co.calculate_cost(g[f"{tag}_sc_norm"], g[f"{tag}_st_norm"], g[f"{tag}_cn"], metric)
+    n = dist_rep.shape[0]
+    np.random.seed(1)
+    cost_scaled = dist_rep + 1e-16 * np.random.rand(n, n)
+    _, colsol, (total, _, _) = oracle.lapjv_f64(cost_scaled)
+    mapped = loc_rep[colsol]
+    ref = g[f"{tag}_{key}_mapped"]
+    compact = co.metric_cost(g[f"{tag}_sc_norm"], g[f"{tag}_st_norm"], metric)          # spots x cells
+    tot_ours = compact[mapped, np.arange(n)].sum(); tot_ref = compact[ref, np.arange(n)].sum()
+    assert abs(tot_ours - tot_ref) <= 1e-9 * max(1.0, abs(tot_ref))
+    assert np.array_equal(np.bincount(mapped, minlength=len(g[f"{tag}_cn"])), g[f"{tag}_cn"])
+    assert np.array_equal(np.bincount(ref, minlength=len(g[f"{tag}_cn"])), g[f"{tag}_cn"])
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_cspr_matrix_restatement_equals_reference(cost_golden, tag):
+    """Golden `cspr_int` = the arcs the reference's match_solution handed to (a recording fake of)
+    ortools for seed 1: int(1e6 * d + 10 * rand + 1) transposed (CYT:335-340)."""
+    g = cost_golden
+    want = g[f"{tag}_cspr_int"]
+    got = co.cspr_matrix_reference(g[f"{tag}_pearson_distance_repeat"], 1)
+    assert got.shape == want.shape
+    skipped = want == 2 ** 40                                   # arcs of cost 0 are skipped (LAS:79)
+    assert np.array_equal(got[~skipped], want[~skipped]) and np.all(got[skipped] == 0)
+    # JV on this integer matrix reproduces the reference's lap_CSPR assignment cost
+    n = want.shape[0]
+    rowsol, colsol, (total, _, _) = oracle.lapjv_i32(np.ascontiguousarray(got.astype(np.int32)))
+    loc_rep = g[f"{tag}_location_repeat"]
+    ref_mapped = g[f"{tag}_pearson_mapped_cspr"]
+    assert np.array_equal(np.bincount(loc_rep[rowsol], minlength=len(g[f"{tag}_cn"])), g[f"{tag}_cn"])
+    compact = co.metric_cost(g[f"{tag}_sc_norm"], g[f"{tag}_st_norm"])
+    mine = compact[loc_rep[rowsol], np.arange(n)].sum(); ref = compact[ref_mapped, np.arange(n)].sum()
+    assert abs(mine - ref) <= n * 11e-6                          # both optimal up to the [1, 11) noise
+
+
+def test_hash_noise_known_answers_and_range():
+    """Known answers computed with an independent C transcription of the splitmix64 hash."""
+    assert co.hash_noise(1, 3, 5).tolist() == [[4, 6, 8, 7, 9], [6, 5, 9, 9, 2], [10, 6, 10, 4, 9]]
+    z = co.hash_noise(12345, 200, 300)
+    assert z.min() == 1 and z.max() == 10
+    assert abs(z.mean() - 5.5) < 0.05
+    assert np.array_equal(co.hash_noise(12345, 200, 300), z)
+    assert not np.array_equal(co.hash_noise(12346, 200, 300), z)
