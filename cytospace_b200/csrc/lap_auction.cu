@@ -101,6 +101,7 @@ struct LapParams {
     int use_lists;
     int sweepers;            // CTAs that rebuild lists during a tail (<= G-1)
     int theta, eps0_div;     // eps schedule: eps0 = range*(P+1)/eps0_div, eps /= theta per phase
+    int tail_mode;           // 0: Gauss-Seidel FIFO tail, 1: Jacobi rounds inside CTA 0 (one warp per bidder)
     int early_stop;          // a phase with eps > 1 ends once <= early_stop persons are free (they bid again next phase)
     int smem_owner;          // 1: every CTA keeps a replica of slot_owner (and minslot) in shared memory
 };
@@ -404,6 +405,8 @@ __global__ void __launch_bounds__(kThreads, 1) lap_auction_kernel(const LapParam
     __shared__ long long red_b1[32], red_b2[32];
     __shared__ int red_j[32], wcnt[32];
     __shared__ int tq[kTailMax], tq_head, tq_cnt, tq_status, sw_stop;
+    __shared__ int lj_obj[32], lj_need[32];
+    __shared__ long long lj_bid[32];
 
     const int G = gridDim.x, b = blockIdx.x, t = threadIdx.x;
     const long long S = (long long)np + 1;
@@ -454,7 +457,7 @@ __global__ void __launch_bounds__(kThreads, 1) lap_auction_kernel(const LapParam
     int status = 0;
     int cur = 0;             // buffer of the current round; the previous round used (cur + 2) % 3
     int prevF = 0;           // records of the previous round (their bid words are cleared in this resolve)
-    const int tail_t = min(P.tail_t, kTailMax);
+    const int tail_t = min(P.tail_t, P.tail_mode == 1 ? 32 : kTailMax);
     // candidate-list keys pack (value << 18 | object): needs every value < 2^46, i.e. scaled costs < 2^45
     // (prices are bounded by kBidLimit = 2^45 already)
     const bool use_lists = P.use_lists && G > 1 && ((long long)cmax - (long long)cmin + 1) * S < (1ll << 45);
@@ -533,7 +536,123 @@ __global__ void __launch_bounds__(kThreads, 1) lap_auction_kernel(const LapParam
                     if (t < F) tq[t] = __ldcg(P.list[cur] + t);
                     if (t == 0) { tq_head = 0; tq_cnt = F; tq_status = 0; }
                     __syncthreads();
-                    while (tq_cnt > 0 && tq_status == 0) {
+                    // ---- tail mode 1: the SAME synchronous (Jacobi) rounds as the grid runs, but inside
+                    // CTA 0: warp w serves bidder w from its candidate list (a full-row scan by the whole CTA
+                    // when the list cannot certify the result), warp 0 resolves the <= 32 bids with
+                    // match.any / redux and commits the winners.  No grid barrier, and because the round
+                    // semantics are unchanged the assignment does not depend on where the switch happens.
+                    // one thread: person i takes the cheapest slot of object o at price `bid`; returns the
+                    // person it evicts (-1: the slot was free)
+                    auto assign_one = [&](int i, int o, long long bid) -> int {
+                        if (bid >= kBidLimit) tq_status = CYB_ERR_OVERFLOW;
+                        const int slot = P.soff ? (P.smem_owner ? sminslot[o] : __ldcg(P.minslot + o)) : o;
+                        const int prev = P.smem_owner ? sowner[slot] : __ldcg(P.slot_owner + slot);
+                        long long mp = bid; int ms = slot;
+                        if (P.soff) cheapest_slot(P, o, slot, bid, ms, mp);
+                        if (P.smem_owner) { sowner[slot] = i; if (P.soff) sminslot[o] = ms; }
+                        P.slot_owner[slot] = i; P.slot_price[slot] = bid;
+                        P.person_obj[i] = o; P.person_slot[i] = slot;
+                        if (P.soff) P.minslot[o] = ms;
+                        P.lambda[o] = mp;
+                        if (SMEMP) sprice[o] = mp;
+                        if (prev >= 0) { P.person_obj[prev] = -1; P.person_slot[prev] = -1; }
+                        return prev;
+                    };
+                    while (P.tail_mode == 1) {
+                        int Fc = tq_cnt;
+                        if (Fc == 0 || tq_status != 0) break;
+                        const int w = t >> 5, lane = t & 31;
+                        if (Fc == 1 && use_lists) {
+                            // a single chain: warp 0 follows it alone (a round with one bidder needs no
+                            // resolution), fetching the evicted person's list the moment it is known
+                            if (w == 0) {
+                                int i = tq[0], nb = 0;
+                                ListRegs lr = list_fetch(P, i);
+                                for (;;) {
+                                    Best s;
+                                    if (!list_eval<SMEMP>(P, i, lr, cmin, S, price_rd, s)) break;     // needs a row scan
+                                    const long long lam = SMEMP ? sprice[s.j1] : __ldcg(P.lambda + s.j1);
+                                    const long long bid = lam + (s.b2 < kInf / 2 ? s.b2 - s.b1 : 0) + eps;
+                                    int prev = 0;
+                                    if (lane == 0) prev = assign_one(i, s.j1, bid);
+                                    prev = __shfl_sync(0xffffffffu, prev, 0);
+                                    ++nb;
+                                    i = prev;
+                                    if (i < 0) break;
+                                    lr = list_fetch(P, i);
+                                    if (bid >= kBidLimit || tail_bids + rounds + nb > P.max_rounds) break;
+                                }
+                                if (lane == 0) {
+                                    lj_need[0] = nb;                                   // bids made on the fast path
+                                    if (i >= 0) tq[0] = i;
+                                    tq_cnt = i >= 0 ? 1 : 0;
+                                    if (tail_bids + rounds + nb > P.max_rounds) tq_status = CYB_ERR_NOT_CONVERGED;
+                                }
+                            }
+                            __syncthreads();
+                            tail_bids += lj_need[0]; list_hits += lj_need[0];
+                            Fc = tq_cnt;
+                            const int st = tq_status;
+                            __syncthreads();                                           // lj_need[0] is rewritten below
+                            if (Fc == 0 || st != 0) break;
+                        }
+                        if (w < Fc) {
+                            const int i = tq[w];
+                            Best s{0, 0, 0};
+                            bool ok = false;
+                            if (use_lists) {
+                                const ListRegs lr = list_fetch(P, i);
+                                ok = list_eval<SMEMP>(P, i, lr, cmin, S, price_rd, s);
+                            }
+                            if (lane == 0) {
+                                lj_need[w] = ok ? 0 : 1;
+                                if (ok) {
+                                    const long long lam = SMEMP ? sprice[s.j1] : __ldcg(P.lambda + s.j1);
+                                    lj_obj[w] = s.j1;
+                                    lj_bid[w] = lam + (s.b2 < kInf / 2 ? s.b2 - s.b1 : 0) + eps;
+                                }
+                            }
+                        }
+                        __syncthreads();
+                        int misses = 0;
+                        for (int k = 0; k < Fc; ++k) misses += lj_need[k];               // uniform across the CTA
+                        if (misses) {
+                            for (int k = 0; k < Fc; ++k) {
+                                if (!lj_need[k]) continue;
+                                const Best s = scan_row<SMEMP>(rowptr(tq[k]), no, cmin, S, price_rd, vec_ok, red_b1, red_b2, red_j);
+                                if (t == 0) {
+                                    const long long lam = SMEMP ? sprice[s.j1] : __ldcg(P.lambda + s.j1);
+                                    lj_obj[k] = s.j1;
+                                    lj_bid[k] = lam + (s.b2 < kInf / 2 ? s.b2 - s.b1 : 0) + eps;
+                                }
+                            }
+                            __syncthreads();
+                        }
+                        tail_bids += Fc; list_hits += Fc - misses;
+                        if (w == 0) {
+                            const bool act = lane < Fc;
+                            const int i = act ? tq[lane] : -1;
+                            const int o = act ? lj_obj[lane] : -1;
+                            const long long bid = act ? lj_bid[lane] : 0;
+                            bool win = act;                        // highest bid on the object, lowest person on ties
+                            for (int j = 0; j < Fc; ++j) {
+                                const int oj = lj_obj[j], ij = tq[j];
+                                const long long bj = lj_bid[j];
+                                if (j != lane && oj == o && (bj > bid || (bj == bid && ij < i))) win = false;
+                            }
+                            __syncwarp();
+                            int entry = i;                         // who is free after this round
+                            if (win) entry = assign_one(i, o, bid);
+                            const unsigned stay = __ballot_sync(0xffffffffu, entry >= 0);
+                            if (entry >= 0) tq[__popc(stay & ((1u << lane) - 1u))] = entry;
+                            if (lane == 0) {
+                                tq_cnt = __popc(stay);
+                                if (tail_bids + rounds > P.max_rounds) tq_status = CYB_ERR_NOT_CONVERGED;
+                            }
+                        }
+                        __syncthreads();
+                    }
+                    while (P.tail_mode == 0 && tq_cnt > 0 && tq_status == 0) {
                         // one bid: thread 0 books the result `s` of person i's scan (list or full row)
                         // commit one bid (one thread): person i takes `slot` of object o at price `bid`,
                         // evicting `prev`; (ms, mp) = the object's cheapest slot / price afterwards
@@ -827,6 +946,94 @@ __global__ void __launch_bounds__(kChkThreads) lap_rowmin_kernel(
     }
 }
 
+// Whole-row variant for price vectors that fit in shared memory (objects <= kChkWholeMax): every CTA
+// stages ALL prices once, a TEAM of four warps streams one row at a time (rows are dealt to ~8 teams
+// per SM, so a 10k-row matrix still balances to within one row in nine), and the certificate terms of
+// that row (violation, cost, capacity count) are taken in the same pass -- no row-minimum buffer, no
+// atomics on it, no second kernel.  acc = {max violation, total, invalid rows} (zero-initialised).
+constexpr int kChkWholeMax = 12288;              // 96 KB of prices -> two CTAs per SM
+constexpr int kTeam = 128;                       // threads per row team
+constexpr int kTeams = kChkThreads / kTeam;
+
+__global__ void __launch_bounds__(kChkThreads) lap_rowcheck_whole_kernel(
+    const int32_t *__restrict__ cost, long long ld, int np, int no, const int32_t *__restrict__ person_obj,
+    const long long *__restrict__ price, long long S, int32_t *__restrict__ count, long long *__restrict__ acc) {
+    extern __shared__ __align__(16) long long spw[];
+    __shared__ long long part[2][kTeams][kTeam / 32];
+    __shared__ long long r_viol[kTeams], r_tot[kTeams];
+    __shared__ int r_bad[kTeams];
+    for (int j = threadIdx.x; j < no; j += kChkThreads) spw[j] = price[j];
+    __syncthreads();
+    const int team = threadIdx.x / kTeam, tt = threadIdx.x % kTeam, lane = tt & 31, wt = tt >> 5;
+    const unsigned long long pol = l2_policy_evict_first();
+    const bool vec_ok = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(cost) & 15) == 0);
+    const int n4 = vec_ok ? (no >> 2) : 0;
+    long long viol = 0, tot = 0;
+    int bad = 0, it = 0;
+    for (int i = blockIdx.x * kTeams + team; i < np; i += gridDim.x * kTeams, ++it) {
+        const int32_t *r = cost + (long long)i * ld;
+        long long m = LLONG_MAX;
+        const int4 *r4 = reinterpret_cast<const int4 *>(r);
+#pragma unroll 8
+        for (int q = tt; q < n4; q += kTeam) {
+            const int4 c = ld_stream(r4 + q, pol);
+            const longlong2 a = *reinterpret_cast<const longlong2 *>(spw + 4 * q);
+            const longlong2 bb = *reinterpret_cast<const longlong2 *>(spw + 4 * q + 2);
+            m = min(m, (long long)c.x * S + a.x);
+            m = min(m, (long long)c.y * S + a.y);
+            m = min(m, (long long)c.z * S + bb.x);
+            m = min(m, (long long)c.w * S + bb.y);
+        }
+        for (int j = (n4 << 2) + tt; j < no; j += kTeam) m = min(m, (long long)__ldg(r + j) * S + spw[j]);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, d));
+        if (lane == 0) part[it & 1][team][wt] = m;
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "r"(kTeam) : "memory");     // the team only
+        if (tt == 0) {
+#pragma unroll
+            for (int k = 0; k < kTeam / 32; ++k) m = min(m, part[it & 1][team][k]);
+            const int o = __ldg(person_obj + i);
+            if (o < 0 || o >= no) ++bad;
+            else {
+                const int c = __ldg(r + o);
+                tot += c;
+                atomicAdd(count + o, 1);
+                viol = max(viol, (long long)c * S + spw[o] - m);
+            }
+        }
+    }
+    if (tt == 0) { r_viol[team] = viol; r_tot[team] = tot; r_bad[team] = bad; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < kTeams; ++k) { viol = max(viol, r_viol[k]); tot += r_tot[k]; bad += r_bad[k]; }
+        if (viol > 0) atomicMax(acc + 0, viol);
+        if (tot) atomicAdd(reinterpret_cast<unsigned long long *>(acc + 1), (unsigned long long)tot);
+        if (bad) atomicAdd(reinterpret_cast<unsigned long long *>(acc + 2), (unsigned long long)bad);
+    }
+}
+
+// capacities + hand the accumulators to the caller's out[4] (single CTA-independent finish)
+__global__ void lap_check_publish_kernel(const int32_t *__restrict__ soff, int no, const int32_t *__restrict__ count,
+                                         long long *__restrict__ acc, long long *__restrict__ out,
+                                         unsigned int *__restrict__ done) {
+    long long bad = 0;
+    for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < no; o += gridDim.x * blockDim.x) {
+        const int cap = soff ? soff[o + 1] - soff[o] : 1;
+        if (count[o] != cap) ++bad;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) bad += __shfl_xor_sync(0xffffffffu, bad, d);
+    if ((threadIdx.x & 31) == 0 && bad) atomicAdd(reinterpret_cast<unsigned long long *>(acc + 3), (unsigned long long)bad);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(done, 1u) == gridDim.x - 1) {          // last CTA publishes
+            __threadfence();
+            for (int k = 0; k < 4; ++k) out[k] = __ldcg(acc + k);
+        }
+    }
+}
+
 __global__ void lap_check_finish_kernel(const int32_t *__restrict__ cost, long long ld, int np, int no,
                                         const int32_t *__restrict__ person_obj,
                                         const long long *__restrict__ price, long long S,
@@ -882,7 +1089,7 @@ WsLayout ws_layout(int64_t np, int64_t no) {
     L.person_slot = take((size_t)np * 4);
     L.minslot = take((size_t)no * 4);
     L.rowmin = take((size_t)np * 8);
-    L.count = take((size_t)no * 4);
+    L.count = take(cyb::align_up((size_t)no * 4, 64) + 64);      // counts, then {4 x int64 accumulators, ticket}
     L.lst_hdr = take((size_t)np * 16);
     L.lst_ent = take((size_t)np * kListK * 8);
     L.small = take(256);
@@ -955,11 +1162,14 @@ extern "C" int cyb_lap_solve_i32(const int32_t *cost_dev, int64_t ld, int64_t n_
     P.lst_hdr = reinterpret_cast<longlong2 *>(ws + L.lst_hdr);
     P.lst_ent = reinterpret_cast<int2 *>(ws + L.lst_ent);
     P.tail_t = 8;
+    P.tail_mode = 1;
     P.early_stop = 0;      // measured: postponed price wars get longer at smaller eps
     P.use_lists = 1;
     P.theta = kTheta; P.eps0_div = kEps0Div;
     if (const char *e = getenv("CYB_LAP_THETA")) P.theta = std::max(2, atoi(e));
     if (const char *e = getenv("CYB_LAP_EPS0")) P.eps0_div = std::max(1, atoi(e));
+    if (const char *e = getenv("CYB_LAP_TAIL_MODE")) P.tail_mode = atoi(e) ? 1 : 0;
+    P.tail_t = P.tail_mode == 1 ? 32 : 8;
     if (const char *e = getenv("CYB_LAP_TAIL")) P.tail_t = atoi(e);
     if (const char *e = getenv("CYB_LAP_EARLY")) P.early_stop = std::max(0, atoi(e));
     if (const char *e = getenv("CYB_LAP_LISTS")) P.use_lists = atoi(e);
@@ -971,7 +1181,7 @@ extern "C" int cyb_lap_solve_i32(const int32_t *cost_dev, int64_t ld, int64_t n_
 
     const size_t q_bytes = cyb::align_up((size_t)P.qcap * 4, 16);
     const size_t smem_with_price = cyb::align_up((size_t)no * 8, 16) + q_bytes;
-    const size_t static_smem = 32 * 8 * 2 + 32 * 4 * 2 + kTailMax * 4 + 160;
+    const size_t static_smem = 2048;              // bound on the kernel's static shared memory (ptxas: 1552 B)
     const bool smemp = smem_with_price + static_smem <= (size_t)max_smem;
     size_t dyn = smemp ? smem_with_price : q_bytes;
     const size_t owner_bytes = cyb::align_up((size_t)np * 4, 16) + (slot_offset_dev ? cyb::align_up((size_t)no * 4, 16) : 0);
@@ -1011,6 +1221,30 @@ extern "C" int cyb_lap_check_i32(const int32_t *cost_dev, int64_t ld, int64_t n_
     char *ws = static_cast<char *>(workspace_dev);
     long long *rowmin = reinterpret_cast<long long *>(ws + L.rowmin);
     int32_t *count = reinterpret_cast<int32_t *>(ws + L.count);
+    int dev0 = 0, sms0 = 0;
+    CYB_CUDA_CHECK(cudaGetDevice(&dev0));
+    CYB_CUDA_CHECK(cudaDeviceGetAttribute(&sms0, cudaDevAttrMultiProcessorCount, dev0));
+    if (no <= kChkWholeMax) {
+        // one memset (counts + accumulators + ticket), one pass over the matrix, one tiny publish kernel
+        const size_t acc_off = cyb::align_up((size_t)no * 4, 64);
+        long long *acc = reinterpret_cast<long long *>(ws + L.count + acc_off);            // 4 x int64, then the ticket
+        unsigned int *done = reinterpret_cast<unsigned int *>(ws + L.count + acc_off + 32);
+        CYB_CUDA_CHECK(cudaMemsetAsync(count, 0, acc_off + 64, stream));
+        const size_t smem = (size_t)no * 8;
+        CYB_CUDA_CHECK(cudaFuncSetAttribute(lap_rowcheck_whole_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        CYB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lap_rowcheck_whole_kernel, kChkThreads, smem));
+        if (per_sm < 1) per_sm = 1;
+        int grid = (int)std::min<long long>((long long)sms0 * per_sm, (np + kTeams - 1) / kTeams);
+        lap_rowcheck_whole_kernel<<<grid, kChkThreads, smem, stream>>>(
+            cost_dev, ld, (int)np, (int)no, person_obj_dev, reinterpret_cast<const long long *>(price_dev), np + 1, count, acc);
+        CYB_CUDA_CHECK(cudaGetLastError());
+        const int pgrid = (int)std::min<long long>(sms0, (no + 255) / 256);
+        lap_check_publish_kernel<<<pgrid, 256, 0, stream>>>(slot_offset_dev, (int)no, count, acc,
+                                                            reinterpret_cast<long long *>(out_dev), done);
+        CYB_CUDA_CHECK(cudaGetLastError());
+        return CYB_OK;
+    }
     CYB_CUDA_CHECK(cudaMemsetAsync(rowmin, 0x7F, (size_t)np * 8, stream));     // large positive sentinel
     CYB_CUDA_CHECK(cudaMemsetAsync(count, 0, (size_t)no * 4, stream));
     const long long out_init[4] = {LLONG_MIN, 0, 0, 0};

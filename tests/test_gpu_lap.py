@@ -64,20 +64,60 @@ def test_result_independent_of_grid_size(engine, grid):
     assert res.total == ref.total and np.array_equal(po, po_ref)      # deterministic tie-breaks
 
 
-def test_matches_cpu_model_of_the_device_algorithm(engine):
-    """Same tie-breaks as oracle/auction_model.c: identical assignment, not just identical total."""
+def _with_env(env, fn):
+    import os
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update({k: str(v) for k, v in env.items()})
+    try:
+        return fn()
+    finally:
+        for k, v in old.items():
+            if v is None:
+                del os.environ[k]
+            else:
+                os.environ[k] = v
+
+
+@pytest.mark.parametrize("tail", [0, 2, 32])
+def test_matches_cpu_model_of_the_device_algorithm(engine, tail):
+    """Same tie-breaks as oracle/auction_model.c: identical assignment, not just identical total.  The
+    in-CTA tail runs the same synchronous rounds as the grid, so the result equals the pure-Jacobi
+    model wherever the switch to the tail happens."""
     rng = np.random.default_rng(3)
     cap = rng.integers(0, 6, 70).astype(np.int32)
     m = rng.integers(-1000, 1000, (int(cap.sum()), 70), dtype=np.int32)
-    import os
-    os.environ["CYB_LAP_TAIL"] = "2"                   # same Jacobi / Gauss-Seidel switch point as the model run
-    try:
-        res, po = solve_and_check(engine, m, cap)
-    finally:
-        del os.environ["CYB_LAP_TAIL"]
+    res, po = _with_env({"CYB_LAP_TAIL": tail, "CYB_LAP_TAIL_MODE": 1}, lambda: solve_and_check(engine, m, cap))
+    po_model, so_model, tot_model, _, _, _ = oracle.auction_model(m, cap, tail_t=0)
+    assert res.total == tot_model and np.array_equal(po, po_model)
+    assert np.array_equal(res.slot_owner.cpu().numpy(), so_model)
+    sq = rng.integers(0, 50, (90, 90), dtype=np.int32)                            # unit capacities, many ties
+    res, po = _with_env({"CYB_LAP_TAIL": tail, "CYB_LAP_TAIL_MODE": 1}, lambda: solve_and_check(engine, sq))
+    assert np.array_equal(po, oracle.auction_model(sq, tail_t=0)[0])
+
+
+def test_gauss_seidel_tail_mode_matches_its_model(engine):
+    """The alternative tail (CYB_LAP_TAIL_MODE=0: one bid at a time, FIFO) against the model's FIFO tail."""
+    rng = np.random.default_rng(3)
+    cap = rng.integers(0, 6, 70).astype(np.int32)
+    m = rng.integers(-1000, 1000, (int(cap.sum()), 70), dtype=np.int32)
+    res, po = _with_env({"CYB_LAP_TAIL": 2, "CYB_LAP_TAIL_MODE": 0}, lambda: solve_and_check(engine, m, cap))
     po_model, so_model, tot_model, _, _, _ = oracle.auction_model(m, cap, tail_t=2)
     assert res.total == tot_model and np.array_equal(po, po_model)
     assert np.array_equal(res.slot_owner.cpu().numpy(), so_model)
+
+
+@pytest.mark.parametrize("mode,tail", [(0, 8), (1, 8), (1, 32), (1, 0)])
+def test_tail_modes_reach_the_same_optimum(engine, mode, tail):
+    sc, st, cn = syn.structured_counts(1200, 200, 800, 6, seed=1004)
+    from oracle import cost_oracle as co
+    compact = co.cost_matrix_i32(co.normalize_data(sc), co.normalize_data(st))
+    m = np.ascontiguousarray(compact.T)
+    res, _ = _with_env({"CYB_LAP_TAIL": tail, "CYB_LAP_TAIL_MODE": mode},
+                       lambda: solve_and_check(engine, m, cn.astype(np.int32)))
+    assert res.total == oracle.lapjv_i32(compact, np.repeat(np.arange(200, dtype=np.int32), 6))[2][0]
+    sq = syn.uniform_cost_i32(700, seed=3)
+    res, _ = _with_env({"CYB_LAP_TAIL": tail, "CYB_LAP_TAIL_MODE": mode}, lambda: solve_and_check(engine, sq))
+    assert res.total == oracle.lapjv_i32(sq)[2][0]
 
 
 @pytest.mark.parametrize("n_obj,max_cap,seed", [(1, 7, 0), (5, 4, 1), (40, 6, 2), (333, 9, 3), (1000, 3, 4)])
@@ -157,3 +197,44 @@ def test_lap_errors(engine):
     with pytest.raises(ValueError, match="square"):
         engine.lap_solve(torch.zeros((4, 32), dtype=torch.int32, device=engine.device), np.array([1, 1]),
                          n_persons=4, n_objects=2)
+
+
+def test_certificate_detects_wrong_assignments(engine):
+    """The certificate is a checker, not a rubber stamp: a swapped pair, an invalid object and a broken
+    capacity are each reported."""
+    cost = np.random.default_rng(8).integers(0, 1_000_000, (500, 500), dtype=np.int32)
+    dev = to_dev(engine, cost)
+    res = engine.lap_solve(dev, None, n_persons=500, n_objects=500)
+    good = engine.lap_check(dev, res)
+    assert good == {"max_violation": good["max_violation"], "total": res.total, "invalid_rows": 0, "capacity_mismatch": 0}
+    assert good["max_violation"] <= 1
+    po = res.person_obj.clone()
+    res.person_obj = po.clone(); res.person_obj[[3, 4]] = po[[4, 3]]              # still a permutation, not optimal
+    bad = engine.lap_check(dev, res)
+    assert bad["max_violation"] > 1 and bad["capacity_mismatch"] == 0 and bad["total"] != res.total
+    res.person_obj = po.clone(); res.person_obj[7] = po[8]                         # object po[8] twice, po[7] never
+    assert engine.lap_check(dev, res)["capacity_mismatch"] == 2
+    res.person_obj = po.clone(); res.person_obj[9] = -1
+    out = engine.lap_check(dev, res)
+    assert out["invalid_rows"] == 1 and out["capacity_mismatch"] == 1
+
+
+def test_certificate_tiled_variant_above_12288_objects(engine):
+    """More than 12 288 objects: the price vector no longer fits in shared memory and the certificate
+    runs tile by tile (the kernel behind the 25k / 50k row-scan numbers)."""
+    n = 12800
+    cost = syn.uniform_cost_i32(n, seed=5)
+    dev = to_dev(engine, cost)
+    res = engine.lap_solve(dev, None, n_persons=n, n_objects=n)
+    po = res.person_obj.cpu().numpy()
+    assert sorted(po.tolist()) == list(range(n))
+    assert int(cost[np.arange(n), po].astype(np.int64).sum()) == res.total
+    cert = engine.lap_check(dev, res)
+    assert cert == {"max_violation": cert["max_violation"], "total": res.total, "invalid_rows": 0, "capacity_mismatch": 0}
+    assert cert["max_violation"] <= 1
+    keep = res.person_obj.clone()
+    res.person_obj = keep.clone(); res.person_obj[[10, 11]] = keep[[11, 10]]
+    bad = engine.lap_check(dev, res)
+    assert bad["max_violation"] > 1 and bad["capacity_mismatch"] == 0
+    res.person_obj = keep.clone(); res.person_obj[5] = keep[6]
+    assert engine.lap_check(dev, res)["capacity_mismatch"] == 2
