@@ -377,7 +377,7 @@ def run_b200(args, wl):
             "clocks": clocks,
             "certificate": cert,
             "lap_stats": {k: res.stats[k] for k in ("phases", "rounds", "bids", "tail_bids", "tails", "list_hits",
-                                                    "max_bidders", "grid", "smem_prices")},
+                                                    "max_bidders", "grid", "smem_prices", "tail_mode")},
             "total_cost": res.total, "lap_ms": lap_ms, "cost_build_ms": cost_ms,
         }
         if world == 1 and not strong and not args.no_cpu_baseline and args.distance_metric == "Pearson_correlation":

@@ -405,7 +405,7 @@ __global__ void __launch_bounds__(kThreads, 1) lap_auction_kernel(const LapParam
     __shared__ long long red_b1[32], red_b2[32];
     __shared__ int red_j[32], wcnt[32];
     __shared__ int tq[kTailMax], tq_head, tq_cnt, tq_status, sw_stop;
-    __shared__ int lj_obj[32], lj_need[32];
+    __shared__ int lj_obj[32], lj_need[32], lj_cur[32], ch_person[2][32], lj_stat[2], lj_stop;
     __shared__ long long lj_bid[32];
 
     const int G = gridDim.x, b = blockIdx.x, t = threadIdx.x;
@@ -558,99 +558,103 @@ __global__ void __launch_bounds__(kThreads, 1) lap_auction_kernel(const LapParam
                         if (prev >= 0) { P.person_obj[prev] = -1; P.person_slot[prev] = -1; }
                         return prev;
                     };
-                    while (P.tail_mode == 1) {
-                        int Fc = tq_cnt;
-                        if (Fc == 0 || tq_status != 0) break;
+                    if (P.tail_mode == 1) {
+                        // Every warp owns one chain: it keeps bidding for the person it currently holds
+                        // (first a free person of the list, afterwards whoever its last win evicted), so
+                        // the next candidate list is fetched by the warp that needs it the moment the
+                        // eviction is known, across the barrier that publishes the round's commits.
                         const int w = t >> 5, lane = t & 31;
-                        if (Fc == 1 && use_lists) {
-                            // a single chain: warp 0 follows it alone (a round with one bidder needs no
-                            // resolution), fetching the evicted person's list the moment it is known
-                            if (w == 0) {
-                                int i = tq[0], nb = 0;
-                                ListRegs lr = list_fetch(P, i);
+                        if (t < 32) { ch_person[0][t] = t < F ? tq[t] : -1; ch_person[1][t] = -1; }
+                        if (t == 0) { lj_stat[0] = 0; lj_stat[1] = 0; lj_stop = 0; }
+                        __syncthreads();
+                        int par = 0;
+                        int me = ch_person[0][w];
+                        ListRegs lr;
+                        bool have_list = false;
+                        for (;;) {
+                            const int pl = ch_person[par][lane];
+                            const unsigned amask = __ballot_sync(0xffffffffu, pl >= 0);
+                            if (amask == 0u || lj_stop != 0) break;       // lj_stop only changes between #1 and #2
+                            const bool alone = (amask & (amask - 1u)) == 0u;
+                            bool ok = false;
+                            Best s{0, 0, 0};
+                            if (me >= 0) {
                                 for (;;) {
-                                    Best s;
-                                    if (!list_eval<SMEMP>(P, i, lr, cmin, S, price_rd, s)) break;     // needs a row scan
+                                    if (use_lists) {
+                                        if (!have_list) { lr = list_fetch(P, me); have_list = true; }
+                                        ok = list_eval<SMEMP>(P, me, lr, cmin, S, price_rd, s);
+                                    }
+                                    if (!(ok && alone)) break;
+                                    // a single chain in flight: this warp follows it alone (a round with one
+                                    // bidder needs no resolution and no barrier)
                                     const long long lam = SMEMP ? sprice[s.j1] : __ldcg(P.lambda + s.j1);
                                     const long long bid = lam + (s.b2 < kInf / 2 ? s.b2 - s.b1 : 0) + eps;
                                     int prev = 0;
-                                    if (lane == 0) prev = assign_one(i, s.j1, bid);
+                                    if (lane == 0) {
+                                        prev = assign_one(me, s.j1, bid);
+                                        const int nb = atomicAdd(&lj_stat[0], 1) + 1; atomicAdd(&lj_stat[1], 1);
+                                        if (nb + rounds > P.max_rounds) tq_status = CYB_ERR_NOT_CONVERGED;
+                                    }
                                     prev = __shfl_sync(0xffffffffu, prev, 0);
-                                    ++nb;
-                                    i = prev;
-                                    if (i < 0) break;
-                                    lr = list_fetch(P, i);
-                                    if (bid >= kBidLimit || tail_bids + rounds + nb > P.max_rounds) break;
+                                    me = prev; have_list = false; ok = false;
+                                    if (me < 0 || bid >= kBidLimit || tq_status != 0) break;
                                 }
                                 if (lane == 0) {
-                                    lj_need[0] = nb;                                   // bids made on the fast path
-                                    if (i >= 0) tq[0] = i;
-                                    tq_cnt = i >= 0 ? 1 : 0;
-                                    if (tail_bids + rounds + nb > P.max_rounds) tq_status = CYB_ERR_NOT_CONVERGED;
+                                    lj_need[w] = (me >= 0 && !ok) ? 1 : 0;
+                                    if (me >= 0 && ok) {
+                                        const long long lam = SMEMP ? sprice[s.j1] : __ldcg(P.lambda + s.j1);
+                                        lj_obj[w] = s.j1;
+                                        lj_bid[w] = lam + (s.b2 < kInf / 2 ? s.b2 - s.b1 : 0) + eps;
+                                    }
+                                    lj_cur[w] = me;                       // person bidding for this chain in this round
+                                }
+                            } else if (lane == 0) {
+                                lj_need[w] = 0; lj_cur[w] = -1;
+                            }
+                            __syncthreads();                                  // #1: every bid (or scan request) is posted
+                            const int cl = lj_cur[lane];
+                            const unsigned miss = __ballot_sync(0xffffffffu, cl >= 0 && lj_need[lane] != 0);
+                            if (miss) {
+                                for (int k = 0; k < 32; ++k) {
+                                    if (!((miss >> k) & 1u)) continue;
+                                    const Best r = scan_row<SMEMP>(rowptr(lj_cur[k]), no, cmin, S, price_rd, vec_ok, red_b1, red_b2, red_j);
+                                    if (t == 0) {
+                                        const long long lam = SMEMP ? sprice[r.j1] : __ldcg(P.lambda + r.j1);
+                                        lj_obj[k] = r.j1;
+                                        lj_bid[k] = lam + (r.b2 < kInf / 2 ? r.b2 - r.b1 : 0) + eps;
+                                    }
+                                }
+                                __syncthreads();
+                            }
+                            int next = me;
+                            if (me >= 0) {
+                                const int o = lj_obj[w];
+                                const long long bid = lj_bid[w];
+                                // highest bid on the object wins, lowest person on equal bids
+                                const bool beats = cl >= 0 && lane != w && lj_obj[lane] == o &&
+                                                   (lj_bid[lane] > bid || (lj_bid[lane] == bid && cl < me));
+                                const bool win = !__any_sync(0xffffffffu, beats);
+                                if (win) {
+                                    int prev = 0;
+                                    if (lane == 0) prev = assign_one(me, o, bid);
+                                    next = __shfl_sync(0xffffffffu, prev, 0);
+                                    have_list = false;
+                                    if (next >= 0 && use_lists) { lr = list_fetch(P, next); have_list = true; }   // in flight across #2
+                                }
+                                if (lane == 0) {
+                                    const int nb = atomicAdd(&lj_stat[0], 1) + 1;
+                                    if (!((miss >> w) & 1u)) atomicAdd(&lj_stat[1], 1);
+                                    if (nb + rounds > P.max_rounds) tq_status = CYB_ERR_NOT_CONVERGED;
                                 }
                             }
-                            __syncthreads();
-                            tail_bids += lj_need[0]; list_hits += lj_need[0];
-                            Fc = tq_cnt;
-                            const int st = tq_status;
-                            __syncthreads();                                           // lj_need[0] is rewritten below
-                            if (Fc == 0 || st != 0) break;
+                            if (lane == 0) ch_person[par ^ 1][w] = next;
+                            if (t == 0) lj_stop = tq_status;
+                            me = next;
+                            par ^= 1;
+                            __syncthreads();                                  // #2: commits and next persons visible
                         }
-                        if (w < Fc) {
-                            const int i = tq[w];
-                            Best s{0, 0, 0};
-                            bool ok = false;
-                            if (use_lists) {
-                                const ListRegs lr = list_fetch(P, i);
-                                ok = list_eval<SMEMP>(P, i, lr, cmin, S, price_rd, s);
-                            }
-                            if (lane == 0) {
-                                lj_need[w] = ok ? 0 : 1;
-                                if (ok) {
-                                    const long long lam = SMEMP ? sprice[s.j1] : __ldcg(P.lambda + s.j1);
-                                    lj_obj[w] = s.j1;
-                                    lj_bid[w] = lam + (s.b2 < kInf / 2 ? s.b2 - s.b1 : 0) + eps;
-                                }
-                            }
-                        }
-                        __syncthreads();
-                        int misses = 0;
-                        for (int k = 0; k < Fc; ++k) misses += lj_need[k];               // uniform across the CTA
-                        if (misses) {
-                            for (int k = 0; k < Fc; ++k) {
-                                if (!lj_need[k]) continue;
-                                const Best s = scan_row<SMEMP>(rowptr(tq[k]), no, cmin, S, price_rd, vec_ok, red_b1, red_b2, red_j);
-                                if (t == 0) {
-                                    const long long lam = SMEMP ? sprice[s.j1] : __ldcg(P.lambda + s.j1);
-                                    lj_obj[k] = s.j1;
-                                    lj_bid[k] = lam + (s.b2 < kInf / 2 ? s.b2 - s.b1 : 0) + eps;
-                                }
-                            }
-                            __syncthreads();
-                        }
-                        tail_bids += Fc; list_hits += Fc - misses;
-                        if (w == 0) {
-                            const bool act = lane < Fc;
-                            const int i = act ? tq[lane] : -1;
-                            const int o = act ? lj_obj[lane] : -1;
-                            const long long bid = act ? lj_bid[lane] : 0;
-                            bool win = act;                        // highest bid on the object, lowest person on ties
-                            for (int j = 0; j < Fc; ++j) {
-                                const int oj = lj_obj[j], ij = tq[j];
-                                const long long bj = lj_bid[j];
-                                if (j != lane && oj == o && (bj > bid || (bj == bid && ij < i))) win = false;
-                            }
-                            __syncwarp();
-                            int entry = i;                         // who is free after this round
-                            if (win) entry = assign_one(i, o, bid);
-                            const unsigned stay = __ballot_sync(0xffffffffu, entry >= 0);
-                            if (entry >= 0) tq[__popc(stay & ((1u << lane) - 1u))] = entry;
-                            if (lane == 0) {
-                                tq_cnt = __popc(stay);
-                                if (tail_bids + rounds > P.max_rounds) tq_status = CYB_ERR_NOT_CONVERGED;
-                            }
-                        }
-                        __syncthreads();
+                        tail_bids += lj_stat[0]; list_hits += lj_stat[1];
+                        if (t == 0) tq_cnt = 0;
                     }
                     while (P.tail_mode == 0 && tq_cnt > 0 && tq_status == 0) {
                         // one bid: thread 0 books the result `s` of person i's scan (list or full row)
@@ -894,7 +898,7 @@ __global__ void __launch_bounds__(kThreads, 1) lap_auction_kernel(const LapParam
     if (b == 0 && t == 0) {
         P.stats[0] = status; P.stats[1] = phases; P.stats[2] = rounds; P.stats[3] = bids;
         P.stats[4] = passes; P.stats[5] = cmin; P.stats[6] = cmax; P.stats[7] = S;
-        P.stats[8] = G; P.stats[9] = SMEMP ? 1 : 0; P.stats[10] = rounds1; P.stats[11] = maxF;
+        P.stats[8] = G; P.stats[9] = SMEMP ? 1 : 0; P.stats[10] = P.tail_mode; P.stats[11] = maxF;
         P.stats[12] = (phases - 1) * (long long)np; P.stats[13] = tail_bids; P.stats[14] = tails; P.stats[15] = list_hits;
     }
 }
@@ -957,7 +961,8 @@ constexpr int kTeams = kChkThreads / kTeam;
 
 __global__ void __launch_bounds__(kChkThreads) lap_rowcheck_whole_kernel(
     const int32_t *__restrict__ cost, long long ld, int np, int no, const int32_t *__restrict__ person_obj,
-    const long long *__restrict__ price, long long S, int32_t *__restrict__ count, long long *__restrict__ acc) {
+    const long long *__restrict__ price, long long S, int32_t *__restrict__ count, long long *__restrict__ acc,
+    const int32_t *__restrict__ soff, long long *__restrict__ out, unsigned int *__restrict__ done) {
     extern __shared__ __align__(16) long long spw[];
     __shared__ long long part[2][kTeams][kTeam / 32];
     __shared__ long long r_viol[kTeams], r_tot[kTeams];
@@ -970,8 +975,15 @@ __global__ void __launch_bounds__(kChkThreads) lap_rowcheck_whole_kernel(
     const int n4 = vec_ok ? (no >> 2) : 0;
     long long viol = 0, tot = 0;
     int bad = 0, it = 0;
-    for (int i = blockIdx.x * kTeams + team; i < np; i += gridDim.x * kTeams, ++it) {
+    const int i0 = blockIdx.x * kTeams + team, istep = gridDim.x * kTeams;
+    // the row's certificate terms ride along with the stream: obj(i) is fetched one row ahead and
+    // cost[i, obj(i)] with the row itself, so the team leader adds no dependent round trip per row
+    int o_cur = (tt == 0 && i0 < np) ? __ldg(person_obj + i0) : -1;
+    for (int i = i0; i < np; i += istep, ++it) {
         const int32_t *r = cost + (long long)i * ld;
+        const int o_next = (tt == 0 && i + istep < np) ? __ldg(person_obj + i + istep) : -1;
+        const bool o_ok = o_cur >= 0 && o_cur < no;
+        const int c_o = (tt == 0 && o_ok) ? __ldg(r + o_cur) : 0;
         long long m = LLONG_MAX;
         const int4 *r4 = reinterpret_cast<const int4 *>(r);
 #pragma unroll 8
@@ -992,15 +1004,14 @@ __global__ void __launch_bounds__(kChkThreads) lap_rowcheck_whole_kernel(
         if (tt == 0) {
 #pragma unroll
             for (int k = 0; k < kTeam / 32; ++k) m = min(m, part[it & 1][team][k]);
-            const int o = __ldg(person_obj + i);
-            if (o < 0 || o >= no) ++bad;
+            if (!o_ok) ++bad;
             else {
-                const int c = __ldg(r + o);
-                tot += c;
-                atomicAdd(count + o, 1);
-                viol = max(viol, (long long)c * S + spw[o] - m);
+                tot += c_o;
+                atomicAdd(count + o_cur, 1);
+                viol = max(viol, (long long)c_o * S + spw[o_cur] - m);
             }
         }
+        o_cur = o_next;
     }
     if (tt == 0) { r_viol[team] = viol; r_tot[team] = tot; r_bad[team] = bad; }
     __syncthreads();
@@ -1009,27 +1020,25 @@ __global__ void __launch_bounds__(kChkThreads) lap_rowcheck_whole_kernel(
         if (viol > 0) atomicMax(acc + 0, viol);
         if (tot) atomicAdd(reinterpret_cast<unsigned long long *>(acc + 1), (unsigned long long)tot);
         if (bad) atomicAdd(reinterpret_cast<unsigned long long *>(acc + 2), (unsigned long long)bad);
-    }
-}
-
-// capacities + hand the accumulators to the caller's out[4] (single CTA-independent finish)
-__global__ void lap_check_publish_kernel(const int32_t *__restrict__ soff, int no, const int32_t *__restrict__ count,
-                                         long long *__restrict__ acc, long long *__restrict__ out,
-                                         unsigned int *__restrict__ done) {
-    long long bad = 0;
-    for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < no; o += gridDim.x * blockDim.x) {
-        const int cap = soff ? soff[o + 1] - soff[o] : 1;
-        if (count[o] != cap) ++bad;
-    }
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) bad += __shfl_xor_sync(0xffffffffu, bad, d);
-    if ((threadIdx.x & 31) == 0 && bad) atomicAdd(reinterpret_cast<unsigned long long *>(acc + 3), (unsigned long long)bad);
-    __syncthreads();
-    if (threadIdx.x == 0) {
         __threadfence();
-        if (atomicAdd(done, 1u) == gridDim.x - 1) {          // last CTA publishes
-            __threadfence();
-            for (int k = 0; k < 4; ++k) out[k] = __ldcg(acc + k);
+        r_bad[0] = (atomicAdd(done, 1u) == gridDim.x - 1) ? 1 : 0;         // the last CTA finishes the certificate
+    }
+    __syncthreads();
+    if (r_bad[0]) {
+        __threadfence();
+        long long capbad = 0;
+        for (int o = threadIdx.x; o < no; o += kChkThreads) {
+            const int cap = soff ? __ldg(soff + o + 1) - __ldg(soff + o) : 1;
+            if (__ldcg(count + o) != cap) ++capbad;
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) capbad += __shfl_xor_sync(0xffffffffu, capbad, d);
+        if (threadIdx.x == 0) r_tot[0] = 0;
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0 && capbad) atomicAdd(reinterpret_cast<unsigned long long *>(&r_tot[0]), (unsigned long long)capbad);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            out[0] = __ldcg(acc + 0); out[1] = __ldcg(acc + 1); out[2] = __ldcg(acc + 2); out[3] = r_tot[0];
         }
     }
 }
@@ -1162,15 +1171,13 @@ extern "C" int cyb_lap_solve_i32(const int32_t *cost_dev, int64_t ld, int64_t n_
     P.lst_hdr = reinterpret_cast<longlong2 *>(ws + L.lst_hdr);
     P.lst_ent = reinterpret_cast<int2 *>(ws + L.lst_ent);
     P.tail_t = 8;
-    P.tail_mode = 1;
+    P.tail_mode = -1;        // chosen below, once the shared-memory residency is known
     P.early_stop = 0;      // measured: postponed price wars get longer at smaller eps
     P.use_lists = 1;
     P.theta = kTheta; P.eps0_div = kEps0Div;
     if (const char *e = getenv("CYB_LAP_THETA")) P.theta = std::max(2, atoi(e));
     if (const char *e = getenv("CYB_LAP_EPS0")) P.eps0_div = std::max(1, atoi(e));
     if (const char *e = getenv("CYB_LAP_TAIL_MODE")) P.tail_mode = atoi(e) ? 1 : 0;
-    P.tail_t = P.tail_mode == 1 ? 32 : 8;
-    if (const char *e = getenv("CYB_LAP_TAIL")) P.tail_t = atoi(e);
     if (const char *e = getenv("CYB_LAP_EARLY")) P.early_stop = std::max(0, atoi(e));
     if (const char *e = getenv("CYB_LAP_LISTS")) P.use_lists = atoi(e);
 
@@ -1188,6 +1195,13 @@ extern "C" int cyb_lap_solve_i32(const int32_t *cost_dev, int64_t ld, int64_t n_
     P.smem_owner = (dyn + owner_bytes + static_smem <= (size_t)max_smem) ? 1 : 0;
     if (const char *e = getenv("CYB_LAP_SMEM_OWNER")) P.smem_owner = P.smem_owner && atoi(e);
     if (P.smem_owner) dyn += owner_bytes;
+    // Tail: with prices AND slot owners in shared memory a Gauss-Seidel step is one L2 round trip
+    // (~0.95 us) and the FIFO tail wins or ties (10k, 30k x 5k); when either lives in L2 every step
+    // chains two or three round trips and the multi-chain Jacobi tail hides them (measured on B200:
+    // 25k 288 -> 244 ms, 50k 975 -> 712 ms).
+    if (P.tail_mode < 0) P.tail_mode = (smemp && P.smem_owner) ? 0 : 1;
+    P.tail_t = P.tail_mode == 1 ? 32 : 8;
+    if (const char *e = getenv("CYB_LAP_TAIL")) P.tail_t = atoi(e);
 
     const void *fn = smemp ? (const void *)lap_auction_kernel<true> : (const void *)lap_auction_kernel<false>;
     CYB_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
@@ -1237,11 +1251,8 @@ extern "C" int cyb_lap_check_i32(const int32_t *cost_dev, int64_t ld, int64_t n_
         if (per_sm < 1) per_sm = 1;
         int grid = (int)std::min<long long>((long long)sms0 * per_sm, (np + kTeams - 1) / kTeams);
         lap_rowcheck_whole_kernel<<<grid, kChkThreads, smem, stream>>>(
-            cost_dev, ld, (int)np, (int)no, person_obj_dev, reinterpret_cast<const long long *>(price_dev), np + 1, count, acc);
-        CYB_CUDA_CHECK(cudaGetLastError());
-        const int pgrid = (int)std::min<long long>(sms0, (no + 255) / 256);
-        lap_check_publish_kernel<<<pgrid, 256, 0, stream>>>(slot_offset_dev, (int)no, count, acc,
-                                                            reinterpret_cast<long long *>(out_dev), done);
+            cost_dev, ld, (int)np, (int)no, person_obj_dev, reinterpret_cast<const long long *>(price_dev), np + 1, count, acc,
+            slot_offset_dev, reinterpret_cast<long long *>(out_dev), done);
         CYB_CUDA_CHECK(cudaGetLastError());
         return CYB_OK;
     }

@@ -79,7 +79,7 @@ extern "C" {
  *  [3] bids (= row scans in rounds)  [4] full-matrix row scans (phase starts)
  *  [5] cost minimum         [6] cost maximum            [7] scale S = n+1
  *  [8] grid size used       [9] 1 if the price vector was shared-memory resident
- *  [10] rounds with <= 1 bidder [11] max bidders in a round
+ *  [10] tail mode used (0 Gauss-Seidel FIFO, 1 in-CTA Jacobi rounds) [11] max bidders in a round
  *  [12] row scans at phase starts (rows whose pair was re-checked)
  *  [13] bids made in Gauss-Seidel tails (one CTA, no grid barrier)  [14] tails run
  *  [15] tail bids served from a candidate list (no row scan) */
