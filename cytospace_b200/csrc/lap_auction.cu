@@ -101,6 +101,7 @@ struct LapParams {
     int use_lists;
     int sweepers;            // CTAs that rebuild lists during a tail (<= G-1)
     int theta, eps0_div;     // eps schedule: eps0 = range*(P+1)/eps0_div, eps /= theta per phase
+    int packed_reduce;       // 1: scan_row reduces packed (value, column) keys with REDUX when the range allows
     int tail_mode;           // 0: Gauss-Seidel FIFO tail, 1: Jacobi rounds inside CTA 0 (one warp per bidder)
     int early_stop;          // a phase with eps > 1 ends once <= early_stop persons are free (they bid again next phase)
     int smem_owner;          // 1: every CTA keeps a replica of slot_owner (and minslot) in shared memory
@@ -141,6 +142,12 @@ __device__ __forceinline__ Best combine(const Best &a, const Best &b) {
     return r;
 }
 
+__device__ __forceinline__ long long global_ns() {
+    long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
 __device__ __forceinline__ void grid_barrier(unsigned int *bar, unsigned int &target, unsigned int G) {
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -176,12 +183,21 @@ __device__ __forceinline__ int block_excl_count(bool valid, int *wcnt, int &tota
     return woff + within;
 }
 
+// Warp minimum of a 64-bit key with two 32-bit REDUX steps (high word, then low word among the lanes
+// that hold the minimal high word).
+__device__ __forceinline__ unsigned long long warp_min64(unsigned long long key) {
+    const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+    const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
+    const unsigned mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xFFFFFFFFu);
+    return ((unsigned long long)mhi << 32) | mlo;
+}
+
 // CTA-wide scan of one person's row: min / second-min / argmin of (c-cmin)*S + lambda.
 // The result is valid in thread 0.
 template <bool SMEMP>
-__device__ __forceinline__ Best scan_row(const int32_t *__restrict__ r, int n, int cmin, long long S,
+__device__ __forceinline__ Best scan_row(const int32_t *__restrict__ r, int n, int cmin, int S,
                                          const long long *__restrict__ price, bool vec_ok,
-                                         long long *red_b1, long long *red_b2, int *red_j) {
+                                         long long *red_b1, long long *red_b2, int *red_j, bool packed) {
     Best s{LLONG_MAX, LLONG_MAX, -1};
     const int t = threadIdx.x;
     const unsigned long long pol = l2_policy_evict_first();
@@ -216,6 +232,32 @@ __device__ __forceinline__ Best scan_row(const int32_t *__restrict__ r, int n, i
     }
     // A thread's columns increase over its iterations and tail columns are larger than vector
     // columns; `upd` keeps the earlier (lower) column on ties, `combine` the lower index.
+    if (packed) {
+        // every finite value is < 2^46 - 1 (scaled cost range < 2^45, prices < 2^45): (value << 18 | column)
+        // orders like (value, column), so the CTA-wide (min, argmin, second min) is four REDUX per level
+        // instead of ten 64-bit shuffle rounds; priced-out objects clamp to the all-ones value
+        const long long vmax = (1ll << 46) - 1;
+        const unsigned long long k1 = s.j1 >= 0 ? (((unsigned long long)min(s.b1, vmax) << kPersonBits) | (unsigned)s.j1) : ~0ull;
+        const unsigned long long k2 = s.b2 != LLONG_MAX ? (((unsigned long long)min(s.b2, vmax) << kPersonBits) | kPersonMask) : ~0ull;
+        const unsigned long long w1 = warp_min64(k1);
+        const unsigned long long w2 = warp_min64(k1 == w1 ? k2 : k1);
+        const int lane = t & 31, w = t >> 5;
+        unsigned long long *rk1 = reinterpret_cast<unsigned long long *>(red_b1);
+        unsigned long long *rk2 = reinterpret_cast<unsigned long long *>(red_b2);
+        if (lane == 0) { rk1[w] = w1; rk2[w] = w2; }
+        __syncthreads();
+        if (w == 0) {
+            const unsigned long long q1 = rk1[lane], q2 = rk2[lane];
+            const unsigned long long W1 = warp_min64(q1);
+            const unsigned long long W2 = warp_min64(q1 == W1 ? q2 : q1);
+            const long long v1 = (long long)(W1 >> kPersonBits), v2 = (long long)(W2 >> kPersonBits);
+            s.j1 = W1 == ~0ull ? -1 : (int)(W1 & kPersonMask);
+            s.b1 = (W1 == ~0ull) ? LLONG_MAX : (v1 == vmax ? kInf : v1);
+            s.b2 = (W2 == ~0ull) ? LLONG_MAX : (v2 == vmax ? kInf : v2);
+        }
+        __syncthreads();
+        return s;
+    }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
         Best o;
@@ -261,7 +303,7 @@ __device__ __forceinline__ void cheapest_slot(const LapParams &P, int o, int t_n
 // stale (lower than current): the bound is then merely weaker, never wrong.
 template <bool SMEMP>
 __device__ __forceinline__ void build_list(const LapParams &P, int i, const int32_t *__restrict__ r, int n, int cmin,
-                                           long long S, const long long *__restrict__ price, bool vec_ok,
+                                           int S, const long long *__restrict__ price, bool vec_ok,
                                            long long *red_b2, int *wcnt) {
     Best s{LLONG_MAX, LLONG_MAX, -1};
     const int t = threadIdx.x;
@@ -321,15 +363,6 @@ __device__ __forceinline__ void build_list(const LapParams &P, int i, const int3
     }
 }
 
-// Warp minimum of a 64-bit key with two 32-bit REDUX steps (high word, then low word among the lanes
-// that hold the minimal high word).
-__device__ __forceinline__ unsigned long long warp_min64(unsigned long long key) {
-    const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
-    const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
-    const unsigned mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xFFFFFFFFu);
-    return ((unsigned long long)mhi << 32) | mlo;
-}
-
 // Leader side (one warp).  A list is FETCHED (header + first 64 entries: one L2 round trip, issued
 // as early as the next bidder is known so that it overlaps the current bid's bookkeeping) and later
 // EVALUATED against the current prices.
@@ -351,7 +384,7 @@ __device__ __forceinline__ ListRegs list_fetch(const LapParams &P, int i) {
 // Returns true with the exact (b1, j1, b2) of a full scan in every lane when the result is certified,
 // false otherwise (no list, torn list, or the second-best candidate is not below the bound).
 template <bool SMEMP>
-__device__ __forceinline__ bool list_eval(const LapParams &P, int i, const ListRegs &r, int cmin, long long S,
+__device__ __forceinline__ bool list_eval(const LapParams &P, int i, const ListRegs &r, int cmin, int S,
                                           const long long *__restrict__ price, Best &out) {
     const int lane = threadIdx.x & 31;
     const longlong2 h = r.h;
@@ -393,7 +426,9 @@ __device__ __forceinline__ bool list_eval(const LapParams &P, int i, const ListR
     return true;
 }
 
-template <bool SMEMP>
+// TM = tail mode (0 Gauss-Seidel FIFO, 1 in-CTA Jacobi rounds): a compile-time choice so that each
+// instantiation carries one tail's code and register pressure only.
+template <bool SMEMP, int TM>
 __global__ void __launch_bounds__(kThreads, 1) lap_auction_kernel(const LapParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int np = P.P, no = P.O;
@@ -409,7 +444,7 @@ __global__ void __launch_bounds__(kThreads, 1) lap_auction_kernel(const LapParam
     __shared__ long long lj_bid[32];
 
     const int G = gridDim.x, b = blockIdx.x, t = threadIdx.x;
-    const long long S = (long long)np + 1;
+    const int S = np + 1;                            // < 2^18: cost * S is a 32 x 32 -> 64 bit multiply-add
     const bool vec_ok = ((P.ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(P.cost) & 15) == 0);
     unsigned int bar_target = 0;
     const long long *price_rd = SMEMP ? sprice : P.lambda;
@@ -453,13 +488,19 @@ __global__ void __launch_bounds__(kThreads, 1) lap_auction_kernel(const LapParam
     long long eps = ((long long)cmax - (long long)cmin) * S / P.eps0_div;
     if (eps < 1) eps = 1;
 
-    long long rounds = 0, bids = 0, passes = 0, phases = 0, rounds1 = 0, maxF = 0, tail_bids = 0, tails = 0, list_hits = 0;
+    // control counters stay in (32-bit) registers; pure statistics live in shared memory (thread 0 of the CTA
+    // updates them) so that they cost no registers in the scan loops
+    int rounds = 0, phases = 0, tails = 0, tail_bids = 0;
+    __shared__ long long st_acc[8];   // bids, max bidders, list hits, small rounds, ns bid / barrier / replay / tail
+    if (t < 8) st_acc[t] = 0;
+    __syncthreads();
     int status = 0;
     int cur = 0;             // buffer of the current round; the previous round used (cur + 2) % 3
     int prevF = 0;           // records of the previous round (their bid words are cleared in this resolve)
-    const int tail_t = min(P.tail_t, P.tail_mode == 1 ? 32 : kTailMax);
+    const int tail_t = min(P.tail_t, TM == 1 ? 32 : kTailMax);
     // candidate-list keys pack (value << 18 | object): needs every value < 2^46, i.e. scaled costs < 2^45
     // (prices are bounded by kBidLimit = 2^45 already)
+    const bool packed = ((long long)cmax - (long long)cmin + 1) * S < (1ll << 45) && P.packed_reduce;
     const bool use_lists = P.use_lists && G > 1 && ((long long)cmax - (long long)cmin + 1) * S < (1ll << 45);
 
     for (;;) {
@@ -471,7 +512,7 @@ __global__ void __launch_bounds__(kThreads, 1) lap_auction_kernel(const LapParam
                 int f = 1;
                 if (o >= 0) {
                     const int32_t *r = rowptr(i);
-                    const Best s = scan_row<SMEMP>(r, no, cmin, S, price_rd, vec_ok, red_b1, red_b2, red_j);
+                    const Best s = scan_row<SMEMP>(r, no, cmin, S, price_rd, vec_ok, red_b1, red_b2, red_j, packed);
                     if (t == 0) {
                         const long long alt = (s.j1 == o) ? s.b2 : s.b1;
                         const long long base = (long long)(__ldg(r + o) - cmin) * S;
@@ -487,7 +528,6 @@ __global__ void __launch_bounds__(kThreads, 1) lap_auction_kernel(const LapParam
                 }
                 if (t == 0) P.flag[i] = f;
             }
-            ++passes;
             grid_barrier(P.bar, bar_target, G);
         }
         int F = 0;
@@ -532,6 +572,7 @@ __global__ void __launch_bounds__(kThreads, 1) lap_auction_kernel(const LapParam
                 // exchanged until the phase ends.  (Same auction, sequential order: still exact.)
                 grid_barrier(P.bar, bar_target, G);          // every CTA has finished its resolve writes
                 ran_tail = true; ++tails;
+                const long long tt0 = (b == 0 && t == 0) ? global_ns() : 0;
                 if (b == 0) {
                     if (t < F) tq[t] = __ldcg(P.list[cur] + t);
                     if (t == 0) { tq_head = 0; tq_cnt = F; tq_status = 0; }
@@ -543,10 +584,13 @@ __global__ void __launch_bounds__(kThreads, 1) lap_auction_kernel(const LapParam
                     // semantics are unchanged the assignment does not depend on where the switch happens.
                     // one thread: person i takes the cheapest slot of object o at price `bid`; returns the
                     // person it evicts (-1: the slot was free)
-                    auto assign_one = [&](int i, int o, long long bid) -> int {
+                    // who holds the slot a winning bid for object o takes (known before any slot price is read)
+                    auto peek_prev = [&](int o, int &slot) -> int {
+                        slot = P.soff ? (P.smem_owner ? sminslot[o] : __ldcg(P.minslot + o)) : o;
+                        return P.smem_owner ? sowner[slot] : __ldcg(P.slot_owner + slot);
+                    };
+                    auto assign_one = [&](int i, int o, long long bid, int slot, int prev) -> int {
                         if (bid >= kBidLimit) tq_status = CYB_ERR_OVERFLOW;
-                        const int slot = P.soff ? (P.smem_owner ? sminslot[o] : __ldcg(P.minslot + o)) : o;
-                        const int prev = P.smem_owner ? sowner[slot] : __ldcg(P.slot_owner + slot);
                         long long mp = bid; int ms = slot;
                         if (P.soff) cheapest_slot(P, o, slot, bid, ms, mp);
                         if (P.smem_owner) { sowner[slot] = i; if (P.soff) sminslot[o] = ms; }
@@ -558,7 +602,7 @@ __global__ void __launch_bounds__(kThreads, 1) lap_auction_kernel(const LapParam
                         if (prev >= 0) { P.person_obj[prev] = -1; P.person_slot[prev] = -1; }
                         return prev;
                     };
-                    if (P.tail_mode == 1) {
+                    if (TM == 1) {
                         // Every warp owns one chain: it keeps bidding for the person it currently holds
                         // (first a free person of the list, afterwards whoever its last win evicted), so
                         // the next candidate list is fetched by the warp that needs it the moment the
@@ -589,14 +633,18 @@ __global__ void __launch_bounds__(kThreads, 1) lap_auction_kernel(const LapParam
                                     // bidder needs no resolution and no barrier)
                                     const long long lam = SMEMP ? sprice[s.j1] : __ldcg(P.lambda + s.j1);
                                     const long long bid = lam + (s.b2 < kInf / 2 ? s.b2 - s.b1 : 0) + eps;
-                                    int prev = 0;
+                                    const int old = me;
+                                    int prev = 0, slot = 0;
+                                    if (lane == 0) prev = peek_prev(s.j1, slot);
+                                    prev = __shfl_sync(0xffffffffu, prev, 0);
+                                    me = prev; have_list = false; ok = false;
+                                    if (me >= 0 && use_lists) { lr = list_fetch(P, me); have_list = true; }   // before the commit's loads
                                     if (lane == 0) {
-                                        prev = assign_one(me, s.j1, bid);
+                                        assign_one(old, s.j1, bid, slot, prev);
                                         const int nb = atomicAdd(&lj_stat[0], 1) + 1; atomicAdd(&lj_stat[1], 1);
                                         if (nb + rounds > P.max_rounds) tq_status = CYB_ERR_NOT_CONVERGED;
                                     }
-                                    prev = __shfl_sync(0xffffffffu, prev, 0);
-                                    me = prev; have_list = false; ok = false;
+                                    __syncwarp();
                                     if (me < 0 || bid >= kBidLimit || tq_status != 0) break;
                                 }
                                 if (lane == 0) {
@@ -617,7 +665,7 @@ __global__ void __launch_bounds__(kThreads, 1) lap_auction_kernel(const LapParam
                             if (miss) {
                                 for (int k = 0; k < 32; ++k) {
                                     if (!((miss >> k) & 1u)) continue;
-                                    const Best r = scan_row<SMEMP>(rowptr(lj_cur[k]), no, cmin, S, price_rd, vec_ok, red_b1, red_b2, red_j);
+                                    const Best r = scan_row<SMEMP>(rowptr(lj_cur[k]), no, cmin, S, price_rd, vec_ok, red_b1, red_b2, red_j, packed);
                                     if (t == 0) {
                                         const long long lam = SMEMP ? sprice[r.j1] : __ldcg(P.lambda + r.j1);
                                         lj_obj[k] = r.j1;
@@ -635,11 +683,12 @@ __global__ void __launch_bounds__(kThreads, 1) lap_auction_kernel(const LapParam
                                                    (lj_bid[lane] > bid || (lj_bid[lane] == bid && cl < me));
                                 const bool win = !__any_sync(0xffffffffu, beats);
                                 if (win) {
-                                    int prev = 0;
-                                    if (lane == 0) prev = assign_one(me, o, bid);
+                                    int prev = 0, slot = 0;
+                                    if (lane == 0) prev = peek_prev(o, slot);
                                     next = __shfl_sync(0xffffffffu, prev, 0);
                                     have_list = false;
                                     if (next >= 0 && use_lists) { lr = list_fetch(P, next); have_list = true; }   // in flight across #2
+                                    if (lane == 0) assign_one(me, o, bid, slot, prev);
                                 }
                                 if (lane == 0) {
                                     const int nb = atomicAdd(&lj_stat[0], 1) + 1;
@@ -653,10 +702,11 @@ __global__ void __launch_bounds__(kThreads, 1) lap_auction_kernel(const LapParam
                             par ^= 1;
                             __syncthreads();                                  // #2: commits and next persons visible
                         }
-                        tail_bids += lj_stat[0]; list_hits += lj_stat[1];
+                        tail_bids += lj_stat[0];
+                        if (t == 0) st_acc[2] += lj_stat[1];
                         if (t == 0) tq_cnt = 0;
                     }
-                    while (P.tail_mode == 0 && tq_cnt > 0 && tq_status == 0) {
+                    while (TM == 0 && tq_cnt > 0 && tq_status == 0) {
                         // one bid: thread 0 books the result `s` of person i's scan (list or full row)
                         // commit one bid (one thread): person i takes `slot` of object o at price `bid`,
                         // evicting `prev`; (ms, mp) = the object's cheapest slot / price afterwards
@@ -739,8 +789,15 @@ __global__ void __launch_bounds__(kThreads, 1) lap_auction_kernel(const LapParam
                                     }
                                     Best s;
                                     if (!list_eval<SMEMP>(P, i, lr, cmin, S, price_rd, s)) break;
-                                    ++list_hits;
+                                    if (t == 0) ++st_acc[2];
                                     ++tail_bids;
+                                    if (nxt < 0 && P.smem_owner && P.soff) {
+                                        // capacitated object: who gets evicted is known from the shared-memory
+                                        // replicas alone, so the next list is requested BEFORE the slot prices
+                                        // of the object are read from L2 (one round trip per step, not two)
+                                        const int pe = sowner[sminslot[s.j1]];
+                                        if (pe >= 0) { nxt = pe; ln = list_fetch(P, nxt); }
+                                    }
                                     const int prev = book_warp(i, s);
                                     __syncwarp();
                                     if (nxt < 0) {
@@ -755,12 +812,13 @@ __global__ void __launch_bounds__(kThreads, 1) lap_auction_kernel(const LapParam
                             if (!(tq_cnt > 0 && tq_status == 0)) break;
                         }
                         const int i = tq[tq_head];
-                        const Best s = scan_row<SMEMP>(rowptr(i), no, cmin, S, price_rd, vec_ok, red_b1, red_b2, red_j);
+                        const Best s = scan_row<SMEMP>(rowptr(i), no, cmin, S, price_rd, vec_ok, red_b1, red_b2, red_j, packed);
                         ++tail_bids;
                         if (t == 0) book(i, s);
                         __syncthreads();
                     }
                     if (t == 0) {
+                        st_acc[7] += global_ns() - tt0;
                         if (tq_status) atomicExch(P.gmm + 2, tq_status);
                         __threadfence();
                         asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(P.gmm + 3), "r"((int)tails) : "memory");
@@ -792,13 +850,13 @@ __global__ void __launch_bounds__(kThreads, 1) lap_auction_kernel(const LapParam
                 break;
             }
             if (++rounds > P.max_rounds) { status = CYB_ERR_NOT_CONVERGED; break; }
-            bids += F;
-            if (F <= 1) ++rounds1;
-            if (F > maxF) maxF = F;
+            if (t == 0) { st_acc[0] += F; if (F > st_acc[1]) st_acc[1] = F; }
+            const bool timed = (b == 0 && t == 0 && F <= G);
+            const long long tm0 = timed ? global_ns() : 0;
             const int myn = F > b ? (F - b - 1) / G + 1 : 0;
             for (int q = 0; q < myn; ++q) {
                 const int i = myq[q];
-                const Best s = scan_row<SMEMP>(rowptr(i), no, cmin, S, price_rd, vec_ok, red_b1, red_b2, red_j);
+                const Best s = scan_row<SMEMP>(rowptr(i), no, cmin, S, price_rd, vec_ok, red_b1, red_b2, red_j, packed);
                 if (t == 0) {
                     const int o = s.j1;
                     const long long lam = SMEMP ? sprice[o] : __ldcg(P.lambda + o);
@@ -811,7 +869,9 @@ __global__ void __launch_bounds__(kThreads, 1) lap_auction_kernel(const LapParam
                               ((unsigned long long)bid << kPersonBits) | (kPersonMask - (unsigned long long)i));
                 }
             }
+            const long long tm1 = timed ? global_ns() : 0;
             grid_barrier(P.bar, bar_target, G);
+            const long long tm2 = timed ? global_ns() : 0;
             // ---- resolve: every CTA replays every record ----------------------
             // (the error flag is checked after the replay so that its load overlaps the record loads)
             status = __ldcg(P.gmm + 2);
@@ -856,6 +916,7 @@ __global__ void __launch_bounds__(kThreads, 1) lap_auction_kernel(const LapParam
             F = Fn;
             cur = nxt;
             __syncthreads();
+            if (timed) { st_acc[4] += tm1 - tm0; st_acc[5] += tm2 - tm1; st_acc[6] += global_ns() - tm2; ++st_acc[3]; }
             if (status) break;
         }
         if (status) break;
@@ -896,10 +957,11 @@ __global__ void __launch_bounds__(kThreads, 1) lap_auction_kernel(const LapParam
         if ((t & 31) == 0 && sum != 0) atomicAdd(reinterpret_cast<unsigned long long *>(P.total), (unsigned long long)sum);
     }
     if (b == 0 && t == 0) {
-        P.stats[0] = status; P.stats[1] = phases; P.stats[2] = rounds; P.stats[3] = bids;
-        P.stats[4] = passes; P.stats[5] = cmin; P.stats[6] = cmax; P.stats[7] = S;
-        P.stats[8] = G; P.stats[9] = SMEMP ? 1 : 0; P.stats[10] = P.tail_mode; P.stats[11] = maxF;
-        P.stats[12] = (phases - 1) * (long long)np; P.stats[13] = tail_bids; P.stats[14] = tails; P.stats[15] = list_hits;
+        P.stats[0] = status; P.stats[1] = phases; P.stats[2] = rounds; P.stats[3] = st_acc[0];
+        P.stats[4] = phases - 1; P.stats[5] = cmin; P.stats[6] = cmax; P.stats[7] = S;
+        P.stats[8] = G; P.stats[9] = SMEMP ? 1 : 0; P.stats[10] = TM; P.stats[11] = st_acc[1];
+        P.stats[12] = (phases - 1) * (long long)np; P.stats[13] = tail_bids; P.stats[14] = tails; P.stats[15] = st_acc[2];
+        P.stats[16] = st_acc[3]; P.stats[17] = st_acc[4]; P.stats[18] = st_acc[5]; P.stats[19] = st_acc[6]; P.stats[20] = st_acc[7];
     }
 }
 
@@ -1171,6 +1233,8 @@ extern "C" int cyb_lap_solve_i32(const int32_t *cost_dev, int64_t ld, int64_t n_
     P.lst_hdr = reinterpret_cast<longlong2 *>(ws + L.lst_hdr);
     P.lst_ent = reinterpret_cast<int2 *>(ws + L.lst_ent);
     P.tail_t = 8;
+    P.packed_reduce = 1;
+    if (const char *e = getenv("CYB_LAP_PACKED")) P.packed_reduce = atoi(e) ? 1 : 0;
     P.tail_mode = -1;        // chosen below, once the shared-memory residency is known
     P.early_stop = 0;      // measured: postponed price wars get longer at smaller eps
     P.use_lists = 1;
@@ -1203,7 +1267,8 @@ extern "C" int cyb_lap_solve_i32(const int32_t *cost_dev, int64_t ld, int64_t n_
     P.tail_t = P.tail_mode == 1 ? 32 : 8;
     if (const char *e = getenv("CYB_LAP_TAIL")) P.tail_t = atoi(e);
 
-    const void *fn = smemp ? (const void *)lap_auction_kernel<true> : (const void *)lap_auction_kernel<false>;
+    const void *fn = smemp ? (P.tail_mode ? (const void *)lap_auction_kernel<true, 1> : (const void *)lap_auction_kernel<true, 0>)
+                           : (P.tail_mode ? (const void *)lap_auction_kernel<false, 1> : (const void *)lap_auction_kernel<false, 0>);
     CYB_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
     int occ = 0;
     CYB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kThreads, dyn));

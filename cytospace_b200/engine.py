@@ -25,7 +25,8 @@ PRECISIONS = {"f16": 0, "f16x3": 1}
 #: ``--distance-metric`` values (argument_parser.py:72-74) -> CYB_METRIC_*
 METRICS = {"Pearson_correlation": 0, "Spearman_correlation": 1, "Euclidean": 2}
 STAT_NAMES = ("status", "phases", "rounds", "bids", "passes", "cost_min", "cost_max", "scale",
-              "grid", "smem_prices", "tail_mode", "max_bidders", "phase_scans", "tail_bids", "tails", "list_hits")
+              "grid", "smem_prices", "tail_mode", "max_bidders", "phase_scans", "tail_bids", "tails", "list_hits",
+              "small_rounds", "ns_bid", "ns_barrier", "ns_resolve", "ns_tail")
 
 
 def _round_up(x: int, a: int) -> int:

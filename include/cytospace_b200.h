@@ -47,7 +47,7 @@
 extern "C" {
 #endif
 
-#define CYB_ABI_VERSION 4
+#define CYB_ABI_VERSION 5
 
 /* status codes */
 #define CYB_OK                 0
@@ -73,7 +73,7 @@ extern "C" {
                                operand error ~2^-22, fp32-accumulation bound         */
 
 /* number of int64 entries written to stats_dev by cyb_lap_solve_i32 */
-#define CYB_LAP_NSTATS 16
+#define CYB_LAP_NSTATS 21
 /* stats_dev layout:
  *  [0] status (0 ok)        [1] eps-scaling phases      [2] bidding rounds
  *  [3] bids (= row scans in rounds)  [4] full-matrix row scans (phase starts)
@@ -82,7 +82,10 @@ extern "C" {
  *  [10] tail mode used (0 Gauss-Seidel FIFO, 1 in-CTA Jacobi rounds) [11] max bidders in a round
  *  [12] row scans at phase starts (rows whose pair was re-checked)
  *  [13] bids made in Gauss-Seidel tails (one CTA, no grid barrier)  [14] tails run
- *  [15] tail bids served from a candidate list (no row scan) */
+ *  [15] tail bids served from a candidate list (no row scan)
+ *  [16] rounds with at most one bidder per CTA, and for those, as seen by CTA 0 (globaltimer ns):
+ *  [17] time in the bid scan  [18] time in the grid barrier  [19] time in the record replay
+ *  [20] ns spent in tails */
 
 int         cyb_abi_version(void);
 const char *cyb_last_error(void);

@@ -1,5 +1,4 @@
-bash scripts/gpu_check.sh test_gpu_metrics test_gpu_lap test_gpu_cost test_gpu_path
-bash scripts/gpu_profile.sh cfg2 2>&1 | tail -15
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_cfg2_spearman.csv \
-    python bench.py --workload cfg2 --steps 2 --warmup 1 --no-cpu-baseline --distance-metric Spearman_correlation > gpurun_out/ncu_launch_spearman.log 2>&1
-bash scripts/gpu_bench_all.sh cfg3 cfg4 chunk25k
+bash scripts/gpu_check.sh test_gpu_lap test_gpu_path
+python scripts/gpu_lap_sweep3.py 10000 20000 1 1002,1003 CYB_LAP_PACKED=1 > gpurun_out/timing_10k.log 2>&1; cat gpurun_out/timing_10k.log
+python scripts/gpu_lap_sweep3.py 30000 6000 6 1004,1008 CYB_LAP_PACKED=1 > gpurun_out/timing_cfg4.log 2>&1; cat gpurun_out/timing_cfg4.log
+python scripts/gpu_lap_sweep3.py 25000 20000 1 1005 CYB_LAP_PACKED=1 > gpurun_out/timing_25k.log 2>&1; cat gpurun_out/timing_25k.log

@@ -26,6 +26,7 @@ for seed in seeds:
         if ref is None: ref = res.total
         tag = " ".join(f"{k.replace('CYB_LAP_', '').lower()}={v}" for k, v in zip(names, combo))
         print(f"seed={seed} n={n} cps={cps} {tag}: {min(ms):.1f} ms ok={res.total == ref} phases={s['phases']} rounds={s['rounds']} "
-              f"bids={s['bids']} tail={s['tail_bids']} hits={s['list_hits']}", flush=True)
+              f"bids={s['bids']} tail={s['tail_bids']} hits={s['list_hits']} | small rounds {s['small_rounds']}: bid {s['ns_bid'] / max(1, s['small_rounds']) / 1e3:.2f} "
+              f"bar {s['ns_barrier'] / max(1, s['small_rounds']) / 1e3:.2f} res {s['ns_resolve'] / max(1, s['small_rounds']) / 1e3:.2f} us; tails {s['ns_tail'] / 1e6:.1f} ms", flush=True)
     cert = eng.lap_check(cost, res)
     print("certificate", cert, flush=True)
