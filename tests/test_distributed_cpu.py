@@ -17,16 +17,20 @@ class OracleEngine:
     """Test double with the AssignmentEngine.assign contract, CPU tensors, oracle arithmetic."""
     device = torch.device("cpu")
 
-    def assign(self, sc, st, cn, log_tpm=False):
+    def assign(self, sc, st, cn, log_tpm=False, metric="Pearson_correlation", cspr_seed=None):
         import oracle
         from oracle import cost_oracle as co
         sc = sc.numpy() if torch.is_tensor(sc) else np.asarray(sc)
         st = st.numpy() if torch.is_tensor(st) else np.asarray(st)
         if log_tpm:
             sc, st = co.normalize_data(sc), co.normalize_data(st)
-        cost = co.cost_matrix_i32(sc, st)
+        cost = co.cost_matrix_i32(sc, st, metric)
         row_map = np.repeat(np.arange(len(cn), dtype=np.int32), np.asarray(cn))
-        _, colsol, _ = oracle.lapjv_i32(cost, row_map)
+        if cspr_seed is not None:
+            cost, row_map_solve = co.cspr_matrix_i32(cost, cn, cspr_seed), None
+        else:
+            row_map_solve = row_map
+        _, colsol, _ = oracle.lapjv_i32(cost, row_map_solve)
         return torch.from_numpy(row_map[colsol].astype(np.int64)), None, None
 
 
@@ -49,31 +53,37 @@ def _problem(mode):
     return sc, st, plan
 
 
+KW = {"single_cell": {}, "sub_spots": {}, "single_cell_spearman": {"metric": "Spearman_correlation"},
+      "sub_spots_cspr": {"metric": "Euclidean", "cspr_seed": 7}}
+BASE = {"single_cell": "single_cell", "sub_spots": "sub_spots", "single_cell_spearman": "single_cell",
+        "sub_spots_cspr": "sub_spots"}
+
+
 def _worker(rank, world, port, mode, q):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         from cytospace_b200 import chunking
-        sc, st, plan = _problem(mode)
+        sc, st, plan = _problem(BASE[mode])
         if rank == 0:
-            out = chunking.solve_chunks(OracleEngine(), sc, st, plan, log_tpm=True)
+            out = chunking.solve_chunks(OracleEngine(), sc, st, plan, log_tpm=True, **KW[mode])
         else:
-            out = chunking.solve_chunks(OracleEngine(), None, None, None, log_tpm=True)
+            out = chunking.solve_chunks(OracleEngine(), None, None, None, log_tpm=True)   # kwargs travel from rank 0
         q.put((rank, out))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", ["single_cell", "sub_spots"])
+@pytest.mark.parametrize("mode", ["single_cell", "sub_spots", "single_cell_spearman", "sub_spots_cspr"])
 def test_two_rank_chunk_distribution_matches_single_process(mode):
     sys.path.insert(0, ROOT)
     from cytospace_b200 import chunking
-    sc, st, plan = _problem(mode)
-    expect = chunking.solve_chunks(OracleEngine(), sc, st, plan, log_tpm=True)
+    sc, st, plan = _problem(BASE[mode])
+    expect = chunking.solve_chunks(OracleEngine(), sc, st, plan, log_tpm=True, **KW[mode])
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + (os.getpid() % 2000) + (0 if mode == "single_cell" else 1)
+    port = 29500 + (os.getpid() % 2000) + sorted(KW).index(mode)
     procs = [ctx.Process(target=_worker, args=(r, 2, port, mode, q)) for r in range(2)]
     for p in procs:
         p.start()
