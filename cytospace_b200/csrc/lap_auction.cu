@@ -286,9 +286,10 @@ __device__ __forceinline__ Best scan_row(const int32_t *__restrict__ r, int n, i
 
 // Cheapest slot of object o (lowest slot index on ties) when slot `t_new` holds `p_new` and
 // every other slot its stored price.
-__device__ __forceinline__ void cheapest_slot(const LapParams &P, int o, int t_new, long long p_new,
-                                              int &ms, long long &mp) {
-    const int s0 = P.soff ? __ldg(P.soff + o) : o, s1 = P.soff ? __ldg(P.soff + o + 1) : o + 1;
+__device__ __forceinline__ void cheapest_slot(const LapParams &P, const int *__restrict__ ssoff, int o, int t_new,
+                                              long long p_new, int &ms, long long &mp) {
+    const int s0 = P.soff ? (ssoff ? ssoff[o] : __ldg(P.soff + o)) : o;
+    const int s1 = P.soff ? (ssoff ? ssoff[o + 1] : __ldg(P.soff + o + 1)) : o + 1;
     ms = s0; mp = (s0 == t_new) ? p_new : __ldcg(P.slot_price + s0);
     for (int t = s0 + 1; t < s1; ++t) {
         const long long p = (t == t_new) ? p_new : __ldcg(P.slot_price + t);
@@ -437,6 +438,9 @@ __global__ void __launch_bounds__(kThreads, 1) lap_auction_kernel(const LapParam
     int *myq = reinterpret_cast<int *>(smem_raw + off);
     int *sowner = myq + ((P.qcap + 3) & ~3);          // [P] replica of slot_owner, only when P.smem_owner
     int *sminslot = sowner + ((np + 3) & ~3);         // [O] replica of minslot, only when P.smem_owner && P.soff
+    // (a shared-memory copy of the slot offsets was measured and rejected: at 30k x 5k it pushes the carve-out
+    // from 196 to 228 KB, the L1 from 60 to 28 KB, and the record replay from 7.4 to 9.0 us)
+    const int *ssoff = nullptr;
     __shared__ long long red_b1[32], red_b2[32];
     __shared__ int red_j[32], wcnt[32];
     __shared__ int tq[kTailMax], tq_head, tq_cnt, tq_status, sw_stop;
@@ -549,7 +553,7 @@ __global__ void __launch_bounds__(kThreads, 1) lap_auction_kernel(const LapParam
             for (int o = t; o < no; o += kThreads) {
                 if (capacity(o) > 1) {
                     int ms; long long mp;
-                    cheapest_slot(P, o, -1, 0, ms, mp);
+                    cheapest_slot(P, ssoff, o, -1, 0, ms, mp);
                     P.minslot[o] = ms;                       // identical write from every CTA
                     if (P.smem_owner) sminslot[o] = ms;
                 }
@@ -592,7 +596,7 @@ __global__ void __launch_bounds__(kThreads, 1) lap_auction_kernel(const LapParam
                     auto assign_one = [&](int i, int o, long long bid, int slot, int prev) -> int {
                         if (bid >= kBidLimit) tq_status = CYB_ERR_OVERFLOW;
                         long long mp = bid; int ms = slot;
-                        if (P.soff) cheapest_slot(P, o, slot, bid, ms, mp);
+                        if (P.soff) cheapest_slot(P, ssoff, o, slot, bid, ms, mp);
                         if (P.smem_owner) { sowner[slot] = i; if (P.soff) sminslot[o] = ms; }
                         P.slot_owner[slot] = i; P.slot_price[slot] = bid;
                         P.person_obj[i] = o; P.person_slot[i] = slot;
@@ -736,7 +740,7 @@ __global__ void __launch_bounds__(kThreads, 1) lap_auction_kernel(const LapParam
                             const int slot = P.soff ? (P.smem_owner ? sminslot[o] : __ldcg(P.minslot + o)) : o;
                             const int prev = P.smem_owner ? sowner[slot] : __ldcg(P.slot_owner + slot);
                             long long mp = bid; int ms = slot;
-                            if (P.soff) cheapest_slot(P, o, slot, bid, ms, mp);
+                            if (P.soff) cheapest_slot(P, ssoff, o, slot, bid, ms, mp);
                             commit(i, o, bid, slot, prev, ms, mp);
                         };
                         // warp version (after a list hit, every lane holds `s`): the slots of a capacitated
@@ -751,7 +755,7 @@ __global__ void __launch_bounds__(kThreads, 1) lap_auction_kernel(const LapParam
                                 if (lane == 0) commit(i, o, bid, o, prev, o, bid);
                                 return prev;
                             }
-                            const int s0 = __ldg(P.soff + o), s1 = __ldg(P.soff + o + 1);
+                            const int s0 = ssoff ? ssoff[o] : __ldg(P.soff + o), s1 = ssoff ? ssoff[o + 1] : __ldg(P.soff + o + 1);
                             if (s1 - s0 > 32) {
                                 const int slot = __ldcg(P.minslot + o);
                                 const int prev = __ldcg(P.slot_owner + slot);
@@ -893,7 +897,7 @@ __global__ void __launch_bounds__(kThreads, 1) lap_auction_kernel(const LapParam
                         const bool mine = (k % G == b);
                         P.slot_owner[rc.y] = i; P.slot_price[rc.y] = bid;     // identical writes from every CTA
                         int ms; long long mp;
-                        cheapest_slot(P, rc.x, rc.y, bid, ms, mp);
+                        cheapest_slot(P, ssoff, rc.x, rc.y, bid, ms, mp);
                         P.minslot[rc.x] = ms;
                         if (P.smem_owner) { sowner[rc.y] = i; if (P.soff) sminslot[rc.x] = ms; }
                         if (SMEMP) { sprice[rc.x] = mp; if (mine) P.lambda[rc.x] = mp; }
@@ -1264,7 +1268,7 @@ extern "C" int cyb_lap_solve_i32(const int32_t *cost_dev, int64_t ld, int64_t n_
     // chains two or three round trips and the multi-chain Jacobi tail hides them (measured on B200:
     // 25k 288 -> 244 ms, 50k 975 -> 712 ms).
     if (P.tail_mode < 0) P.tail_mode = (smemp && P.smem_owner) ? 0 : 1;
-    P.tail_t = P.tail_mode == 1 ? 32 : 8;
+    P.tail_t = P.tail_mode == 1 ? 32 : (slot_offset_dev ? 6 : 8);   // a capacitated Gauss-Seidel step costs more: later switch
     if (const char *e = getenv("CYB_LAP_TAIL")) P.tail_t = atoi(e);
 
     const void *fn = smemp ? (P.tail_mode ? (const void *)lap_auction_kernel<true, 1> : (const void *)lap_auction_kernel<true, 0>)
