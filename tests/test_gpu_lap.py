@@ -238,3 +238,29 @@ def test_certificate_tiled_variant_above_12288_objects(engine):
     assert bad["max_violation"] > 1 and bad["capacity_mismatch"] == 0
     res.person_obj = keep.clone(); res.person_obj[5] = keep[6]
     assert engine.lap_check(dev, res)["capacity_mismatch"] == 2
+
+
+@pytest.mark.parametrize("approx", [1, 0])
+@pytest.mark.parametrize("tail_mode", [0, 1])
+def test_l2_price_paths_on_small_problems(engine, lap_golden, approx, tail_mode):
+    """The code paths of problems too large for shared-memory prices (50k objects), forced on small
+    inputs: 64-bit prices streamed from L2 (approx=0) and the 32-bit price-prefix scan with exact
+    re-evaluation of the candidates (approx=1).  Same totals, same assignment as the default path."""
+    env = {"CYB_LAP_SMEM_PRICES": 0, "CYB_LAP_APPROX": approx, "CYB_LAP_TAIL_MODE": tail_mode}
+    for name in LAP_NAMES:
+        cost = lap_golden[f"{name}_cost"]
+        res, po = _with_env(env, lambda: solve_and_check(engine, cost))
+        assert res.total == int(lap_golden[f"{name}_opt"]) and res.stats["smem_prices"] == 0
+    rng = np.random.default_rng(12)
+    cap = rng.integers(0, 5, 300).astype(np.int32)
+    m = rng.integers(-200_000, 200_000, (int(cap.sum()), 300), dtype=np.int32)
+    ref, po_ref = _with_env({"CYB_LAP_TAIL_MODE": tail_mode}, lambda: solve_and_check(engine, m, cap))
+    res, po = _with_env(env, lambda: solve_and_check(engine, m, cap))
+    assert res.total == ref.total and np.array_equal(po, po_ref)
+    sq = syn.uniform_cost_i32(1500, seed=9, high=3000)                    # many near-ties: exercises the fallback
+    ref, po_ref = _with_env({"CYB_LAP_TAIL_MODE": tail_mode}, lambda: solve_and_check(engine, sq))
+    res, po = _with_env(env, lambda: solve_and_check(engine, sq))
+    assert res.total == ref.total == oracle.lapjv_i32(sq)[2][0] and np.array_equal(po, po_ref)
+    tie = np.zeros((200, 200), np.int32)                                   # every column ties: always falls back
+    res, _ = _with_env(env, lambda: solve_and_check(engine, tie))
+    assert res.total == 0
