@@ -1133,12 +1133,12 @@ __global__ void __launch_bounds__(kChkThreads) lap_rowmin_kernel(
 }
 
 // Whole-row variant for price vectors that fit in shared memory (objects <= kChkWholeMax): every CTA
-// stages ALL prices once, a TEAM of four warps streams one row at a time (rows are dealt to ~8 teams
-// per SM, so a 10k-row matrix still balances to within one row in nine), and the certificate terms of
+// stages ALL prices once, a TEAM of eight warps streams one row at a time (rows are dealt to 4 teams
+// per SM, so a 10k-row matrix balances to within one row in seventeen), and the certificate terms of
 // that row (violation, cost, capacity count) are taken in the same pass -- no row-minimum buffer, no
 // atomics on it, no second kernel.  acc = {max violation, total, invalid rows} (zero-initialised).
 constexpr int kChkWholeMax = 12288;              // 96 KB of prices -> two CTAs per SM
-constexpr int kTeam = 128;                       // threads per row team
+constexpr int kTeam = 256;                       // threads per row team (10k-column row: ten 16-byte loads per thread, all in flight)
 constexpr int kTeams = kChkThreads / kTeam;
 
 __global__ void __launch_bounds__(kChkThreads) lap_rowcheck_whole_kernel(
@@ -1168,7 +1168,7 @@ __global__ void __launch_bounds__(kChkThreads) lap_rowcheck_whole_kernel(
         const int c_o = (tt == 0 && o_ok) ? __ldg(r + o_cur) : 0;
         long long m = LLONG_MAX;
         const int4 *r4 = reinterpret_cast<const int4 *>(r);
-#pragma unroll 8
+#pragma unroll 12
         for (int q = tt; q < n4; q += kTeam) {
             const int4 c = ld_stream(r4 + q, pol);
             const longlong2 a = *reinterpret_cast<const longlong2 *>(spw + 4 * q);
@@ -1353,9 +1353,9 @@ extern "C" int cyb_lap_solve_i32(const int32_t *cost_dev, int64_t ld, int64_t n_
     P.lst_hdr = reinterpret_cast<longlong2 *>(ws + L.lst_hdr);
     P.lst_ent = reinterpret_cast<int2 *>(ws + L.lst_ent);
     P.tail_t = 8;
-    // rows longer than the 64 KB a CTA keeps in flight (measured: 50k 680 -> 620 ms; neutral at 40 KB rows;
-    // prefetching for the sweepers as well slowed the tail they run beside: 25k tails 177 -> 187 ms)
-    P.prefetch = no * 4 > 65536 ? 1 : 0;
+    // rows much longer than the 64 KB a CTA keeps in flight (measured: 50k 680 -> 620 ms; neutral at 40 KB rows,
+    // within noise at 100 KB; prefetching for the sweepers as well slowed the tail they run beside)
+    P.prefetch = no * 4 > 131072 ? 1 : 0;
     if (const char *e = getenv("CYB_LAP_PREFETCH")) P.prefetch = atoi(e) ? 1 : 0;
     P.packed_reduce = 1;
     if (const char *e = getenv("CYB_LAP_PACKED")) P.packed_reduce = atoi(e) ? 1 : 0;
@@ -1396,7 +1396,7 @@ extern "C" int cyb_lap_solve_i32(const int32_t *cost_dev, int64_t ld, int64_t n_
     // chains two or three round trips and the multi-chain Jacobi tail hides them (measured on B200:
     // 25k 288 -> 244 ms, 50k 975 -> 712 ms).
     if (P.tail_mode < 0) P.tail_mode = (smemp && P.smem_owner) ? 0 : 1;
-    P.tail_t = P.tail_mode == 1 ? 32 : (slot_offset_dev ? 6 : 8);   // a capacitated Gauss-Seidel step costs more: later switch
+    P.tail_t = P.tail_mode == 1 ? 32 : 8;      // (6 for capacitated problems helped one 30k x 5k instance, hurt another)
     if (const char *e = getenv("CYB_LAP_TAIL")) P.tail_t = atoi(e);
 
     const void *fn = smemp ? (P.tail_mode ? (const void *)lap_auction_kernel<true, 1> : (const void *)lap_auction_kernel<true, 0>)

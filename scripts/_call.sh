@@ -1,5 +1,6 @@
-bash scripts/gpu_check.sh test_gpu_lap
-python scripts/gpu_lap_sweep3.py 10000 20000 1 1002 CYB_LAP_PREFETCH=0,1 > gpurun_out/pf_10k.log 2>&1; cat gpurun_out/pf_10k.log
-python scripts/gpu_lap_sweep3.py 30000 6000 6 1004 CYB_LAP_PREFETCH=0,1 > gpurun_out/pf_cfg4.log 2>&1; cat gpurun_out/pf_cfg4.log
-python scripts/gpu_lap_sweep3.py 25000 20000 1 1005 CYB_LAP_PREFETCH=0,1 > gpurun_out/pf_25k.log 2>&1; cat gpurun_out/pf_25k.log
-python scripts/gpu_lap_sweep3.py 50000 20000 1 1003 CYB_LAP_PREFETCH=0,1 > gpurun_out/pf_50k.log 2>&1; cat gpurun_out/pf_50k.log
+bash scripts/gpu_check.sh test_gpu_metrics test_gpu_lap test_gpu_cost test_gpu_path
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+bash scripts/gpu_profile.sh cfg2 2>&1 | grep -v "^-rw\|^drwx\|^total"
+bash scripts/gpu_bench_all.sh cfg3 cfg4 chunk25k
+for M in Spearman_correlation Euclidean; do python bench.py --workload cfg2 --steps 3 --warmup 3 --no-cpu-baseline --distance-metric $M > gpurun_out/bench_cfg2_$M.json 2>/dev/null; python -c "
+import json; d=json.load(open('gpurun_out/bench_cfg2_$M.json')); print('$M', d['ms_per_step'], d['lap_ms'], d['cost_build_ms'], d['certificate'])"; done
