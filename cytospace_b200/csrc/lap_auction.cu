@@ -1133,12 +1133,12 @@ __global__ void __launch_bounds__(kChkThreads) lap_rowmin_kernel(
 }
 
 // Whole-row variant for price vectors that fit in shared memory (objects <= kChkWholeMax): every CTA
-// stages ALL prices once, a TEAM of eight warps streams one row at a time (rows are dealt to 4 teams
-// per SM, so a 10k-row matrix balances to within one row in seventeen), and the certificate terms of
+// stages ALL prices once, a TEAM of four warps streams one row at a time (rows are dealt to ~8 teams
+// per SM, so a 10k-row matrix still balances to within one row in nine), and the certificate terms of
 // that row (violation, cost, capacity count) are taken in the same pass -- no row-minimum buffer, no
 // atomics on it, no second kernel.  acc = {max violation, total, invalid rows} (zero-initialised).
 constexpr int kChkWholeMax = 12288;              // 96 KB of prices -> two CTAs per SM
-constexpr int kTeam = 256;                       // threads per row team (10k-column row: ten 16-byte loads per thread, all in flight)
+constexpr int kTeam = 128;                       // threads per row team (measured: 256-thread teams are slower, 148 vs 102 us at 10k)
 constexpr int kTeams = kChkThreads / kTeam;
 
 __global__ void __launch_bounds__(kChkThreads) lap_rowcheck_whole_kernel(
@@ -1168,7 +1168,7 @@ __global__ void __launch_bounds__(kChkThreads) lap_rowcheck_whole_kernel(
         const int c_o = (tt == 0 && o_ok) ? __ldg(r + o_cur) : 0;
         long long m = LLONG_MAX;
         const int4 *r4 = reinterpret_cast<const int4 *>(r);
-#pragma unroll 12
+#pragma unroll 8
         for (int q = tt; q < n4; q += kTeam) {
             const int4 c = ld_stream(r4 + q, pol);
             const longlong2 a = *reinterpret_cast<const longlong2 *>(spw + 4 * q);
