@@ -44,11 +44,31 @@
 // Lists, records and bid words rotate over three buffers by round: a fast CTA
 // bidding in round r+1 never disturbs a slow CTA resolving round r, and the bid
 // words of round r-1 are cleared during resolve r (their next use is round r+2).
-// When <= tail_t bidders are left, CTA 0 alone drains them as a Gauss-Seidel
-// FIFO (no barrier per bid); the other CTAs pick up the prices at the phase end.
+// Tail.  A round costs ~7 us whatever its size and most rounds have one or two
+// bidders (long eviction chains), so when few bidders are left CTA 0 finishes
+// the phase alone while the other CTAs ("sweepers") keep per-person candidate
+// lists fresh -- a list certifies the exact result of a row scan from a handful
+// of entries.  Two tails, a compile-time choice (template parameter TM) made on
+// the host from what fits in shared memory:
+//   TM = 0  Gauss-Seidel FIFO (<= 8 bidders): one bid at a time by warp 0, each
+//           seeing the prices the previous one left; used when prices AND slot
+//           owners are shared-memory resident (a step = one L2 round trip).
+//   TM = 1  Jacobi rounds inside CTA 0 (<= 32 bidders): every warp owns one
+//           eviction chain, all bids of a round see the same prices, winners are
+//           resolved from the posted bids; same round semantics as the grid, so
+//           the result does not depend on where the switch happens.  Used when
+//           prices or owners live in L2 (25k, 50k): parallel chains hide the
+//           two or three chained L2 round trips of a step.
+// The other CTAs pick up prices / owners at the phase end.
 //
 // HBM traffic: each bid reads one row (O*4 bytes) once; prices, holders, lists
 // and bid words live in shared memory / L2.
+//
+// Tuning knobs (environment, read at launch; defaults are the measured best):
+// CYB_LAP_TAIL_MODE, CYB_LAP_TAIL, CYB_LAP_THETA, CYB_LAP_EPS0, CYB_LAP_LISTS,
+// CYB_LAP_SWEEPERS, CYB_LAP_PACKED, CYB_LAP_PREFETCH, CYB_LAP_SMEM_OWNER, and
+// the experiments that did not pay (off): CYB_LAP_EARLY, CYB_LAP_APPROX;
+// CYB_LAP_SMEM_PRICES=0 forces the L2-price code paths (tests).
 
 #include <algorithm>
 #include <climits>

@@ -233,10 +233,13 @@ size_t cyb_lap_workspace_bytes(int64_t n_persons, int64_t n_objects);
  *   total_dev       int64[1] out: sum_i cost[i, person_obj[i]]
  *   stats_dev       int64[CYB_LAP_NSTATS] out (layout above)
  *   grid_hint       0 = auto (one CTA per SM); otherwise the number of CTAs
- * Synchronous eps-scaling auction (Jacobi rounds, Gauss-Seidel tail) in one persistent
- * cooperative kernel; costs scaled by n_persons+1, last phase eps = 1 => the returned
- * assignment is optimal for the integer matrix.  Deterministic: lowest object index wins a
- * person's tie, highest bid then lowest person index wins an object.               */
+ * Synchronous eps-scaling auction (Jacobi rounds over the grid; the last few bidders of a
+ * phase are finished by one CTA, as a Gauss-Seidel FIFO or as in-CTA Jacobi rounds depending
+ * on what is shared-memory resident, stats[10]) in one persistent cooperative kernel; costs
+ * scaled by n_persons+1, last phase eps = 1 => the returned assignment is optimal for the
+ * integer matrix.  Deterministic for a given device and problem: lowest object index wins a
+ * person's tie, highest bid then lowest person index wins an object; independent of the grid
+ * size.  Limits: n_persons < 2^18, |cost| < 2^30.                                         */
 int cyb_lap_solve_i32(const int32_t *cost_dev, int64_t ld, int64_t n_persons, int64_t n_objects,
                       const int32_t *slot_offset_dev, int32_t *person_obj_dev,
                       int32_t *slot_owner_dev, int64_t *price_dev, int64_t *total_dev,

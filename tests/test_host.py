@@ -44,6 +44,9 @@ def test_native_argument_errors_without_gpu():
     rc = lib.cyb_lap_solve_i32(ffi.NULL, 8, 8, 4, ffi.NULL, ffi.NULL, ffi.NULL, ffi.NULL, ffi.NULL, ffi.NULL,
                                ffi.NULL, 0, 0, ffi.NULL)
     assert rc == lib.CYB_ERR_INVALID and b"square" in ffi.string(lib.cyb_last_error())
+    rc = lib.cyb_lap_solve_i32(ffi.NULL, 1 << 18, 1 << 18, 1 << 18, ffi.NULL, ffi.NULL, ffi.NULL, ffi.NULL, ffi.NULL,
+                               ffi.NULL, ffi.NULL, 0, 0, ffi.NULL)
+    assert rc == lib.CYB_ERR_INVALID and b"2^18" in ffi.string(lib.cyb_last_error())     # person index is 18 bits
     rc = lib.cyb_cost_gemm_i32(ffi.cast("void *", 16), ffi.cast("void *", 16), 8, 8, 70, 1.0,
                                ffi.cast("int32_t *", 16), 8, ffi.NULL)
     assert rc == lib.CYB_ERR_INVALID           # k not a multiple of 64
