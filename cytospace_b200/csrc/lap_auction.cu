@@ -410,6 +410,7 @@ __device__ __forceinline__ void cheapest_slot(const LapParams &P, const int *__r
     const int s0 = P.soff ? (ssoff ? ssoff[o] : __ldg(P.soff + o)) : o;
     const int s1 = P.soff ? (ssoff ? ssoff[o + 1] : __ldg(P.soff + o + 1)) : o + 1;
     ms = s0; mp = (s0 == t_new) ? p_new : __ldcg(P.slot_price + s0);
+#pragma unroll 4
     for (int t = s0 + 1; t < s1; ++t) {
         const long long p = (t == t_new) ? p_new : __ldcg(P.slot_price + t);
         if (p < mp) { mp = p; ms = t; }
@@ -670,7 +671,7 @@ __global__ void __launch_bounds__(kThreads, 1) lap_auction_kernel(const LapParam
             const int i = i0 + t;
             const int f = (i < np) ? (phases == 1 ? 1 : __ldcg(P.flag + i)) : 0;
             if (f >= 2) {
-                P.slot_owner[f - 2] = -1;                    // identical write from every CTA; price stays
+                if (i % G == b || !P.smem_owner) P.slot_owner[f - 2] = -1;      // the slot keeps its price
                 if (P.smem_owner) sowner[f - 2] = -1;
                 if (i % G == b) { P.person_obj[i] = -1; P.person_slot[i] = -1; }
             }
@@ -685,7 +686,7 @@ __global__ void __launch_bounds__(kThreads, 1) lap_auction_kernel(const LapParam
                 if (capacity(o) > 1) {
                     int ms; long long mp;
                     cheapest_slot(P, ssoff, o, -1, 0, ms, mp);
-                    P.minslot[o] = ms;                       // identical write from every CTA
+                    if (o % G == b || !P.smem_owner) P.minslot[o] = ms;
                     if (P.smem_owner) sminslot[o] = ms;
                 }
             }
@@ -1030,10 +1031,19 @@ __global__ void __launch_bounds__(kThreads, 1) lap_auction_kernel(const LapParam
                     if (wperson == i) {
                         const long long bid = (long long)(key >> kPersonBits);
                         const bool mine = (k % G == b);
-                        P.slot_owner[rc.y] = i; P.slot_price[rc.y] = bid;     // identical writes from every CTA
                         int ms; long long mp;
+                        // sibling slot prices FIRST: with the stores in front, 148 CTAs storing to one line and
+                        // then loading from it serialised at the L2 slice (replay 8.3 us -> 3.0 us at 30k x 5k)
                         cheapest_slot(P, ssoff, rc.x, rc.y, bid, ms, mp);
-                        P.minslot[rc.x] = ms;
+                        // global copies: every CTA writes them (identical values) only when some CTA reads them
+                        // back before the next barrier, i.e. without the shared-memory replicas
+                        // (slot prices are only read behind a barrier: one writer; the cheapest-slot index of a
+                        // unit-capacity object never changes)
+                        if (mine || !P.smem_owner) {
+                            P.slot_owner[rc.y] = i;
+                            if (P.soff) P.minslot[rc.x] = ms;
+                        }
+                        if (mine) P.slot_price[rc.y] = bid;
                         if (P.smem_owner) { sowner[rc.y] = i; if (P.soff) sminslot[rc.x] = ms; }
                         if (SMEMP) { sprice[rc.x] = mp; if (mine) P.lambda[rc.x] = mp; }
                         else { P.lambda[rc.x] = mp; if (P.approx) sp32[rc.x] = price_hi(mp); }
