@@ -164,7 +164,7 @@ def run_reference(args, wl):
 
 
 # ----------------------------------------------------------------------------------- B200 arm
-def cpu_baseline(cost_np, row_map, sc_host, st_host, wl, total_gpu):
+def cpu_baseline(cost_np, row_map, sc_host, st_host, wl, total_gpu, with_scipy=False):
     """Oracle on this box's host cores: restated JV (int32, 1 thread) on the GPU-built matrix (full
     size up to 10k, else its leading 10k block) + numpy float64 cost build on a 2k x 2k x G block."""
     import oracle
@@ -182,6 +182,16 @@ def cpu_baseline(cost_np, row_map, sc_host, st_host, wl, total_gpu):
         t0 = time.perf_counter()
         total_cpu = oracle.lapjv_i32(cost_np, row_map)[2][0]
         t_lap = time.perf_counter() - t0
+        # an independent implementation on the same integer matrix (SURVEY 8c pin (i)): SciPy's JV variant
+        try:
+            if with_scipy and n <= 10000 and row_map is None:           # ~90 s at 10k: opt-in (--cpu-scipy)
+                from scipy.optimize import linear_sum_assignment
+                t0 = time.perf_counter()
+                ri, ci = linear_sum_assignment(cost_np.astype(np.float64))
+                out["scipy_lap_s"] = time.perf_counter() - t0
+                out["scipy_total_equal"] = bool(int(cost_np[ri, ci].astype(np.int64).sum()) == total_gpu)
+        except Exception as e:            # a reported extra, never allowed to cost the bench line
+            out["scipy_error"] = repr(e)[:200]
         out.update(value=n / (t_cost + t_lap), lap_s=t_lap, cost_build_s_scaled=t_cost,
                    total_cost=int(total_cpu), total_equal=bool(total_cpu == total_gpu),
                    sample=f"LAP: restated JV (int32, 1 thread) on the full GPU-built {n}x{n} matrix; cost build: "
@@ -386,7 +396,7 @@ def run_b200(args, wl):
             row_map = None if cps == 1 else np.repeat(np.arange(n_spots, dtype=np.int32), cn)
             # the oracle takes the reference's orientation (spots x cells)
             cost_np = np.ascontiguousarray((cost[:, :n_cells] if cps == 1 else cost[:, :n_spots].T).cpu().numpy())
-            line["cpu_baseline"] = cpu_baseline(cost_np, row_map, sc_host, st_host, wl, res.total)
+            line["cpu_baseline"] = cpu_baseline(cost_np, row_map, sc_host, st_host, wl, res.total, args.cpu_scipy)
         emit(line)
     if world > 1:
         dist.barrier()
@@ -420,6 +430,8 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default="f16x3", choices=["f16", "f16x3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-scipy", action="store_true",
+                    help="also time scipy.optimize.linear_sum_assignment on the GPU-built matrix (n <= 10k; ~90 s)")
     ap.add_argument("--distance-metric", default="Pearson_correlation",
                     choices=["Pearson_correlation", "Spearman_correlation", "Euclidean"])
     args = ap.parse_args()
