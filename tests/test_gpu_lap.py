@@ -264,3 +264,23 @@ def test_l2_price_paths_on_small_problems(engine, lap_golden, approx, tail_mode)
     tie = np.zeros((200, 200), np.int32)                                   # every column ties: always falls back
     res, _ = _with_env(env, lambda: solve_and_check(engine, tie))
     assert res.total == 0
+
+
+@pytest.mark.parametrize("tail_mode", [0, 1])
+@pytest.mark.parametrize("smem_prices", [1, 0])
+def test_without_shared_memory_owner_replicas(engine, tail_mode, smem_prices):
+    """Problems too large for the slot-owner replicas (25k and up) read owners / cheapest slots from global
+    memory, kept identical by every CTA's replay: forced here on small capacitated and unit problems."""
+    env = {"CYB_LAP_SMEM_OWNER": 0, "CYB_LAP_SMEM_PRICES": smem_prices, "CYB_LAP_TAIL_MODE": tail_mode}
+    rng = np.random.default_rng(21)
+    cap = rng.integers(0, 7, 250).astype(np.int32)
+    m = rng.integers(-300_000, 300_000, (int(cap.sum()), 250), dtype=np.int32)
+    ref, po_ref = _with_env({"CYB_LAP_TAIL_MODE": tail_mode}, lambda: solve_and_check(engine, m, cap))
+    res, po = _with_env(env, lambda: solve_and_check(engine, m, cap))
+    assert res.total == ref.total and np.array_equal(po, po_ref)
+    row_map = np.repeat(np.arange(250, dtype=np.int32), cap)
+    assert res.total == oracle.lapjv_i32(np.ascontiguousarray(m.T), row_map)[2][0]
+    sq = syn.uniform_cost_i32(1200, seed=4)
+    ref, po_ref = _with_env({"CYB_LAP_TAIL_MODE": tail_mode}, lambda: solve_and_check(engine, sq))
+    res, po = _with_env(env, lambda: solve_and_check(engine, sq))
+    assert res.total == ref.total == oracle.lapjv_i32(sq)[2][0] and np.array_equal(po, po_ref)
