@@ -38,9 +38,13 @@
 //                update the slot, the object's cheapest slot / price (also in
 //                the CTA's shared-memory replica) and the next free list (a
 //                block-wide prefix sum gives every CTA the same positions;
-//                CTA b keeps positions = b mod G as its next work queue).  All
-//                CTAs write identical values, so each CTA's own view of the
-//                state is complete without a second barrier.
+//                CTA b keeps positions = b mod G as its next work queue).  Every
+//                CTA ends the replay with the same view of the state -- in its
+//                shared-memory replicas (prices, slot owners, cheapest slots)
+//                when they fit, otherwise by writing the identical values to
+//                global memory itself -- so no second barrier is needed; state
+//                that is only read behind the next barrier has ONE writer (148
+//                CTAs storing to one line serialise at the L2 slice).
 // Lists, records and bid words rotate over three buffers by round: a fast CTA
 // bidding in round r+1 never disturbs a slow CTA resolving round r, and the bid
 // words of round r-1 are cleared during resolve r (their next use is round r+2).
