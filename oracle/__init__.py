@@ -34,7 +34,7 @@ _lib = None
 
 def build(force: bool = False) -> str:
     """Compile liboracle.so with the committed Makefile (gcc, -O3)."""
-    srcs = [os.path.join(_HERE, f) for f in ("lapjv_oracle.c", "lapjv_body.inc", "auction_model.c", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in ("lapjv_oracle.c", "lapjv_body.inc", "auction_model.c", "sap_model.c", "Makefile")]
     stale = force or not os.path.exists(_LIB_PATH) or any(
         os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs)
     if stale:
@@ -62,6 +62,9 @@ def _load():
         lib.auction_model_i32.restype = ctypes.c_int
         lib.auction_model_i32.argtypes = [ctypes.c_int, ctypes.c_int, i32p, ctypes.c_int64, i32p, i32p, i32p, i64p, i64p,
                                           ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, i64p, i32p, ctypes.c_int64, ctypes.c_int]
+        lib.sap_model_i32.restype = ctypes.c_int
+        lib.sap_model_i32.argtypes = [ctypes.c_int, ctypes.c_int, i32p, ctypes.c_int64, i32p, i32p, i32p, i64p, i64p,
+                                      ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, i64p]
         _lib = lib
     return _lib
 
@@ -158,3 +161,25 @@ def auction_model(m, cap=None, theta=4, eps0_div=4, tail_t=0, round_cap=0, varia
     if rc != 0:
         raise RuntimeError(f"auction_model_i32 failed rc={rc}")
     return person_obj, slot_owner, int(total[0]), lam, stats, rlog[:min(round_cap, int(stats[1]))]
+
+
+def sap_model(m, cap=None, theta=4, eps0_div=4, sap_t=64, K=148, multi=0):
+    """Sequential model of the hybrid device solver (auction rounds + shortest-augmenting-path finish,
+    ``sap_model.c``).  Same orientation as ``auction_model``.  Returns (person_obj, slot_owner, total,
+    lambda, stats, phase_log) -- stats / phase_log columns are documented in sap_model.c."""
+    lib = _load()
+    m = np.ascontiguousarray(m, dtype=np.int32)
+    P, O = m.shape
+    capa = None if cap is None else np.ascontiguousarray(cap, dtype=np.int32)
+    if (O if capa is None else int(capa.sum())) != P:
+        raise ValueError("capacities must sum to the number of persons")
+    person_obj = np.empty(P, np.int32); slot_owner = np.empty(P, np.int32)
+    lam = np.zeros(O, np.int64); total = np.zeros(1, np.int64); stats = np.zeros(8, np.int64)
+    rc = lib.sap_model_i32(P, O, _ptr(m, ctypes.c_int32), m.shape[1], _ptr(capa, ctypes.c_int32),
+                           _ptr(person_obj, ctypes.c_int32), _ptr(slot_owner, ctypes.c_int32),
+                           _ptr(lam, ctypes.c_int64), _ptr(total, ctypes.c_int64),
+                           theta, eps0_div, sap_t, K, multi, _ptr(stats, ctypes.c_int64))
+    if rc != 0:
+        raise RuntimeError(f"sap_model_i32 failed rc={rc}")
+    log = np.ctypeslib.as_array((ctypes.c_int64 * 8 * 64).in_dll(lib, "sap_phase_log")).copy()
+    return person_obj, slot_owner, int(total[0]), lam, stats, log[:int(stats[0])]

@@ -1,0 +1,336 @@
+/* TEST INFRASTRUCTURE ONLY -- sequential CPU model of the HYBRID device LAP solver:
+ * synchronous (Jacobi) eps-scaling auction rounds for the bulk of every phase (as in
+ * auction_model.c) and, once few persons are free, a multi-source SHORTEST AUGMENTING PATH
+ * finish whose search is a label-correcting (delta-stepping) relaxation that the device runs
+ * level-synchronously over the whole grid.  Used (i) as the CPU experiment that sized the device
+ * design -- dependent rounds and row scans per tail against the Gauss-Seidel tail's dependent
+ * bids -- and (ii) as the reference the device kernel's assignment is compared with.
+ *
+ * Same problem and state as auction_model.c (transportation form of CytoSPACE's expanded LAP,
+ * linear_assignment_solvers.py:63-66; the solve the reference reaches at
+ * linear_assignment_solvers.py:38).  Cs = (m - cmin) * (P+1).
+ *
+ * The SAP finish keeps the auction's invariant exactly.  Residual graph at the current eps:
+ *   person i (assigned to o_i) -> object k != o_i :  len = Cs[i,k] + lambda[k] + eps - (Cs[i,o_i] + lambda[o_i])  >= 0  (eps-CS)
+ *   free person i              -> object k        :  len = Cs[i,k] + lambda[k] - min_k'(Cs[i,k'] + lambda[k'])    >= 0
+ *   object o -> every person it holds             :  len = 0
+ * Labels d[o] are relaxed from all free persons at once; the search ends when no object with
+ * d[o] < D still has to be (re)scanned, D = the smallest label of an object with a free slot
+ * (multi-path mode: the D at which `want` source trees have reached distinct free objects).
+ * Then lambda[o] += D - d[o] for d[o] < D (prices only rise; every relaxed arc keeps len >= 0 and
+ * the tree arcs become tight), and the assignment is flipped along the tree path(s): the new pair
+ * (i, o) satisfies Cs[i,o] + lambda[o] + eps = (old value of i) i.e. eps-CS with slack eps.  Slot
+ * prices of touched objects become max(old, lambda[o]) and lambda[o] for the slots taken.
+ * Because a fixed point of the relaxation below D is all the proof needs, labels may be relaxed
+ * in any order: each round takes the `K` smallest labelled dirty objects' holders (rows) at once.
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define SAP_INF ((int64_t)1 << 60)
+#define GAP(b1, b2) (((b2) >= SAP_INF / 2) ? 0 : (b2) - (b1))
+
+/* per phase: [0] free at phase start, [1] auction rounds, [2] auction bids, [3] searches,
+ * [4] search rounds (dependent grid rounds), [5] rows scanned in searches, [6] paths applied,
+ * [7] free persons when the SAP finish took over */
+int64_t sap_phase_log[64][8];
+
+typedef struct { int64_t d; int32_t o; } lab_t;
+static int lab_cmp(const void *a, const void *b) {
+    const lab_t *x = (const lab_t *)a, *y = (const lab_t *)b;
+    if (x->d != y->d) return x->d < y->d ? -1 : 1;
+    return x->o < y->o ? -1 : (x->o > y->o);
+}
+
+/* stats: [0] phases, [1] auction rounds, [2] auction bids, [3] searches, [4] search rounds,
+ * [5] search row scans, [6] paths, [7] phase-start passes.
+ * sap_t: the SAP finish takes over when <= sap_t persons are free (0: never -> pure auction).
+ * K: rows relaxed per search round (target; whole objects are taken).
+ * multi: 0 = one augmenting path per search, m > 0 = a search continues until min(free, m)
+ * source trees have reached distinct free objects (all of them applied after one price update). */
+int sap_model_i32(int P, int O, const int32_t *m, int64_t ld, const int32_t *cap,
+                  int32_t *person_obj, int32_t *slot_owner, int64_t *lambda, int64_t *total,
+                  int64_t theta, int64_t eps0_div, int64_t sap_t, int64_t K, int64_t multi, int64_t *stats)
+{
+    if (P <= 0 || O <= 0) { if (total) *total = 0; return (P == 0) ? 0 : -1; }
+    const int64_t S = (int64_t)P + 1;
+    int32_t *soff = (int32_t *)malloc(sizeof(int32_t) * ((size_t)O + 1));
+    soff[0] = 0;
+    for (int o = 0; o < O; ++o) soff[o + 1] = soff[o] + (cap ? cap[o] : 1);
+    if (soff[O] != P) { free(soff); return -3; }
+    int32_t cmin = INT32_MAX, cmax = INT32_MIN;
+    for (int i = 0; i < P; ++i) {
+        const int32_t *r = m + (size_t)i * ld;
+        for (int o = 0; o < O; ++o) { if (r[o] < cmin) cmin = r[o]; if (r[o] > cmax) cmax = r[o]; }
+    }
+    int64_t *slot_price = (int64_t *)calloc((size_t)P, sizeof(int64_t));
+    int32_t *minslot = (int32_t *)malloc(sizeof(int32_t) * (size_t)O);
+    int32_t *person_slot = (int32_t *)malloc(sizeof(int32_t) * (size_t)P);
+    int32_t *freel = (int32_t *)malloc(sizeof(int32_t) * (size_t)P);
+    int32_t *nextl = (int32_t *)malloc(sizeof(int32_t) * (size_t)P);
+    int64_t *bidp = (int64_t *)malloc(sizeof(int64_t) * (size_t)O);
+    int32_t *bidr = (int32_t *)malloc(sizeof(int32_t) * (size_t)O);
+    int32_t *kobj = (int32_t *)malloc(sizeof(int32_t) * (size_t)P);
+    /* search state */
+    int64_t *d = (int64_t *)malloc(sizeof(int64_t) * (size_t)O);
+    int64_t *snap = (int64_t *)malloc(sizeof(int64_t) * (size_t)O);
+    int32_t *pred = (int32_t *)malloc(sizeof(int32_t) * (size_t)O);
+    int32_t *nfreeslot = (int32_t *)malloc(sizeof(int32_t) * (size_t)O);
+    lab_t *cand = (lab_t *)malloc(sizeof(lab_t) * (size_t)O);
+    int32_t *fo = (int32_t *)malloc(sizeof(int32_t) * (size_t)O);
+    int32_t *dirty = (int32_t *)malloc(sizeof(int32_t) * (size_t)O);
+    int32_t *front = (int32_t *)malloc(sizeof(int32_t) * (size_t)O);
+    int32_t *claim = (int32_t *)malloc(sizeof(int32_t) * (size_t)O);
+    int32_t *claim_src = (int32_t *)malloc(sizeof(int32_t) * (size_t)P);
+    int32_t *slot_obj = (int32_t *)malloc(sizeof(int32_t) * (size_t)P);
+    char *indirty = (char *)malloc((size_t)O);
+    char *touched = (char *)malloc((size_t)O);
+    for (int o = 0; o < O; ++o) for (int t = soff[o]; t < soff[o + 1]; ++t) slot_obj[t] = o;
+    for (int o = 0; o < O; ++o) { lambda[o] = (soff[o + 1] > soff[o]) ? 0 : SAP_INF; minslot[o] = soff[o]; bidr[o] = -1; }
+    for (int t = 0; t < P; ++t) slot_owner[t] = -1;
+    for (int i = 0; i < P; ++i) { person_obj[i] = -1; person_slot[i] = -1; }
+    int64_t st[8] = {0, 0, 0, 0, 0, 0, 0, 1};
+    int rc = 0;
+
+#define SCAN(i, b1, b2, o1)                                                        \
+    do {                                                                           \
+        const int32_t *r_ = m + (size_t)(i) * ld;                                  \
+        b1 = INT64_MAX; b2 = INT64_MAX; o1 = -1;                                   \
+        for (int o_ = 0; o_ < O; ++o_) {                                           \
+            int64_t h_ = (int64_t)(r_[o_] - cmin) * S + lambda[o_];                \
+            if (h_ < b1) { b2 = b1; b1 = h_; o1 = o_; }                            \
+            else if (h_ < b2) b2 = h_;                                             \
+        }                                                                          \
+    } while (0)
+#define REFRESH(o)                                                                 \
+    do {                                                                           \
+        int ms_ = soff[o]; int64_t mp_ = slot_price[ms_];                          \
+        for (int t_ = soff[o] + 1; t_ < soff[(o) + 1]; ++t_)                       \
+            if (slot_price[t_] < mp_) { mp_ = slot_price[t_]; ms_ = t_; }          \
+        minslot[o] = ms_; lambda[o] = mp_;                                         \
+    } while (0)
+
+    int64_t eps = ((int64_t)cmax - (int64_t)cmin) * S / (eps0_div > 0 ? eps0_div : 4);
+    if (eps < 1) eps = 1;
+    for (;;) {
+        ++st[0];
+        int nfree = 0;
+        if (st[0] == 1) {
+            for (int i = 0; i < P; ++i) freel[nfree++] = i;
+        } else {
+            ++st[7];
+            for (int i = 0; i < P; ++i) {
+                int64_t b1, b2; int o1;
+                SCAN(i, b1, b2, o1);
+                const int o = person_obj[i];
+                int drop = 1;
+                if (o >= 0) {
+                    const int64_t alt = (o1 == o) ? b2 : b1;
+                    const int64_t base = (int64_t)(m[(size_t)i * ld + o] - cmin) * S;
+                    if (alt >= SAP_INF / 2) drop = 0;
+                    else {
+                        drop = base + lambda[o] > alt + eps;
+                        if (!drop && base + slot_price[person_slot[i]] > alt + eps) slot_price[person_slot[i]] = alt + eps - base;
+                    }
+                }
+                if (drop) {
+                    if (o >= 0) slot_owner[person_slot[i]] = -1;
+                    person_obj[i] = -1; person_slot[i] = -1; freel[nfree++] = i;
+                }
+            }
+            for (int o = 0; o < O; ++o) if (soff[o + 1] > soff[o]) REFRESH(o);
+        }
+        const int ph = (int)st[0] - 1;
+        int64_t ph0[8]; memcpy(ph0, st, sizeof(st));
+        if (ph < 64) { memset(sap_phase_log[ph], 0, sizeof(sap_phase_log[ph])); sap_phase_log[ph][0] = nfree; }
+        while (nfree > 0) {
+            if (nfree <= sap_t) {
+                if (ph < 64 && sap_phase_log[ph][7] == 0) sap_phase_log[ph][7] = nfree;
+                /* ================= SAP finish: one search, one price update, >= 1 augmentation ============ */
+                ++st[3];
+                int nfo = 0;
+                for (int o = 0; o < O; ++o) {
+                    d[o] = SAP_INF; pred[o] = -1; nfreeslot[o] = 0; indirty[o] = 0;
+                    for (int t = soff[o]; t < soff[o + 1]; ++t) if (slot_owner[t] < 0) ++nfreeslot[o];
+                    if (nfreeslot[o] > 0) fo[nfo++] = o;
+                }
+                /* round 0: the free persons relax their rows (values relative to the row minimum); source k is
+                 * recorded as pred = P + k */
+                ++st[4];
+                for (int k = 0; k < nfree; ++k) {
+                    const int i = freel[k];
+                    int64_t b1, b2; int o1;
+                    SCAN(i, b1, b2, o1);
+                    (void)b2; (void)o1;
+                    const int32_t *r = m + (size_t)i * ld;
+                    for (int o = 0; o < O; ++o) {
+                        if (lambda[o] >= SAP_INF / 2) continue;
+                        const int64_t nd = (int64_t)(r[o] - cmin) * S + lambda[o] - b1;
+                        if (nd < d[o] || (nd == d[o] && P + k < pred[o])) { d[o] = nd; pred[o] = P + k; }
+                    }
+                    st[5] += 2;
+                }
+                int ndirty = 0;
+                for (int o = 0; o < O; ++o) if (d[o] < SAP_INF / 2) { dirty[ndirty++] = o; indirty[o] = 1; }
+                int want = nfree < nfo ? nfree : nfo;
+                if (multi <= 0) want = 1; else if (want > multi) want = (int)multi;
+                int64_t D = SAP_INF;
+                for (;;) {
+                    /* D = the want-th smallest label of an object with a free slot */
+                    int nc = 0;
+                    for (int q = 0; q < nfo; ++q) if (d[fo[q]] < SAP_INF / 2) { cand[nc].d = d[fo[q]]; cand[nc].o = fo[q]; ++nc; }
+                    qsort(cand, (size_t)nc, sizeof(lab_t), lab_cmp);
+                    D = nc >= want ? cand[want - 1].d : SAP_INF;
+                    /* dirty objects that still matter: label < D and somebody to scan */
+                    int nd2 = 0; int64_t dmin = INT64_MAX, dmax = INT64_MIN, wsum = 0;
+                    for (int q = 0; q < ndirty; ++q) {
+                        const int o = dirty[q];
+                        if (d[o] < D && (soff[o + 1] - soff[o]) - nfreeslot[o] > 0) {
+                            dirty[nd2++] = o;
+                            if (d[o] < dmin) dmin = d[o];
+                            if (d[o] > dmax) dmax = d[o];
+                            wsum += soff[o + 1] - soff[o];
+                        } else indirty[o] = 0;
+                    }
+                    ndirty = nd2;
+                    if (ndirty == 0) break;
+                    /* threshold: 256 power-of-two bins over [dmin, dmax], first bin where the cumulative slot count reaches K */
+                    int64_t T = dmax;
+                    if (wsum > K) {
+                        int sh = 0;
+                        while (((dmax - dmin) >> sh) >= 256) ++sh;
+                        int64_t hist[256]; memset(hist, 0, sizeof(hist));
+                        for (int q = 0; q < ndirty; ++q) hist[(d[dirty[q]] - dmin) >> sh] += soff[dirty[q] + 1] - soff[dirty[q]];
+                        int64_t cum = 0; int bsel = 255;
+                        for (int bb = 0; bb < 256; ++bb) { cum += hist[bb]; if (cum >= K) { bsel = bb; break; } }
+                        T = dmin + (((int64_t)bsel + 1) << sh) - 1;
+                    }
+                    ++st[4];
+                    memcpy(snap, d, sizeof(int64_t) * (size_t)O);
+                    int nkeep = 0, nfront = 0;
+                    for (int q = 0; q < ndirty; ++q) { const int o = dirty[q]; if (snap[o] <= T) front[nfront++] = o; else dirty[nkeep++] = o; }
+                    ndirty = nkeep;
+                    for (int q = 0; q < nfront; ++q) indirty[front[q]] = 0;
+                    int64_t rows = 0;
+                    for (int q = 0; q < nfront; ++q) {
+                        const int o = front[q];
+                        const int64_t dl = snap[o];
+                        for (int t = soff[o]; t < soff[o + 1]; ++t) {
+                            const int i = slot_owner[t];
+                            if (i < 0) continue;
+                            ++rows;
+                            const int32_t *r = m + (size_t)i * ld;
+                            const int64_t base = (int64_t)(r[o] - cmin) * S + lambda[o];
+                            for (int k = 0; k < O; ++k) {
+                                if (k == o || lambda[k] >= SAP_INF / 2) continue;
+                                const int64_t nd = dl + (int64_t)(r[k] - cmin) * S + lambda[k] + eps - base;
+                                if (nd < dl) { rc = -5; goto done; }          /* eps-CS violated: model bug */
+                                if (nd < snap[k] && (nd < d[k] || (nd == d[k] && t < pred[k]))) {
+                                    d[k] = nd; pred[k] = t;
+                                    if (!indirty[k]) { indirty[k] = 1; dirty[ndirty++] = k; }
+                                }
+                            }
+                        }
+                    }
+                    st[5] += rows;
+                }
+                if (D >= SAP_INF / 2) { rc = -6; goto done; }
+                /* candidates: free objects with label <= D by (label, object); rank = position */
+                int nc = 0;
+                for (int q = 0; q < nfo; ++q) if (d[fo[q]] <= D) { cand[nc].d = d[fo[q]]; cand[nc].o = fo[q]; ++nc; }
+                qsort(cand, (size_t)nc, sizeof(lab_t), lab_cmp);
+                if (nc > want) nc = want;
+                for (int o = 0; o < O; ++o) claim[o] = INT32_MAX;
+                for (int k = 0; k < nfree; ++k) claim_src[k] = INT32_MAX;
+                for (int c = 0; c < nc; ++c) {
+                    int o = cand[c].o, guard = 0;
+                    for (;;) {
+                        if (claim[o] > c) claim[o] = c;
+                        const int s = pred[o];
+                        if (s >= P) { if (claim_src[s - P] > c) claim_src[s - P] = c; break; }
+                        o = slot_obj[s];
+                        if (++guard > P) { rc = -7; goto done; }
+                    }
+                }
+                /* price update (before the flips: slot prices of the slots taken are the NEW object prices) */
+                for (int o = 0; o < O; ++o) {
+                    if (d[o] < D) {
+                        lambda[o] += D - d[o];
+                        for (int t = soff[o]; t < soff[o + 1]; ++t) if (slot_price[t] < lambda[o]) slot_price[t] = lambda[o];
+                        touched[o] = 1;
+                    } else touched[o] = 0;
+                }
+                int applied = 0;
+                for (int c = 0; c < nc; ++c) {
+                    int o = cand[c].o, ok = 1;
+                    for (;;) {
+                        if (claim[o] != c) { ok = 0; break; }
+                        const int s = pred[o];
+                        if (s >= P) { ok = claim_src[s - P] == c; break; }
+                        o = slot_obj[s];
+                    }
+                    if (!ok) continue;
+                    o = cand[c].o;
+                    int slot = -1;
+                    for (int t = soff[o]; t < soff[o + 1]; ++t) if (slot_owner[t] < 0) { slot = t; break; }
+                    for (;;) {
+                        const int s = pred[o];
+                        const int p = s >= P ? freel[s - P] : slot_owner[s];
+                        slot_owner[slot] = p; slot_price[slot] = lambda[o]; person_obj[p] = o; person_slot[p] = slot;
+                        touched[o] = 1;
+                        if (s >= P) break;
+                        o = slot_obj[s]; slot = s;
+                    }
+                    ++applied;
+                }
+                if (applied == 0) { rc = -8; goto done; }
+                st[6] += applied;
+                for (int o = 0; o < O; ++o) if (touched[o]) REFRESH(o);
+                {
+                    int nn = 0;
+                    for (int k = 0; k < nfree; ++k) { const int i = freel[k]; if (person_obj[i] < 0) nextl[nn++] = i; }
+                    int32_t *tmp = freel; freel = nextl; nextl = tmp; nfree = nn;
+                }
+                continue;
+            }
+            ++st[1]; st[2] += nfree;
+            for (int k = 0; k < nfree; ++k) {
+                const int i = freel[k];
+                int64_t b1, b2; int o1;
+                SCAN(i, b1, b2, o1);
+                const int64_t bp = lambda[o1] + GAP(b1, b2) + eps;
+                kobj[k] = o1;
+                if (bidr[o1] < 0 || bp > bidp[o1] || (bp == bidp[o1] && i < bidr[o1])) { bidp[o1] = bp; bidr[o1] = i; }
+            }
+            int nnext = 0;
+            for (int k = 0; k < nfree; ++k) {
+                const int i = freel[k], o = kobj[k];
+                if (bidr[o] == i) {
+                    const int t = minslot[o], old = slot_owner[t];
+                    slot_owner[t] = i; slot_price[t] = bidp[o]; person_obj[i] = o; person_slot[i] = t;
+                    if (old >= 0) { person_obj[old] = -1; person_slot[old] = -1; nextl[nnext++] = old; }
+                } else {
+                    nextl[nnext++] = i;
+                }
+            }
+            for (int k = 0; k < nfree; ++k) {
+                const int o = kobj[k];
+                if (bidr[o] >= 0) { REFRESH(o); bidr[o] = -1; }
+            }
+            int32_t *tmp = freel; freel = nextl; nextl = tmp; nfree = nnext;
+        }
+        if (ph < 64) for (int q = 1; q <= 6; ++q) sap_phase_log[ph][q] = st[q] - ph0[q];
+        if (eps == 1) break;
+        eps = eps / theta; if (eps < 1) eps = 1;
+    }
+done:;
+    int64_t tot = 0;
+    for (int i = 0; i < P; ++i) if (person_obj[i] >= 0) tot += m[(size_t)i * ld + person_obj[i]];
+    if (total) *total = tot;
+    if (stats) memcpy(stats, st, sizeof(st));
+    free(soff); free(slot_price); free(minslot); free(person_slot); free(freel); free(nextl);
+    free(bidp); free(bidr); free(kobj); free(d); free(snap); free(pred); free(nfreeslot);
+    free(cand); free(fo); free(dirty); free(front); free(claim); free(claim_src); free(slot_obj); free(indirty); free(touched);
+    return rc;
+}
