@@ -81,6 +81,14 @@
 
 #include "common.h"
 
+namespace cyb {
+int lap_solve_auction(const int32_t *cost_dev, int64_t ld, int64_t n_persons, int64_t n_objects,
+                      const int32_t *slot_offset_dev, int32_t *person_obj_dev, int32_t *slot_owner_dev,
+                      int64_t *price_dev, int64_t *total_dev, int64_t *stats_dev, void *workspace_dev,
+                      size_t workspace_bytes, int grid_hint, void *stream_v);
+size_t lap_auction_workspace_bytes(int64_t n_persons, int64_t n_objects);
+}  // namespace cyb
+
 namespace {
 
 constexpr int kThreads = 1024;
@@ -1324,16 +1332,18 @@ WsLayout ws_layout(int64_t np, int64_t no) {
 
 }  // namespace
 
-extern "C" size_t cyb_lap_workspace_bytes(int64_t n_persons, int64_t n_objects) {
+// (the exported cyb_lap_workspace_bytes / cyb_lap_solve_i32 live in lap_sap.cu; this is the round-1 solver,
+// reachable with CYB_LAP_SOLVER=auction for A/B measurements)
+size_t cyb::lap_auction_workspace_bytes(int64_t n_persons, int64_t n_objects) {
     if (n_persons <= 0 || n_objects <= 0) return 256;
     return ws_layout(n_persons, n_objects).total;
 }
 
-extern "C" int cyb_lap_solve_i32(const int32_t *cost_dev, int64_t ld, int64_t n_persons, int64_t n_objects,
-                                 const int32_t *slot_offset_dev, int32_t *person_obj_dev,
-                                 int32_t *slot_owner_dev, int64_t *price_dev, int64_t *total_dev,
-                                 int64_t *stats_dev, void *workspace_dev, size_t workspace_bytes,
-                                 int grid_hint, void *stream_v) {
+int cyb::lap_solve_auction(const int32_t *cost_dev, int64_t ld, int64_t n_persons, int64_t n_objects,
+                           const int32_t *slot_offset_dev, int32_t *person_obj_dev,
+                           int32_t *slot_owner_dev, int64_t *price_dev, int64_t *total_dev,
+                           int64_t *stats_dev, void *workspace_dev, size_t workspace_bytes,
+                           int grid_hint, void *stream_v) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
     const int64_t np = n_persons, no = n_objects;
     if (np <= 0 || np >= (1ll << kPersonBits) || no <= 0 || no > np)

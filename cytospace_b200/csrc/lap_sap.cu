@@ -1,0 +1,1179 @@
+// Exact dense linear assignment (transportation form) on sm_100a -- the solver behind
+// cyb_lap_solve_i32: eps-scaling auction rounds for the bulk of every phase, and a grid-wide
+// multi-source SHORTEST-AUGMENTING-PATH finish for the last free persons of the phase, all in ONE
+// persistent cooperative kernel (one CTA per SM).
+//
+// Replaces the third-party `lapjv.lapjv(cost)` call CytoSPACE makes at
+// cytospace/linear_assignment_solvers/linear_assignment_solvers.py:38 (from
+// cytospace/cytospace.py:329) on the expanded matrix `cost[location_repeat, :]`
+// (linear_assignment_solvers.py:63-66).  The expansion is never materialised: PERSONS are the
+// rows of the matrix, OBJECTS the columns, object o has cap[o] SLOTS:
+//     min sum_i M[i, obj(i)]   s.t.  object o holds exactly cap[o] persons.
+//
+// Auction part (unchanged from round 1; lap_auction.cu keeps the long description).
+// C = (M - cmin) * (P+1) >= 0; every slot has a price and a holder, the object's price lambda[o] is
+// its cheapest slot; a free person bids lambda[o*] + (w - v1) + eps for the cheapest slot of its
+// best object, the highest bid per object wins.  Invariant (eps-CS): for every assigned (i, o)
+//     C[i,o] + lambda[o] <= min_k (C[i,k] + lambda[k]) + eps,
+// lambda never decreases, eps is divided by theta per phase down to 1; with the factor P+1 on the
+// costs eps = 1 makes the integer total optimal (DESIGN.md has the proof).
+//
+// Why a different finish.  The last few free persons of a phase cost the auction thousands of
+// DEPENDENT single bids (an augmenting path traced one eviction at a time: measured 45.7k dependent
+// steps of ~0.9 us at 10k x 10k, 58-74 % of every solve).  A shortest-path search finds the same
+// augmenting paths breadth-first: a few dozen grid-wide rounds, each relaxing a few hundred rows in
+// parallel (bandwidth-shaped work), per search.  oracle/sap_model.c is the CPU model of exactly this
+// algorithm (the experiment that sized it, and the reference the tests compare assignments with).
+//
+// SAP finish (runs when <= sap_t persons are free), residual graph at the current eps:
+//   assigned person i (object o_i) -> object k != o_i : len = C[i,k]+lambda[k]+eps - (C[i,o_i]+lambda[o_i]) >= 0
+//   free person i                  -> object k        : len = C[i,k]+lambda[k] - min_k'(C[i,k']+lambda[k'])   >= 0
+//   object o -> every person it holds                 : len = 0
+// One search relaxes labels d[o] from ALL free persons at once (label-correcting, any order is
+// valid): round 0 = the free persons' rows; every further round takes the dirty objects (label
+// lowered since their holders last relaxed) with the smallest labels -- about K rows, chosen by a
+// 256-bin histogram threshold -- and relaxes their holders' rows with 64-bit atomicMin on
+// (label << 18 | entering slot).  D = the want-th smallest label of an object with a free slot;
+// the search ends when no dirty object has a label < D.  Then lambda[o] += D - d[o] for d[o] < D
+// (prices only rise, every relaxed arc keeps len >= 0, tree arcs become tight) and the assignment
+// is flipped along up to `want` vertex-disjoint tree paths (one warp traces each candidate, the
+// paths claim their objects with atomicMin(rank); a path is applied iff it owns all its claims --
+// the closest candidate always does).  A new pair (i, o) has C[i,o]+lambda[o]+eps = (old value of
+// i): eps-CS is kept exactly, so auction rounds and searches mix freely inside a phase.
+//
+// Determinism.  A relaxation only counts if it is STRICTLY below the label the object had when the
+// round started (shared-memory snapshot g[k] = lambda[k] - d[k]; without shared-memory prices: the
+// racy global label plus "equal labels only displace an entry written this round"), so the labels
+// and the (label, slot) minima do not depend on the interleaving; the lists built with atomics are
+// sets.  Same assignment for any grid size (tested against the CPU model).
+//
+// Shared memory per CTA (when it fits): 8 B per object -- the price lambda[o] during auction rounds,
+// g[o] during a search -- plus 4 B per slot (holder replica) and 4 B per object (tree predecessor).
+// HBM traffic: one row (O*4 bytes) per bid and per relaxed row; everything else is L2 / shared.
+//
+// Tuning knobs (environment, read at launch): CYB_LAP_SAP_T (free persons at which the search
+// takes over), CYB_LAP_SAP_K (rows per search round), CYB_LAP_SAP_MULTI (paths per search, <= 32),
+// CYB_LAP_THETA, CYB_LAP_EPS0, CYB_LAP_SMEM_PRICES=0 / CYB_LAP_SMEM_OWNER=0 (force the L2 paths),
+// CYB_LAP_SOLVER=auction (the round-1 solver, kept for A/B measurements).
+
+#include <algorithm>
+#include <climits>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <cstdio>
+
+#include "common.h"
+
+namespace cyb {
+// round-1 solver (lap_auction.cu)
+int lap_solve_auction(const int32_t *cost_dev, int64_t ld, int64_t n_persons, int64_t n_objects,
+                      const int32_t *slot_offset_dev, int32_t *person_obj_dev, int32_t *slot_owner_dev,
+                      int64_t *price_dev, int64_t *total_dev, int64_t *stats_dev, void *workspace_dev,
+                      size_t workspace_bytes, int grid_hint, void *stream_v);
+size_t lap_auction_workspace_bytes(int64_t n_persons, int64_t n_objects);
+}  // namespace cyb
+
+namespace {
+
+constexpr int kThreads = 1024;
+constexpr int kPB = 18;                                        // P < 2^18 - kSapMax
+constexpr unsigned long long kPM = (1ull << kPB) - 1;
+constexpr long long kInf = 1ll << 60;                          // price of an object without capacity / label "unreached"
+constexpr long long kGInf = 1ll << 61;                         // g of a priced-out object: never relaxed
+constexpr long long kBidLimit = 1ll << 45;                     // 46-bit bid / label field
+constexpr int kSapMax = 256;                                   // free persons a search can start from
+constexpr int kMultiMax = 32;                                  // augmenting paths per search (one warp each)
+constexpr int kRowsMax = 32;                                   // rows a CTA relaxes per chunk
+constexpr int kEPT = 4;                                        // dirty-list entries a thread caches in registers
+constexpr int kMaxSearch = 1 << 24;
+
+struct SapParams {
+    const int32_t *cost;
+    long long ld;
+    int P, O;
+    const int32_t *soff;     // slot offsets [O+1] (nullptr: every capacity is 1)
+    int32_t *person_obj, *slot_owner;
+    long long *lambda, *total, *stats;
+    long long *slot_price;
+    int32_t *person_slot, *minslot, *slot_obj;
+    int32_t *list[3];
+    int4 *rec[3];
+    unsigned long long *bidw[3];
+    int32_t *flag;
+    unsigned int *bar;
+    int *gmm;                // [0] cmin, [1] cmax, [2] status
+    // search state
+    unsigned long long *dkey;        // [O] (label << 18 | entering slot; sources are P + k), ~0 = unreached
+    int32_t *cstamp;                 // [O] round id of the last append to a dirty list
+    int32_t *chg[3];                 // dirty lists, rotating by round
+    int *nchg;                       // [3] their lengths
+    int32_t *claim;                  // [O + kSapMax] path claims (decreasing base per search)
+    int4 *moves;                     // [P] (person, object, slot, -) of the accepted paths
+    int *nmoves;                     // [1]
+    int32_t *srcdone;                // [kSapMax]
+    int qcap;
+    long long max_rounds;
+    int sap_t, sap_k, multi;
+    int theta, eps0_div;
+    int packed_reduce, prefetch;
+};
+
+struct Best {
+    long long b1, b2;
+    int j1;
+};
+
+__device__ __forceinline__ unsigned long long l2_policy_evict_first() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ int4 ld_stream(const int4 *p, unsigned long long pol) {
+    int4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.s32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ void prefetch_row_l2(const int32_t *r, int n) {
+    const unsigned bytes = ((unsigned)n * 4u) & ~15u;
+    const unsigned chunk = 8192u;
+    const unsigned off = threadIdx.x * chunk;
+    if (off < bytes && ((reinterpret_cast<uintptr_t>(r) & 15) == 0)) {
+        const unsigned len = min(chunk, bytes - off);
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const char *>(r) + off), "r"(len) : "memory");
+    }
+}
+__device__ __forceinline__ long long global_ns() {
+    long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void upd(Best &s, long long h, int j) {
+    if (h < s.b2) {
+        if (h < s.b1) { s.b2 = s.b1; s.b1 = h; s.j1 = j; }
+        else s.b2 = h;
+    }
+}
+__device__ __forceinline__ Best combine(const Best &a, const Best &b) {
+    const bool bwins = (b.b1 < a.b1) || (b.b1 == a.b1 && (unsigned)b.j1 < (unsigned)a.j1);
+    Best r;
+    if (bwins) { r.b1 = b.b1; r.j1 = b.j1; r.b2 = a.b1 < b.b2 ? a.b1 : b.b2; }
+    else       { r.b1 = a.b1; r.j1 = a.j1; r.b2 = b.b1 < a.b2 ? b.b1 : a.b2; }
+    return r;
+}
+// Grid barrier with a watchdog.  `abortf` is a global flag: a CTA that waits longer than 5 s (only a
+// protocol bug can do that) raises it, every other CTA leaves its wait when it sees it, and the kernel
+// returns CYB_ERR_NOT_CONVERGED instead of hanging the GPU.  Returns true when the launch is aborted.
+__device__ __forceinline__ bool spin_until(unsigned int *bar, unsigned int target, int *abortf, int line) {
+    unsigned int v, spins = 0;
+    long long t0 = 0;
+    bool dead = false;
+    for (;;) {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+        if ((int)(v - target) >= 0) break;
+        if ((++spins & 0x3FFu) == 0) {
+            int a;
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(a) : "l"(abortf) : "memory");
+            const long long now = global_ns();
+            if (!t0) t0 = now;
+            if (a != 0 || now - t0 > 5000000000ll) {
+                if (a == 0) printf("[cyb lap] CTA %d: wait at line %d timed out (counter %u, target %u)\n", blockIdx.x, line, v, target);
+                atomicExch(abortf, 1);
+                dead = true;
+                break;
+            }
+        }
+    }
+    return dead;
+}
+__device__ __forceinline__ bool grid_barrier(unsigned int *bar, unsigned int &target, unsigned int G, int *abortf, int line) {
+    __syncthreads();
+    bool dead = false;
+    if (threadIdx.x == 0) {
+        target += G;
+        __threadfence();
+        atomicAdd(bar, 1u);
+        dead = spin_until(bar, target, abortf, line);
+        __threadfence();
+    }
+    return __syncthreads_or(dead);
+}
+// Split grid barrier: every CTA `arrive`s once it has finished READING the labels of the round, and
+// `wait`s before its first atomic on them; the selection work in between hides the round trip.
+__device__ __forceinline__ void grid_arrive(unsigned int *bar, unsigned int &target, unsigned int G) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        target += G;
+        __threadfence();
+        atomicAdd(bar, 1u);
+    }
+}
+__device__ __forceinline__ bool grid_wait(unsigned int *bar, unsigned int target, int *abortf, int line) {
+    bool dead = false;
+    if (threadIdx.x == 0) {
+        dead = spin_until(bar, target, abortf, line);
+        __threadfence();
+    }
+    return __syncthreads_or(dead);
+}
+// Block-wide exclusive prefix count of `valid`; `total` = number of valid threads.
+__device__ __forceinline__ int block_excl_count(bool valid, int *wcnt, int &total) {
+    const unsigned m = __ballot_sync(0xffffffffu, valid);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int within = __popc(m & ((1u << lane) - 1u));
+    if (lane == 0) wcnt[w] = __popc(m);
+    __syncthreads();
+    const int c = wcnt[lane];
+    int inc = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += y;
+    }
+    const int woff = __shfl_sync(0xffffffffu, inc - c, w);
+    total = __shfl_sync(0xffffffffu, inc, 31);
+    __syncthreads();
+    return woff + within;
+}
+__device__ __forceinline__ unsigned long long warp_min64(unsigned long long key) {
+    const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+    const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
+    const unsigned mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xFFFFFFFFu);
+    return ((unsigned long long)mhi << 32) | mlo;
+}
+constexpr long long kPackMax = (1ll << 46) - 1;
+__device__ __forceinline__ unsigned long long pack_key(long long v, unsigned j) {
+    return ((unsigned long long)min(v, kPackMax) << kPB) | j;
+}
+__device__ __forceinline__ Best packed_reduce(unsigned long long k1, unsigned long long k2, long long *red_b1,
+                                              long long *red_b2) {
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const unsigned long long w1 = warp_min64(k1);
+    const unsigned long long w2 = warp_min64(k1 == w1 ? k2 : k1);
+    unsigned long long *rk1 = reinterpret_cast<unsigned long long *>(red_b1);
+    unsigned long long *rk2 = reinterpret_cast<unsigned long long *>(red_b2);
+    if (lane == 0) { rk1[w] = w1; rk2[w] = w2; }
+    __syncthreads();
+    Best s{LLONG_MAX, LLONG_MAX, -1};
+    if (w == 0) {
+        const unsigned long long q1 = rk1[lane], q2 = rk2[lane];
+        const unsigned long long W1 = warp_min64(q1);
+        const unsigned long long W2 = warp_min64(q1 == W1 ? q2 : q1);
+        const long long v1 = (long long)(W1 >> kPB), v2 = (long long)(W2 >> kPB);
+        s.j1 = W1 == ~0ull ? -1 : (int)(W1 & kPM);
+        s.b1 = (W1 == ~0ull) ? LLONG_MAX : (v1 == kPackMax ? kInf : v1);
+        s.b2 = (W2 == ~0ull) ? LLONG_MAX : (v2 == kPackMax ? kInf : v2);
+    }
+    __syncthreads();
+    return s;
+}
+
+// CTA-wide scan of one person's row: min / second-min / argmin of (c-cmin)*S + price[.]; valid in thread 0.
+template <bool SMEMP>
+__device__ __forceinline__ Best scan_row(const int32_t *__restrict__ r, int n, int cmin, int S,
+                                         const long long *__restrict__ price, bool vec_ok,
+                                         long long *red_b1, long long *red_b2, int *red_j, bool packed) {
+    Best s{LLONG_MAX, LLONG_MAX, -1};
+    const int t = threadIdx.x;
+    const unsigned long long pol = l2_policy_evict_first();
+    int jtail = 0;
+    if (vec_ok) {
+        const int4 *r4 = reinterpret_cast<const int4 *>(r);
+        const int n4 = n >> 2;
+#pragma unroll 4
+        for (int q = t; q < n4; q += kThreads) {
+            const int4 c = ld_stream(r4 + q, pol);
+            const int j = q << 2;
+            long long p0, p1, p2, p3;
+            if (SMEMP) {
+                const longlong2 a = *reinterpret_cast<const longlong2 *>(price + j);
+                const longlong2 b = *reinterpret_cast<const longlong2 *>(price + j + 2);
+                p0 = a.x; p1 = a.y; p2 = b.x; p3 = b.y;
+            } else {
+                const longlong2 a = __ldcg(reinterpret_cast<const longlong2 *>(price + j));
+                const longlong2 b = __ldcg(reinterpret_cast<const longlong2 *>(price + j + 2));
+                p0 = a.x; p1 = a.y; p2 = b.x; p3 = b.y;
+            }
+            upd(s, (long long)(c.x - cmin) * S + p0, j);
+            upd(s, (long long)(c.y - cmin) * S + p1, j + 1);
+            upd(s, (long long)(c.z - cmin) * S + p2, j + 2);
+            upd(s, (long long)(c.w - cmin) * S + p3, j + 3);
+        }
+        jtail = n4 << 2;
+    }
+    for (int j = jtail + t; j < n; j += kThreads) {
+        const long long p = SMEMP ? price[j] : __ldcg(price + j);
+        upd(s, (long long)(__ldg(r + j) - cmin) * S + p, j);
+    }
+    if (packed) {
+        const unsigned long long k1 = s.j1 >= 0 ? pack_key(s.b1, (unsigned)s.j1) : ~0ull;
+        const unsigned long long k2 = s.b2 != LLONG_MAX ? pack_key(s.b2, (unsigned)kPM) : ~0ull;
+        return packed_reduce(k1, k2, red_b1, red_b2);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        Best o;
+        o.b1 = __shfl_xor_sync(0xffffffffu, s.b1, d);
+        o.b2 = __shfl_xor_sync(0xffffffffu, s.b2, d);
+        o.j1 = __shfl_xor_sync(0xffffffffu, s.j1, d);
+        s = combine(s, o);
+    }
+    const int lane = t & 31, w = t >> 5;
+    if (lane == 0) { red_b1[w] = s.b1; red_b2[w] = s.b2; red_j[w] = s.j1; }
+    __syncthreads();
+    if (w == 0) {
+        s.b1 = red_b1[lane]; s.b2 = red_b2[lane]; s.j1 = red_j[lane];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            Best o;
+            o.b1 = __shfl_xor_sync(0xffffffffu, s.b1, d);
+            o.b2 = __shfl_xor_sync(0xffffffffu, s.b2, d);
+            o.j1 = __shfl_xor_sync(0xffffffffu, s.j1, d);
+            s = combine(s, o);
+        }
+    }
+    __syncthreads();
+    return s;
+}
+
+// Cheapest slot of object o (lowest slot index on ties) when slot `t_new` holds `p_new` and every
+// other slot its stored price.
+__device__ __forceinline__ void cheapest_slot(const SapParams &P, int o, int t_new, long long p_new, int &ms, long long &mp) {
+    const int s0 = P.soff ? __ldg(P.soff + o) : o;
+    const int s1 = P.soff ? __ldg(P.soff + o + 1) : o + 1;
+    ms = s0; mp = (s0 == t_new) ? p_new : __ldcg(P.slot_price + s0);
+#pragma unroll 4
+    for (int t = s0 + 1; t < s1; ++t) {
+        const long long p = (t == t_new) ? p_new : __ldcg(P.slot_price + t);
+        if (p < mp) { mp = p; ms = t; }
+    }
+}
+
+// SMEMP: prices (auction) / g (search) in shared memory.  SMEMO: slot-owner, tree-predecessor and
+// (capacitated) cheapest-slot replicas in shared memory.
+template <bool SMEMP, bool SMEMO>
+__global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int np = P.P, no = P.O;
+    size_t off = 0;
+    long long *sarr = reinterpret_cast<long long *>(smem_raw);
+    if (SMEMP) off += ((size_t)no * 8 + 15) / 16 * 16;
+    long long *myqd = reinterpret_cast<long long *>(smem_raw + off);   // [qcap] labels of this CTA's frontier objects
+    off += ((size_t)P.qcap * 8 + 15) / 16 * 16;
+    int *myq = reinterpret_cast<int *>(smem_raw + off);                // [qcap] work queue (persons / frontier objects)
+    off += ((size_t)P.qcap * 4 + 15) / 16 * 16;
+    unsigned *sfront = reinterpret_cast<unsigned *>(smem_raw + off);   // [(O+31)/32] frontier membership (L2-label tie rule)
+    off += ((size_t)((no + 31) / 32) * 4 + 15) / 16 * 16;
+    int *sowner = reinterpret_cast<int *>(smem_raw + off);             // SMEMO: [P]
+    int *spred = sowner + ((np + 3) & ~3);                             // SMEMO: [O]
+    int *sminslot = spred + ((no + 3) & ~3);                           // SMEMO && soff: [O]
+
+    __shared__ long long red_b1[32], red_b2[32];
+    __shared__ int red_j[32], wcnt[32];
+    __shared__ long long st_acc[12];   // bids, max bidders, -, small rounds, ns bid / barrier / replay / sap, relax hits, sap ns select, sap ns trace
+    __shared__ int ssrc[kSapMax], sfo[kSapMax];
+    __shared__ long long sfo_d[kSapMax];
+    __shared__ int hist[256];
+    __shared__ long long sh_ll[4];      // broadcast slots: [0] D, [1] dmin, [2] dmax, [3] T
+    __shared__ int sh_i[8];             // [0] wsum, [1] count, [2] nfront, [3] status, [4] n moves
+    __shared__ int rw_person[kRowsMax], rw_slot[kRowsMax];
+    __shared__ long long rw_thr[kRowsMax];
+    __shared__ int pth_ok[kMultiMax], pth_len[kMultiMax], pth_obj[kMultiMax];
+
+    const int G = gridDim.x, b = blockIdx.x, t = threadIdx.x;
+    const int lane = t & 31, warp = t >> 5;
+    const int S = np + 1;
+    const bool vec_ok = ((P.ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(P.cost) & 15) == 0);
+    unsigned int bar_target = 0, bar2_target = 0;
+    // a wait that timed out: the launch is given up (status only; the outputs are undefined)
+#define LAP_ABORT() do { if (threadIdx.x == 0) P.stats[0] = CYB_ERR_NOT_CONVERGED; return; } while (0)
+#define GRID_BARRIER() do { if (grid_barrier(P.bar, bar_target, G, P.gmm + 5, __LINE__)) LAP_ABORT(); } while (0)
+    const long long *price_rd = SMEMP ? sarr : P.lambda;
+    const bool capd = P.soff != nullptr;
+
+    auto rowptr = [&](int i) -> const int32_t * { return P.cost + (long long)i * P.ld; };
+    auto capacity = [&](int o) -> int { return capd ? __ldg(P.soff + o + 1) - __ldg(P.soff + o) : 1; };
+    auto owner_of = [&](int slot) -> int { return SMEMO ? sowner[slot] : __ldcg(P.slot_owner + slot); };
+    auto obj_of_slot = [&](int slot) -> int { return capd ? __ldcg(P.slot_obj + slot) : slot; };
+
+    // ---- pass 0: state init and the cost range ------------------------------
+    {
+        int lmin = INT_MAX, lmax = INT_MIN;
+        for (int i = b; i < np; i += G) {
+            const int32_t *r = rowptr(i);
+            for (int j = t; j < no; j += kThreads) {
+                const int c = __ldg(r + j);
+                lmin = min(lmin, c); lmax = max(lmax, c);
+            }
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            lmin = min(lmin, __shfl_xor_sync(0xffffffffu, lmin, d));
+            lmax = max(lmax, __shfl_xor_sync(0xffffffffu, lmax, d));
+        }
+        if (lane == 0 && lmin <= lmax) { atomicMin(P.gmm + 0, lmin); atomicMax(P.gmm + 1, lmax); }
+        for (int i = b * kThreads + t; i < np; i += G * kThreads) {
+            P.slot_price[i] = 0; P.slot_owner[i] = -1; P.person_obj[i] = -1; P.person_slot[i] = -1;
+        }
+        for (int o = b * kThreads + t; o < no; o += G * kThreads) {
+            P.lambda[o] = capacity(o) > 0 ? 0 : kInf;          // a spot that takes no cell is priced out
+            P.minslot[o] = capd ? __ldg(P.soff + o) : o;
+            P.bidw[0][o] = 0ull; P.bidw[1][o] = 0ull; P.bidw[2][o] = 0ull;
+            P.cstamp[o] = 0;
+            if (capd) for (int s = __ldg(P.soff + o); s < __ldg(P.soff + o + 1); ++s) P.slot_obj[s] = o;
+        }
+        for (int o = b * kThreads + t; o < no + kSapMax; o += G * kThreads) P.claim[o] = INT_MAX;
+        if (SMEMP) for (int o = t; o < no; o += kThreads) sarr[o] = capacity(o) > 0 ? 0 : kInf;
+        if (SMEMO) {
+            for (int k = t; k < np; k += kThreads) sowner[k] = -1;
+            if (capd) for (int o = t; o < no; o += kThreads) sminslot[o] = __ldg(P.soff + o);
+        }
+        for (int w = t; w < (no + 31) / 32; w += kThreads) sfront[w] = 0u;
+    }
+    GRID_BARRIER();
+    const int cmin = __ldcg(P.gmm + 0), cmax = __ldcg(P.gmm + 1);
+    long long eps = ((long long)cmax - (long long)cmin) * S / P.eps0_div;
+    if (eps < 1) eps = 1;
+
+    int rounds = 0, phases = 0, searches = 0, srounds = 0, paths = 0, rid = 0;
+    long long srows = 0;
+    if (t < 12) st_acc[t] = 0;
+    __syncthreads();
+    int status = 0;
+    // the input contract is |cost| < 2^30; a wider range would overflow the 32-bit (c - cmin)
+    if ((long long)cmax - (long long)cmin >= (1ll << 31) - 1 || cmin <= -(1 << 30) || cmax >= (1 << 30)) status = CYB_ERR_OVERFLOW;
+    int cur = 0, prevF = 0;
+    const bool packed = ((long long)cmax - (long long)cmin + 1) * S < (1ll << 45) && P.packed_reduce;
+    auto scan = [&](const int32_t *r) -> Best {
+        return scan_row<SMEMP>(r, no, cmin, S, price_rd, vec_ok, red_b1, red_b2, red_j, packed);
+    };
+    const int sap_t = min(P.sap_t, kSapMax);
+
+    while (!status) {
+        ++phases;
+        // ---- phase start: which pairs survive eps-CS at the new eps? --------
+        if (phases > 1) {
+            for (int i = b; i < np; i += G) {
+                const int o = __ldcg(P.person_obj + i);
+                int f = 1;
+                if (i + G < np && P.prefetch) prefetch_row_l2(rowptr(i + G), no);
+                if (o >= 0) {
+                    const int32_t *r = rowptr(i);
+                    const Best s = scan(r);
+                    if (t == 0) {
+                        const long long alt = (s.j1 == o) ? s.b2 : s.b1;
+                        const long long base = (long long)(__ldg(r + o) - cmin) * S;
+                        const long long lam = SMEMP ? sarr[o] : __ldcg(P.lambda + o);
+                        const int ps = __ldcg(P.person_slot + i);
+                        f = 0;
+                        if (alt < kInf / 2) {
+                            if (base + lam > alt + eps) f = ps + 2;                       // drop: vacate slot ps
+                            else if (base + __ldcg(P.slot_price + ps) > alt + eps)
+                                P.slot_price[ps] = alt + eps - base;                      // clamp (>= lambda[o])
+                        }
+                    }
+                }
+                if (t == 0) P.flag[i] = f;
+            }
+            GRID_BARRIER();
+        }
+        int F = 0;
+        for (int i0 = 0; i0 < np; i0 += kThreads) {
+            const int i = i0 + t;
+            const int f = (i < np) ? (phases == 1 ? 1 : __ldcg(P.flag + i)) : 0;
+            if (f >= 2) {
+                if (i % G == b || !SMEMO) P.slot_owner[f - 2] = -1;      // the slot keeps its price
+                if (SMEMO) sowner[f - 2] = -1;
+                if (i % G == b) { P.person_obj[i] = -1; P.person_slot[i] = -1; }
+            }
+            int tot;
+            const int pos = F + block_excl_count(f != 0, wcnt, tot);
+            if (f != 0 && pos % G == b) { P.list[cur][pos] = i; myq[pos / G] = i; }
+            F += tot;
+        }
+        if (phases > 1 && capd) {
+            // clamps / searches may have left an equally cheap slot with a lower index: refresh the argmin
+            for (int o = t; o < no; o += kThreads) {
+                if (capacity(o) > 1) {
+                    int ms; long long mp;
+                    cheapest_slot(P, o, -1, 0, ms, mp);
+                    if (o % G == b || !SMEMO) P.minslot[o] = ms;
+                    if (SMEMO) sminslot[o] = ms;
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- bidding rounds (more than sap_t persons free) -------------------
+        while (F > sap_t) {
+            if (++rounds > P.max_rounds) { status = CYB_ERR_NOT_CONVERGED; break; }
+            if (t == 0) { st_acc[0] += F; if (F > st_acc[1]) st_acc[1] = F; }
+            const bool timed = (b == 0 && t == 0 && F <= G);
+            const long long tm0 = timed ? global_ns() : 0;
+            const int myn = F > b ? (F - b - 1) / G + 1 : 0;
+            if (myn > 0 && P.prefetch) prefetch_row_l2(rowptr(myq[0]), no);
+            for (int q = 0; q < myn; ++q) {
+                const int i = myq[q];
+                if (q + 1 < myn && P.prefetch) prefetch_row_l2(rowptr(myq[q + 1]), no);
+                const Best s = scan(rowptr(i));
+                if (t == 0) {
+                    const int o = s.j1;
+                    const long long lam = SMEMP ? sarr[o] : __ldcg(P.lambda + o);
+                    const long long bid = lam + (s.b2 < kInf / 2 ? s.b2 - s.b1 : 0) + eps;
+                    if (bid >= kBidLimit) atomicExch(P.gmm + 2, CYB_ERR_OVERFLOW);
+                    const int slot = capd ? (SMEMO ? sminslot[o] : __ldcg(P.minslot + o)) : o;
+                    const int prev = owner_of(slot);
+                    P.rec[cur][q * G + b] = make_int4(o, slot, prev, 0);
+                    atomicMax(P.bidw[cur] + o, ((unsigned long long)bid << kPB) | (kPM - (unsigned long long)i));
+                }
+            }
+            const long long tm1 = timed ? global_ns() : 0;
+            GRID_BARRIER();
+            const long long tm2 = timed ? global_ns() : 0;
+            // ---- resolve: every CTA replays every record ----------------------
+            status = __ldcg(P.gmm + 2);
+            const int nxt = cur == 2 ? 0 : cur + 1, prv = cur == 0 ? 2 : cur - 1;
+            for (int k = b * kThreads + t; k < prevF; k += G * kThreads)
+                P.bidw[prv][__ldcg(&P.rec[prv][k].x)] = 0ull;
+            int Fn = 0;
+            for (int k0 = 0; k0 < F; k0 += kThreads) {
+                const int k = k0 + t;
+                int entry = -1;
+                if (k < F) {
+                    const int i = __ldcg(P.list[cur] + k);
+                    const int4 rc = __ldcg(P.rec[cur] + k);
+                    const unsigned long long key = __ldcg(P.bidw[cur] + rc.x);
+                    const int wperson = (int)(kPM - (key & kPM));
+                    if (wperson == i) {
+                        const long long bid = (long long)(key >> kPB);
+                        const bool mine = (k % G == b);
+                        int ms; long long mp;
+                        // sibling slot prices FIRST (loads before the stores to the same line, see lap_auction.cu)
+                        cheapest_slot(P, rc.x, rc.y, bid, ms, mp);
+                        if (mine || !SMEMO) {
+                            P.slot_owner[rc.y] = i;
+                            if (capd) P.minslot[rc.x] = ms;
+                        }
+                        if (mine) P.slot_price[rc.y] = bid;
+                        if (SMEMO) { sowner[rc.y] = i; if (capd) sminslot[rc.x] = ms; }
+                        if (SMEMP) { sarr[rc.x] = mp; if (mine) P.lambda[rc.x] = mp; }
+                        else P.lambda[rc.x] = mp;
+                        if (mine) {
+                            P.person_obj[i] = rc.x; P.person_slot[i] = rc.y;
+                            if (rc.z >= 0) { P.person_obj[rc.z] = -1; P.person_slot[rc.z] = -1; }
+                        }
+                        entry = rc.z;
+                    } else {
+                        entry = i;
+                    }
+                }
+                int tot;
+                const int pos = Fn + block_excl_count(entry >= 0, wcnt, tot);
+                if (entry >= 0 && pos % G == b) { P.list[nxt][pos] = entry; myq[pos / G] = entry; }
+                Fn += tot;
+            }
+            prevF = F;
+            F = Fn;
+            cur = nxt;
+            __syncthreads();
+            if (timed) { st_acc[4] += tm1 - tm0; st_acc[5] += tm2 - tm1; st_acc[6] += global_ns() - tm2; ++st_acc[3]; }
+            if (status) break;
+        }
+        if (status) break;
+        GRID_BARRIER();        // state of the last resolve becomes visible
+        {
+            const int prv = cur == 0 ? 2 : cur - 1;
+            for (int k = b * kThreads + t; k < prevF; k += G * kThreads)
+                P.bidw[prv][__ldcg(&P.rec[prv][k].x)] = 0ull;
+            prevF = 0;
+        }
+
+        // ---- shortest-augmenting-path finish -------------------------------------
+        const long long ts0 = (b == 0 && t == 0) ? global_ns() : 0;
+        if (F > 0) {
+            if (t < F) ssrc[t] = __ldcg(P.list[cur] + t);
+            __syncthreads();
+        }
+        while (F > 0) {
+            ++searches;
+            if (searches >= kMaxSearch) { status = CYB_ERR_NOT_CONVERGED; break; }
+            const int cbase = (kMaxSearch - searches) * kMultiMax;
+            // S0: labels unreached, lists empty; shared memory switches from prices to g = lambda - d
+            for (int o = b * kThreads + t; o < no; o += G * kThreads) P.dkey[o] = ~0ull;
+            if (b == 0 && t < 3) P.nchg[t] = 0;
+            if (SMEMP) for (int o = t; o < no; o += kThreads) { const long long l = sarr[o]; sarr[o] = l >= kInf / 2 ? kGInf : l - kInf; }
+            GRID_BARRIER();
+            // (every CTA has finished applying the previous search's moves: their buffers can be reset)
+            if (b == 0 && t == 0) P.nmoves[0] = 0;
+            if (b == 0 && t < kSapMax) P.srcdone[t] = 0;
+            // objects with a free slot, in increasing order (every CTA builds the same list)
+            int nfo = 0;
+            for (int o0 = 0; o0 < no; o0 += kThreads) {
+                const int o = o0 + t;
+                bool fr = false;
+                if (o < no) {
+                    if (!capd) fr = owner_of(o) < 0;
+                    else for (int s = __ldg(P.soff + o); s < __ldg(P.soff + o + 1); ++s) fr = fr || owner_of(s) < 0;
+                }
+                int tot;
+                const int pos = nfo + block_excl_count(fr, wcnt, tot);
+                if (fr && pos < kSapMax) sfo[pos] = o;
+                nfo += tot;
+            }
+            if (nfo > kSapMax || nfo < 1) { status = CYB_ERR_NOT_CONVERGED; break; }     // cannot happen: free slots == free persons
+            const int want = min(min(F, nfo), P.multi);
+            __syncthreads();
+            // S1: round 0 -- the free persons relax their rows, values relative to the row minimum
+            ++rid; ++srounds;
+            for (int k = b; k < F; k += G) {
+                const int i = ssrc[k];
+                const int32_t *r = rowptr(i);
+                // over C + g (g = lambda - 2^60: a common shift; negative, hence the unpacked reduction)
+                const Best s = scan_row<SMEMP>(r, no, cmin, S, price_rd, vec_ok, red_b1, red_b2, red_j, false);
+                if (t == 0) sh_ll[0] = s.b1;
+                __syncthreads();
+                const long long b1 = sh_ll[0];
+                const unsigned long long src = (unsigned long long)(np + k);
+                for (int j = t; j < no; j += kThreads) {
+                    const long long p = SMEMP ? sarr[j] : __ldcg(P.lambda + j);
+                    if (p >= kInf / 2) continue;                      // priced out (kGInf in g form as well)
+                    const long long nd = (long long)(__ldg(r + j) - cmin) * S + p - b1;
+                    if (nd >= kBidLimit) { atomicExch(P.gmm + 2, CYB_ERR_OVERFLOW); continue; }
+                    const unsigned long long key = ((unsigned long long)nd << kPB) | src;
+                    if (key < __ldcg(P.dkey + j)) atomicMin(P.dkey + j, key);
+                }
+                srows += 2;
+                __syncthreads();
+            }
+            GRID_BARRIER();
+            // S2: search rounds.  The dirty list of round r is chg[r % 3] (round 1: every object).
+            long long D = kInf;
+            int lr = 0;
+            bool implicit = true;
+            for (;;) {
+                ++rid;
+                const long long tq0 = (b == 0 && t == 0) ? global_ns() : 0;
+                const int lnext = lr == 2 ? 0 : lr + 1, lclear = lr == 0 ? 2 : lr - 1;
+                const int n = implicit ? no : __ldcg(P.nchg + lr);
+                const int32_t *L = P.chg[lr];
+                if (b == 0 && t == 0 && !implicit) P.nchg[lclear] = 0;      // read in the previous round, appended to in the next
+                // D = the want-th smallest label of an object with a free slot
+                if (t < nfo) { const unsigned long long key = __ldcg(P.dkey + sfo[t]); sfo_d[t] = key == ~0ull ? kInf : (long long)(key >> kPB); }
+                if (t == 0) { sh_ll[0] = kInf; sh_ll[1] = LLONG_MAX; sh_ll[2] = 0; sh_i[0] = 0; sh_i[1] = 0; }
+                if (t < 256) hist[t] = 0;
+                for (int w = t; w < (no + 31) / 32; w += kThreads) sfront[w] = 0u;
+                __syncthreads();
+                if (t < nfo) {
+                    const long long dm = sfo_d[t];
+                    int rank = 0;
+                    for (int u = 0; u < nfo; ++u) { const long long du = sfo_d[u]; rank += (du < dm || (du == dm && u < t)) ? 1 : 0; }
+                    if (rank == want - 1) sh_ll[0] = dm;
+                }
+                __syncthreads();
+                D = sh_ll[0];
+                // pass A: fetch entries, refresh the replicas, eligibility, label range
+                auto fetch = [&](int e, int &o, long long &d) -> bool {
+                    o = implicit ? e : __ldcg(L + e);
+                    const unsigned long long key = __ldcg(P.dkey + o);
+                    d = key == ~0ull ? kInf : (long long)(key >> kPB);
+                    if (key != ~0ull) {
+                        if (SMEMP) { const long long lam = __ldcg(P.lambda + o); sarr[o] = lam >= kInf / 2 ? kGInf : lam - d; }
+                        if (SMEMO) spred[o] = (int)(key & kPM);
+                    }
+                    if (!(d < D)) return false;
+                    if (!capd) return owner_of(o) >= 0;
+                    bool held = false;
+                    for (int s = __ldg(P.soff + o); s < __ldg(P.soff + o + 1); ++s) held = held || owner_of(s) >= 0;
+                    return held;
+                };
+                int eo[kEPT]; long long ed[kEPT]; bool ee[kEPT];
+                long long lmin = LLONG_MAX, lmax = LLONG_MIN; int lw = 0, lc = 0;
+#pragma unroll
+                for (int j = 0; j < kEPT; ++j) {
+                    const int e = t + j * kThreads;
+                    ee[j] = false; eo[j] = 0; ed[j] = 0;
+                    if (e < n) {
+                        ee[j] = fetch(e, eo[j], ed[j]);
+                        if (ee[j]) { lmin = min(lmin, ed[j]); lmax = max(lmax, ed[j]); lw += capacity(eo[j]); ++lc; }
+                    }
+                }
+                for (int e = t + kEPT * kThreads; e < n; e += kThreads) {
+                    int o; long long d;
+                    if (fetch(e, o, d)) { lmin = min(lmin, d); lmax = max(lmax, d); lw += capacity(o); ++lc; }
+                }
+#pragma unroll
+                for (int dd = 16; dd > 0; dd >>= 1) {
+                    lmin = min(lmin, __shfl_xor_sync(0xffffffffu, lmin, dd));
+                    lmax = max(lmax, __shfl_xor_sync(0xffffffffu, lmax, dd));
+                    lw += __shfl_xor_sync(0xffffffffu, lw, dd);
+                    lc += __shfl_xor_sync(0xffffffffu, lc, dd);
+                }
+                if (lane == 0 && lc > 0) {
+                    atomicMin(reinterpret_cast<unsigned long long *>(&sh_ll[1]), (unsigned long long)lmin);     // labels are >= 0
+                    atomicMax(reinterpret_cast<unsigned long long *>(&sh_ll[2]), (unsigned long long)lmax);
+                    atomicAdd(&sh_i[0], lw); atomicAdd(&sh_i[1], lc);
+                }
+                __syncthreads();
+                const int nelig = sh_i[1];
+                if (nelig == 0) break;                                  // fixed point below D: the search is over
+                if (++srounds + rounds > P.max_rounds) { status = CYB_ERR_NOT_CONVERGED; break; }
+                // Other CTAs must not lower labels while this one still reads them: arrive as soon as the
+                // reads are done (entries cached in registers: now; otherwise after the last pass).
+                const bool cached = n <= kEPT * kThreads;
+                if (cached) grid_arrive(P.bar + 1, bar2_target, G);
+                const long long dmin = sh_ll[1], dmax = sh_ll[2];
+                long long T = dmax;
+                if (sh_i[0] > P.sap_k) {
+                    // 256 power-of-two bins over [dmin, dmax]: first bin where the cumulative slot count reaches K
+                    int sh = 0;
+                    while (((dmax - dmin) >> sh) >= 256) ++sh;
+#pragma unroll
+                    for (int j = 0; j < kEPT; ++j) if (ee[j]) atomicAdd(&hist[(int)((ed[j] - dmin) >> sh)], capacity(eo[j]));
+                    for (int e = t + kEPT * kThreads; e < n; e += kThreads) {
+                        int o; long long d;
+                        if (fetch(e, o, d)) atomicAdd(&hist[(int)((d - dmin) >> sh)], capacity(o));
+                    }
+                    __syncthreads();
+                    if (warp == 0) {
+                        int c8[8], sum = 0;
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) { c8[q] = hist[lane * 8 + q]; sum += c8[q]; }
+                        int inc = sum;
+#pragma unroll
+                        for (int dd = 1; dd < 32; dd <<= 1) { const int y = __shfl_up_sync(0xffffffffu, inc, dd); if (lane >= dd) inc += y; }
+                        int run = inc - sum, bsel = INT_MAX;
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) { run += c8[q]; if (run >= P.sap_k && bsel == INT_MAX) bsel = lane * 8 + q; }
+                        bsel = __reduce_min_sync(0xffffffffu, (unsigned)bsel);
+                        if (bsel == INT_MAX) bsel = 255;
+                        if (lane == 0) sh_ll[3] = dmin + (((long long)bsel + 1) << sh) - 1;
+                    }
+                    __syncthreads();
+                    T = sh_ll[3];
+                }
+                // pass C: the frontier (label <= T), dealt to the CTAs by rank; the rest is carried over
+                int nfront = 0, myn = 0;
+                auto passC = [&](int e, bool el, int o, long long d, int base_e) {
+                    (void)base_e;
+                    const bool fr = el && d <= T;
+                    if (el && !fr && (e % G == b)) {
+                        if (atomicMax(P.cstamp + o, rid) < rid) P.chg[lnext][atomicAdd(P.nchg + lnext, 1)] = o;
+                    }
+                    if (fr && !SMEMP) atomicOr(&sfront[o >> 5], 1u << (o & 31));
+                    int tot;
+                    const int pos = nfront + block_excl_count(fr, wcnt, tot);
+                    if (fr && pos % G == b) { myq[pos / G] = o; myqd[pos / G] = d; }
+                    nfront += tot;
+                };
+#pragma unroll
+                for (int j = 0; j < kEPT; ++j) {
+                    if (j * kThreads < n) passC(t + j * kThreads, ee[j], eo[j], ed[j], j);
+                }
+                for (int e0 = kEPT * kThreads; e0 < n; e0 += kThreads) {
+                    const int e = e0 + t;
+                    int o = 0; long long d = 0;
+                    const bool el = e < n ? fetch(e, o, d) : false;
+                    passC(e, el, o, d, 0);
+                }
+                myn = nfront > b ? (nfront - b - 1) / G + 1 : 0;
+                if (!cached) grid_arrive(P.bar + 1, bar2_target, G);
+                __syncthreads();
+                const long long tq1 = (b == 0 && t == 0) ? global_ns() : 0;
+                // relax: the holders of this CTA's frontier objects, kRowsMax rows at a time
+                int qi = 0, si = 0;          // next frontier object of this CTA, next slot inside it
+                bool waited = false;
+                while (qi < myn) {
+                    __syncthreads();
+                    if (t == 0) {
+                        // the next <= kRowsMax slots of the queue (holders are looked up in parallel below)
+                        int nr = 0;
+                        while (qi < myn && nr < kRowsMax) {
+                            const int o = myq[qi];
+                            const int s0 = capd ? __ldg(P.soff + o) : o, s1 = capd ? __ldg(P.soff + o + 1) : o + 1;
+                            int s = s0 + si;
+                            for (; s < s1 && nr < kRowsMax; ++s) { rw_slot[nr] = s; rw_person[nr] = qi; ++nr; }
+                            if (s >= s1) { ++qi; si = 0; } else si = s - s0;
+                        }
+                        sh_i[5] = nr; sh_i[6] = qi; sh_i[7] = si;
+                    }
+                    __syncthreads();
+                    const int nr = sh_i[5];
+                    qi = sh_i[6]; si = sh_i[7];
+                    if (t < nr) {
+                        // thr = C[i,o] + lambda[o] - d[o] - eps;  a relaxation of k gives  nd = C[i,k] + lambda[k] - thr
+                        const int q = rw_person[t], o = myq[q];
+                        const int i = owner_of(rw_slot[t]);
+                        long long thr = 0;
+                        if (i >= 0) {
+                            const long long lam_minus_d = SMEMP ? sarr[o] : __ldcg(P.lambda + o) - myqd[q];
+                            thr = (long long)(__ldg(rowptr(i) + o) - cmin) * S + lam_minus_d - eps;
+                        }
+                        rw_thr[t] = thr;
+                        rw_person[t] = i;            // (this thread's own entry: the queue index is no longer needed)
+                    }
+                    if (!waited) { if (grid_wait(P.bar + 1, bar2_target, P.gmm + 5, __LINE__)) LAP_ABORT(); waited = true; }     // includes a __syncthreads
+                    else __syncthreads();
+                    const unsigned long long pol = l2_policy_evict_first();
+                    for (int rr = 0; rr < nr; ++rr) {
+                        if (rw_person[rr] < 0) continue;                 // empty slot
+                        ++srows;
+                        const int32_t *r = rowptr(rw_person[rr]);
+                        const long long thr = rw_thr[rr];
+                        const unsigned long long slot = (unsigned long long)rw_slot[rr];
+                        auto relax = [&](int k, int c, long long gk_or_lam, unsigned long long curkey) {
+                            if (SMEMP) {
+                                // g form: strictly below the label of the round start
+                                const long long v = (long long)(c - cmin) * S;
+                                if (v + gk_or_lam < thr) {
+                                    const long long nd = v + __ldcg(P.lambda + k) - thr;
+                                    if (nd >= kBidLimit) { atomicExch(P.gmm + 2, CYB_ERR_OVERFLOW); return; }
+                                    const unsigned long long key = ((unsigned long long)nd << kPB) | slot;
+                                    const unsigned long long prev = atomicMin(P.dkey + k, key);
+                                    if (key < prev && atomicMax(P.cstamp + k, rid) < rid) P.chg[lnext][atomicAdd(P.nchg + lnext, 1)] = k;
+                                }
+                            } else {
+                                if (gk_or_lam >= kInf / 2) return;
+                                const long long nd = (long long)(c - cmin) * S + gk_or_lam - thr;
+                                const long long rd = curkey == ~0ull ? kInf : (long long)(curkey >> kPB);
+                                bool go = nd < rd;
+                                if (!go && nd == rd) {
+                                    // equal labels only displace an entry written in THIS round (its writer is in the frontier)
+                                    const int ps = (int)(curkey & kPM);
+                                    if (ps < np) { const int po = obj_of_slot(ps); go = (sfront[po >> 5] >> (po & 31)) & 1u; }
+                                }
+                                if (go) {
+                                    if (nd >= kBidLimit) { atomicExch(P.gmm + 2, CYB_ERR_OVERFLOW); return; }
+                                    const unsigned long long key = ((unsigned long long)nd << kPB) | slot;
+                                    const unsigned long long prev = atomicMin(P.dkey + k, key);
+                                    if (key < prev && atomicMax(P.cstamp + k, rid) < rid) P.chg[lnext][atomicAdd(P.nchg + lnext, 1)] = k;
+                                }
+                            }
+                        };
+                        int jtail = 0;
+                        if (vec_ok) {
+                            const int4 *r4 = reinterpret_cast<const int4 *>(r);
+                            const int n4 = no >> 2;
+#pragma unroll 4
+                            for (int q = t; q < n4; q += kThreads) {
+                                const int4 c = ld_stream(r4 + q, pol);
+                                const int j = q << 2;
+                                if (SMEMP) {
+                                    const longlong2 a = *reinterpret_cast<const longlong2 *>(sarr + j);
+                                    const longlong2 bb = *reinterpret_cast<const longlong2 *>(sarr + j + 2);
+                                    relax(j, c.x, a.x, 0); relax(j + 1, c.y, a.y, 0); relax(j + 2, c.z, bb.x, 0); relax(j + 3, c.w, bb.y, 0);
+                                } else {
+                                    const longlong2 a = __ldcg(reinterpret_cast<const longlong2 *>(P.lambda + j));
+                                    const longlong2 bb = __ldcg(reinterpret_cast<const longlong2 *>(P.lambda + j + 2));
+                                    const ulonglong2 ka = __ldcg(reinterpret_cast<const ulonglong2 *>(P.dkey + j));
+                                    const ulonglong2 kb = __ldcg(reinterpret_cast<const ulonglong2 *>(P.dkey + j + 2));
+                                    relax(j, c.x, a.x, ka.x); relax(j + 1, c.y, a.y, ka.y); relax(j + 2, c.z, bb.x, kb.x); relax(j + 3, c.w, bb.y, kb.y);
+                                }
+                            }
+                            jtail = n4 << 2;
+                        }
+                        for (int j = jtail + t; j < no; j += kThreads) {
+                            if (SMEMP) relax(j, __ldg(r + j), sarr[j], 0);
+                            else relax(j, __ldg(r + j), __ldcg(P.lambda + j), __ldcg(P.dkey + j));
+                        }
+                    }
+                }
+                if (b == 0 && t == 0) { st_acc[9] += tq1 - tq0; st_acc[10] += global_ns() - tq1; }
+                implicit = false;
+                lr = lnext;
+                GRID_BARRIER();
+                status = __ldcg(P.gmm + 2);
+                if (status) break;
+            }
+            if (status) break;
+            if (D >= kInf / 2) { status = CYB_ERR_NOT_CONVERGED; break; }
+            const long long tr0 = (b == 0 && t == 0) ? global_ns() : 0;
+            // S3a: price update -- lambda[o] += D - d[o] below D; shared memory goes back to prices
+            for (int o = t; o < no; o += kThreads) {
+                const bool mine = (o % G == b);
+                if (!SMEMP && !mine) continue;
+                const unsigned long long key = __ldcg(P.dkey + o);
+                const long long d = key == ~0ull ? kInf : (long long)(key >> kPB);
+                long long lam;
+                if (SMEMP) { const long long g = sarr[o]; lam = g >= kGInf / 2 ? kInf : g + d; }
+                else lam = __ldcg(P.lambda + o);
+                if (d < D) {
+                    lam += D - d;
+                    if (mine) {
+                        if (lam >= kBidLimit) atomicExch(P.gmm + 2, CYB_ERR_OVERFLOW);
+                        P.lambda[o] = lam;
+                        const int s0 = capd ? __ldg(P.soff + o) : o, s1 = capd ? __ldg(P.soff + o + 1) : o + 1;
+                        for (int s = s0; s < s1; ++s) if (__ldcg(P.slot_price + s) < lam) P.slot_price[s] = lam;
+                    }
+                }
+                if (SMEMP) sarr[o] = lam;
+            }
+            // S3b: CTA 0 traces the candidate paths (one warp each) and publishes the accepted moves
+            if (b == 0) {
+                // candidate c = the free object of rank c by (label, object)
+                if (t < nfo) {
+                    const long long dm = sfo_d[t];
+                    int rank = 0;
+                    for (int u = 0; u < nfo; ++u) { const long long du = sfo_d[u]; rank += (du < dm || (du == dm && u < t)) ? 1 : 0; }
+                    if (rank < want) pth_obj[rank] = sfo[t];
+                }
+                __syncthreads();
+                auto pred_of = [&](int o) -> int { return SMEMO ? spred[o] : (int)(__ldcg(P.dkey + o) & kPM); };
+                if (warp < want && lane == 0) {
+                    int o = pth_obj[warp], len = 0;
+                    for (;;) {
+                        atomicMin(P.claim + o, cbase + warp);
+                        const int s = pred_of(o);
+                        ++len;
+                        if (s >= np) { atomicMin(P.claim + no + (s - np), cbase + warp); break; }
+                        o = obj_of_slot(s);
+                        if (len > np) break;                         // cannot happen (the tree has no cycles)
+                    }
+                    pth_len[warp] = len;
+                }
+                __syncthreads();
+                if (warp < want && lane == 0) {
+                    int o = pth_obj[warp], ok = 1, len = 0;
+                    for (;;) {
+                        ok &= (__ldcg(P.claim + o) == cbase + warp);
+                        const int s = pred_of(o);
+                        if (s >= np) { ok &= (__ldcg(P.claim + no + (s - np)) == cbase + warp); break; }
+                        o = obj_of_slot(s);
+                        if (++len > np) { ok = 0; break; }
+                    }
+                    pth_ok[warp] = ok;
+                }
+                __syncthreads();
+                if (warp < want && lane == 0 && pth_ok[warp]) {
+                    int base = 0;
+                    for (int u = 0; u < warp; ++u) if (pth_ok[u]) base += pth_len[u];
+                    int o = pth_obj[warp];
+                    int slot = -1;
+                    {
+                        const int s0 = capd ? __ldg(P.soff + o) : o, s1 = capd ? __ldg(P.soff + o + 1) : o + 1;
+                        for (int s = s0; s < s1; ++s) if (owner_of(s) < 0) { slot = s; break; }
+                    }
+                    for (;;) {
+                        const int s = pred_of(o);
+                        const int p = s >= np ? ssrc[s - np] : owner_of(s);
+                        P.moves[base++] = make_int4(p, o, slot, 0);
+                        if (s >= np) { P.srcdone[s - np] = 1; break; }
+                        o = obj_of_slot(s); slot = s;
+                    }
+                }
+                __syncthreads();
+                if (t == 0) {
+                    int tot = 0, np_ = 0;
+                    for (int u = 0; u < want; ++u) if (pth_ok[u]) { tot += pth_len[u]; ++np_; }
+                    P.nmoves[0] = tot;
+                    sh_i[4] = np_;
+                }
+                __syncthreads();
+            }
+            GRID_BARRIER();
+            status = __ldcg(P.gmm + 2);
+            if (status) break;
+            // S3c: every CTA applies the moves to its replicas; global state has one writer per move
+            {
+                const int nm = __ldcg(P.nmoves);
+                for (int k = t; k < nm; k += kThreads) {
+                    const int4 mv = __ldcg(P.moves + k);
+                    if (SMEMO) sowner[mv.z] = mv.x;
+                    if (k % G == b) {
+                        P.slot_owner[mv.z] = mv.x; P.person_obj[mv.x] = mv.y; P.person_slot[mv.x] = mv.z;
+                        P.slot_price[mv.z] = SMEMP ? sarr[mv.y] : __ldcg(P.lambda + mv.y);
+                    }
+                }
+                // the free persons that are still free, in order
+                const bool still = t < F && __ldcg(P.srcdone + t) == 0;
+                const int me = t < F ? ssrc[t] : -1;
+                int tot;
+                const int pos = block_excl_count(still, wcnt, tot);
+                if (still) ssrc[pos] = me;
+                paths += F - tot;
+                if (tot == F) { status = CYB_ERR_NOT_CONVERGED; }        // no path applied: cannot happen
+                F = tot;
+                __syncthreads();
+            }
+            if (b == 0 && t == 0) st_acc[11] += global_ns() - tr0;
+            if (status) break;
+            if (F > 0 && !SMEMO) GRID_BARRIER();     // the next search reads slot owners from global memory
+        }
+        if (b == 0 && t == 0) st_acc[7] += global_ns() - ts0;
+        if (status) break;
+        GRID_BARRIER();        // moves / prices of the last search become visible
+        status = __ldcg(P.gmm + 2);
+        if (status) break;
+        if (eps == 1) break;
+        eps /= P.theta;
+        if (eps < 1) eps = 1;
+    }
+    if (status) atomicExch(P.gmm + 2, status);
+
+    // ---- total cost of the assignment -------------------------------------------
+    if (!status) {
+        long long sum = 0;
+        for (int i = b * kThreads + t; i < np; i += G * kThreads) {
+            const int o = __ldcg(P.person_obj + i);
+            if (o >= 0) sum += (long long)__ldg(rowptr(i) + o);
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+        if (lane == 0 && sum != 0) atomicAdd(reinterpret_cast<unsigned long long *>(P.total), (unsigned long long)sum);
+    }
+    if (t == 0 && srows) atomicAdd(reinterpret_cast<unsigned long long *>(P.stats + 13), (unsigned long long)srows);
+    if (b == 0 && t == 0) {
+        P.stats[0] = status; P.stats[1] = phases; P.stats[2] = rounds; P.stats[3] = st_acc[0];
+        P.stats[4] = phases - 1; P.stats[5] = cmin; P.stats[6] = cmax; P.stats[7] = S;
+        P.stats[8] = G; P.stats[9] = SMEMP ? 1 : 0; P.stats[10] = 2 + (SMEMO ? 1 : 0); P.stats[11] = st_acc[1];
+        P.stats[12] = (phases - 1) * (long long)np; P.stats[14] = searches; P.stats[15] = srounds;
+        P.stats[16] = st_acc[3]; P.stats[17] = st_acc[4]; P.stats[18] = st_acc[5]; P.stats[19] = st_acc[6]; P.stats[20] = st_acc[7];
+        P.stats[21] = paths; P.stats[22] = st_acc[9]; P.stats[23] = st_acc[10]; P.stats[24] = st_acc[11];
+    }
+}
+
+struct SapLayout {
+    size_t list[3], rec[3], bidw[3], flag, slot_price, person_slot, minslot, slot_obj, dkey, cstamp, chg[3], claim, moves, small, total;
+};
+
+SapLayout sap_layout(int64_t np, int64_t no) {
+    SapLayout L;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o = cyb::align_up(o + bytes, 256); return r; };
+    for (int k = 0; k < 3; ++k) L.list[k] = take((size_t)np * 4);
+    for (int k = 0; k < 3; ++k) L.rec[k] = take((size_t)np * 16);
+    for (int k = 0; k < 3; ++k) L.bidw[k] = take((size_t)no * 8);
+    L.flag = take((size_t)np * 4);
+    L.slot_price = take((size_t)np * 8);
+    L.person_slot = take((size_t)np * 4);
+    L.minslot = take((size_t)no * 4);
+    L.slot_obj = take((size_t)np * 4);
+    L.dkey = take((size_t)no * 8);
+    L.cstamp = take((size_t)no * 4);
+    for (int k = 0; k < 3; ++k) L.chg[k] = take((size_t)no * 4);
+    L.claim = take((size_t)(no + kSapMax) * 4);
+    L.moves = take((size_t)np * 16);
+    L.small = take(2048);
+    L.total = o;
+    return L;
+}
+
+}  // namespace
+
+extern "C" size_t cyb_lap_workspace_bytes(int64_t n_persons, int64_t n_objects) {
+    if (n_persons <= 0 || n_objects <= 0) return 256;
+    return std::max(sap_layout(n_persons, n_objects).total, cyb::lap_auction_workspace_bytes(n_persons, n_objects));
+}
+
+extern "C" int cyb_lap_solve_i32(const int32_t *cost_dev, int64_t ld, int64_t n_persons, int64_t n_objects,
+                                 const int32_t *slot_offset_dev, int32_t *person_obj_dev,
+                                 int32_t *slot_owner_dev, int64_t *price_dev, int64_t *total_dev,
+                                 int64_t *stats_dev, void *workspace_dev, size_t workspace_bytes,
+                                 int grid_hint, void *stream_v) {
+    if (const char *e = getenv("CYB_LAP_SOLVER"))
+        if (!strcmp(e, "auction"))
+            return cyb::lap_solve_auction(cost_dev, ld, n_persons, n_objects, slot_offset_dev, person_obj_dev, slot_owner_dev,
+                                          price_dev, total_dev, stats_dev, workspace_dev, workspace_bytes, grid_hint, stream_v);
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    const int64_t np = n_persons, no = n_objects;
+    if (np <= 0 || np >= (1ll << kPB) - kSapMax || no <= 0 || no > np)
+        return cyb::set_error(CYB_ERR_INVALID,
+                              "cyb_lap_solve_i32: persons=%lld objects=%lld outside 1 <= objects <= persons < 2^18 - 256",
+                              (long long)np, (long long)no);
+    if (!slot_offset_dev && no != np)
+        return cyb::set_error(CYB_ERR_INVALID, "cyb_lap_solve_i32: without capacities the problem must be square");
+    if (!cost_dev || !person_obj_dev || !slot_owner_dev || !price_dev || !total_dev || !stats_dev || !workspace_dev)
+        return cyb::set_error(CYB_ERR_INVALID, "cyb_lap_solve_i32: null pointer argument");
+    if (ld < no)
+        return cyb::set_error(CYB_ERR_INVALID, "cyb_lap_solve_i32: ld=%lld < objects=%lld", (long long)ld, (long long)no);
+    const SapLayout L = sap_layout(np, no);
+    if (workspace_bytes < L.total)
+        return cyb::set_error(CYB_ERR_WORKSPACE, "cyb_lap_solve_i32: workspace %zu < required %zu", workspace_bytes, L.total);
+    if (reinterpret_cast<uintptr_t>(workspace_dev) & 255)
+        return cyb::set_error(CYB_ERR_INVALID, "cyb_lap_solve_i32: workspace must be 256-byte aligned");
+
+    int dev = 0;
+    CYB_CUDA_CHECK(cudaGetDevice(&dev));
+    int sms = 0, coop = 0, max_smem = 0;
+    CYB_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    CYB_CUDA_CHECK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+    CYB_CUDA_CHECK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    if (!coop) return cyb::set_error(CYB_ERR_UNSUPPORTED, "device lacks cooperative launch");
+
+    int G = grid_hint > 0 ? grid_hint : sms;
+    if (G > sms) G = sms;
+    if (G > np) G = (int)np;
+    if (G < 1) G = 1;
+
+    char *ws = static_cast<char *>(workspace_dev);
+    SapParams P;
+    memset(&P, 0, sizeof(P));
+    P.cost = cost_dev; P.ld = ld; P.P = (int)np; P.O = (int)no; P.soff = slot_offset_dev;
+    P.person_obj = person_obj_dev; P.slot_owner = slot_owner_dev;
+    P.lambda = reinterpret_cast<long long *>(price_dev);
+    P.total = reinterpret_cast<long long *>(total_dev); P.stats = reinterpret_cast<long long *>(stats_dev);
+    for (int k = 0; k < 3; ++k) {
+        P.list[k] = reinterpret_cast<int32_t *>(ws + L.list[k]);
+        P.rec[k] = reinterpret_cast<int4 *>(ws + L.rec[k]);
+        P.bidw[k] = reinterpret_cast<unsigned long long *>(ws + L.bidw[k]);
+        P.chg[k] = reinterpret_cast<int32_t *>(ws + L.chg[k]);
+    }
+    P.flag = reinterpret_cast<int32_t *>(ws + L.flag);
+    P.slot_price = reinterpret_cast<long long *>(ws + L.slot_price);
+    P.person_slot = reinterpret_cast<int32_t *>(ws + L.person_slot);
+    P.minslot = reinterpret_cast<int32_t *>(ws + L.minslot);
+    P.slot_obj = reinterpret_cast<int32_t *>(ws + L.slot_obj);
+    P.dkey = reinterpret_cast<unsigned long long *>(ws + L.dkey);
+    P.cstamp = reinterpret_cast<int32_t *>(ws + L.cstamp);
+    P.claim = reinterpret_cast<int32_t *>(ws + L.claim);
+    P.moves = reinterpret_cast<int4 *>(ws + L.moves);
+    P.bar = reinterpret_cast<unsigned int *>(ws + L.small);
+    P.gmm = reinterpret_cast<int *>(ws + L.small + 16);
+    P.nchg = reinterpret_cast<int *>(ws + L.small + 64);
+    P.nmoves = reinterpret_cast<int *>(ws + L.small + 96);
+    P.srcdone = reinterpret_cast<int32_t *>(ws + L.small + 128);          // kSapMax ints = 1 KB
+    P.qcap = (int)((np + G - 1) / G);
+    P.max_rounds = 2000ll * np + 100000;
+    P.prefetch = no * 4 > 131072 ? 1 : 0;
+    if (const char *e = getenv("CYB_LAP_PREFETCH")) P.prefetch = atoi(e) ? 1 : 0;
+    P.packed_reduce = 1;
+    if (const char *e = getenv("CYB_LAP_PACKED")) P.packed_reduce = atoi(e) ? 1 : 0;
+    P.theta = 64; P.eps0_div = 4;
+    if (const char *e = getenv("CYB_LAP_THETA")) P.theta = std::max(2, atoi(e));
+    if (const char *e = getenv("CYB_LAP_EPS0")) P.eps0_div = std::max(1, atoi(e));
+    P.sap_t = std::min(G, kSapMax); P.sap_k = 2 * G; P.multi = kMultiMax;
+    if (const char *e = getenv("CYB_LAP_SAP_T")) P.sap_t = std::max(1, std::min(kSapMax, atoi(e)));
+    if (const char *e = getenv("CYB_LAP_SAP_K")) P.sap_k = std::max(1, atoi(e));
+    if (const char *e = getenv("CYB_LAP_SAP_MULTI")) P.multi = std::max(1, std::min(kMultiMax, atoi(e)));
+
+    // barrier counters [0..1], gmm = {cmin, cmax, status, -, -, abort flag}
+    const int init[16] = {0, 0, 0, 0, INT_MAX, INT_MIN, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    CYB_CUDA_CHECK(cudaMemcpyAsync(ws + L.small, init, sizeof(init), cudaMemcpyHostToDevice, stream));
+    CYB_CUDA_CHECK(cudaMemsetAsync(total_dev, 0, sizeof(int64_t), stream));
+    CYB_CUDA_CHECK(cudaMemsetAsync(stats_dev, 0, sizeof(int64_t) * CYB_LAP_NSTATS, stream));
+
+    const size_t base_bytes = cyb::align_up((size_t)P.qcap * 8, 16) + cyb::align_up((size_t)P.qcap * 4, 16) +
+                              cyb::align_up((size_t)((no + 31) / 32) * 4, 16);
+    const size_t price_bytes = cyb::align_up((size_t)no * 8, 16);
+    const size_t owner_bytes = (size_t)((np + 3) & ~3) * 4 + (size_t)((no + 3) & ~3) * 4 +
+                               (slot_offset_dev ? (size_t)((no + 3) & ~3) * 4 : 0) + 16;
+    const size_t static_smem = 8192;              // bound on the kernel's static shared memory
+    bool smemp = base_bytes + price_bytes + static_smem <= (size_t)max_smem;
+    if (const char *e = getenv("CYB_LAP_SMEM_PRICES")) smemp = smemp && atoi(e);
+    size_t dyn = base_bytes + (smemp ? price_bytes : 0);
+    bool smemo = smemp && dyn + owner_bytes + static_smem <= (size_t)max_smem;
+    if (const char *e = getenv("CYB_LAP_SMEM_OWNER")) smemo = smemo && atoi(e);
+    if (smemo) dyn += owner_bytes;
+
+    const void *fn = smemp ? (smemo ? (const void *)lap_sap_kernel<true, true> : (const void *)lap_sap_kernel<true, false>)
+                           : (const void *)lap_sap_kernel<false, false>;
+    CYB_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    int occ = 0;
+    CYB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kThreads, dyn));
+    if (occ < 1) return cyb::set_error(CYB_ERR_UNSUPPORTED, "lap kernel does not fit on an SM (smem %zu)", dyn);
+    if (G > occ * sms) G = occ * sms;
+    void *args[] = {(void *)&P};
+    CYB_CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(G), dim3(kThreads), args, dyn, stream));
+    CYB_CUDA_CHECK(cudaGetLastError());
+    return CYB_OK;
+}
