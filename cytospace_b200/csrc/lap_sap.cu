@@ -77,6 +77,7 @@ size_t lap_auction_workspace_bytes(int64_t n_persons, int64_t n_objects);
 namespace {
 
 constexpr int kThreads = 1024;
+constexpr int kWarps = kThreads / 32;
 constexpr int kPB = 18;                                        // P < 2^18 - kSapMax
 constexpr unsigned long long kPM = (1ull << kPB) - 1;
 constexpr long long kInf = 1ll << 60;                          // price of an object without capacity / label "unreached"
@@ -85,7 +86,6 @@ constexpr long long kBidLimit = 1ll << 45;                     // 46-bit bid / l
 constexpr int kSapMax = 256;                                   // free persons a search can start from
 constexpr int kMultiMax = 32;                                  // augmenting paths per search (one warp each)
 constexpr int kRowsMax = 32;                                   // rows a CTA relaxes per chunk
-constexpr int kEPT = 4;                                        // dirty-list entries a thread caches in registers
 constexpr int kMaxSearch = 1 << 24;
 
 struct SapParams {
@@ -105,13 +105,14 @@ struct SapParams {
     int *gmm;                // [0] cmin, [1] cmax, [2] status
     // search state
     unsigned long long *dkey;        // [O] (label << 18 | entering slot; sources are P + k), ~0 = unreached
-    int32_t *cstamp;                 // [O] round id of the last append to a dirty list
-    int32_t *chg[3];                 // dirty lists, rotating by round
-    int *nchg;                       // [3] their lengths
+    unsigned *chgbits[3];            // [(O+31)/32] objects whose label a round lowered, rotating by round
     int32_t *claim;                  // [O + kSapMax] path claims (decreasing base per search)
     int4 *moves;                     // [P] (person, object, slot, -) of the accepted paths
     int *nmoves;                     // [1]
     int32_t *srcdone;                // [kSapMax]
+    unsigned long long *cand[3];     // [O] candidate lists (label << 18 | object), rotating by round
+    int *rstat;                      // [3][8] per round {candidates, their slots, eligible slots, -, min eligible label (64 bit)}
+    int wpc;                         // label words (32 objects) a CTA classifies per round
     int qcap;
     long long max_rounds;
     int sap_t, sap_k, multi;
@@ -199,24 +200,6 @@ __device__ __forceinline__ bool grid_barrier(unsigned int *bar, unsigned int &ta
     }
     return __syncthreads_or(dead);
 }
-// Split grid barrier: every CTA `arrive`s once it has finished READING the labels of the round, and
-// `wait`s before its first atomic on them; the selection work in between hides the round trip.
-__device__ __forceinline__ void grid_arrive(unsigned int *bar, unsigned int &target, unsigned int G) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        target += G;
-        __threadfence();
-        atomicAdd(bar, 1u);
-    }
-}
-__device__ __forceinline__ bool grid_wait(unsigned int *bar, unsigned int target, int *abortf, int line) {
-    bool dead = false;
-    if (threadIdx.x == 0) {
-        dead = spin_until(bar, target, abortf, line);
-        __threadfence();
-    }
-    return __syncthreads_or(dead);
-}
 // Block-wide exclusive prefix count of `valid`; `total` = number of valid threads.
 __device__ __forceinline__ int block_excl_count(bool valid, int *wcnt, int &total) {
     const unsigned m = __ballot_sync(0xffffffffu, valid);
@@ -224,7 +207,7 @@ __device__ __forceinline__ int block_excl_count(bool valid, int *wcnt, int &tota
     const int within = __popc(m & ((1u << lane) - 1u));
     if (lane == 0) wcnt[w] = __popc(m);
     __syncthreads();
-    const int c = wcnt[lane];
+    const int c = lane < kWarps ? wcnt[lane] : 0;
     int inc = c;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -257,7 +240,7 @@ __device__ __forceinline__ Best packed_reduce(unsigned long long k1, unsigned lo
     __syncthreads();
     Best s{LLONG_MAX, LLONG_MAX, -1};
     if (w == 0) {
-        const unsigned long long q1 = rk1[lane], q2 = rk2[lane];
+        const unsigned long long q1 = lane < kWarps ? rk1[lane] : ~0ull, q2 = lane < kWarps ? rk2[lane] : ~0ull;
         const unsigned long long W1 = warp_min64(q1);
         const unsigned long long W2 = warp_min64(q1 == W1 ? q2 : q1);
         const long long v1 = (long long)(W1 >> kPB), v2 = (long long)(W2 >> kPB);
@@ -281,7 +264,7 @@ __device__ __forceinline__ Best scan_row(const int32_t *__restrict__ r, int n, i
     if (vec_ok) {
         const int4 *r4 = reinterpret_cast<const int4 *>(r);
         const int n4 = n >> 2;
-#pragma unroll 4
+#pragma unroll 8
         for (int q = t; q < n4; q += kThreads) {
             const int4 c = ld_stream(r4 + q, pol);
             const int j = q << 2;
@@ -323,7 +306,8 @@ __device__ __forceinline__ Best scan_row(const int32_t *__restrict__ r, int n, i
     if (lane == 0) { red_b1[w] = s.b1; red_b2[w] = s.b2; red_j[w] = s.j1; }
     __syncthreads();
     if (w == 0) {
-        s.b1 = red_b1[lane]; s.b2 = red_b2[lane]; s.j1 = red_j[lane];
+        if (lane < kWarps) { s.b1 = red_b1[lane]; s.b2 = red_b2[lane]; s.j1 = red_j[lane]; }
+        else { s.b1 = LLONG_MAX; s.b2 = LLONG_MAX; s.j1 = -1; }
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) {
             Best o;
@@ -363,7 +347,15 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
     off += ((size_t)P.qcap * 8 + 15) / 16 * 16;
     int *myq = reinterpret_cast<int *>(smem_raw + off);                // [qcap] work queue (persons / frontier objects)
     off += ((size_t)P.qcap * 4 + 15) / 16 * 16;
-    unsigned *sfront = reinterpret_cast<unsigned *>(smem_raw + off);   // [(O+31)/32] frontier membership (L2-label tie rule)
+    unsigned *sfront = reinterpret_cast<unsigned *>(smem_raw + off);   // [(O+31)/32] frontier of the round
+    off += ((size_t)((no + 31) / 32) * 4 + 15) / 16 * 16;
+    long long *sld = reinterpret_cast<long long *>(smem_raw + off);     // [wpc*32] labels of this CTA's slice (as classified)
+    off += (size_t)P.wpc * 32 * 8;
+    unsigned *sel_loc = reinterpret_cast<unsigned *>(smem_raw + off);  // [wpc] eligible objects of the slice
+    off += ((size_t)P.wpc * 4 + 15) / 16 * 16;
+    unsigned *sdirty_loc = reinterpret_cast<unsigned *>(smem_raw + off);   // [wpc] slice objects lowered since their holders last relaxed
+    off += ((size_t)P.wpc * 4 + 15) / 16 * 16;
+    int *swbase = reinterpret_cast<int *>(smem_raw + off);             // [(O+31)/32] frontier rank of a word's first bit
     off += ((size_t)((no + 31) / 32) * 4 + 15) / 16 * 16;
     int *sowner = reinterpret_cast<int *>(smem_raw + off);             // SMEMO: [P]
     int *spred = sowner + ((np + 3) & ~3);                             // SMEMO: [O]
@@ -377,7 +369,7 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
     __shared__ int hist[256];
     __shared__ long long sh_ll[4];      // broadcast slots: [0] D, [1] dmin, [2] dmax, [3] T
     __shared__ int sh_i[8];             // [0] wsum, [1] count, [2] nfront, [3] status, [4] n moves
-    __shared__ int rw_person[kRowsMax], rw_slot[kRowsMax];
+    __shared__ int rw_person[kRowsMax], rw_slot[kRowsMax], rw_qi[kRowsMax], rw_slot2[kRowsMax], rw_qi2[kRowsMax];
     __shared__ long long rw_thr[kRowsMax];
     __shared__ int pth_ok[kMultiMax], pth_len[kMultiMax], pth_obj[kMultiMax];
 
@@ -385,7 +377,7 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
     const int lane = t & 31, warp = t >> 5;
     const int S = np + 1;
     const bool vec_ok = ((P.ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(P.cost) & 15) == 0);
-    unsigned int bar_target = 0, bar2_target = 0;
+    unsigned int bar_target = 0;
     // a wait that timed out: the launch is given up (status only; the outputs are undefined)
 #define LAP_ABORT() do { if (threadIdx.x == 0) P.stats[0] = CYB_ERR_NOT_CONVERGED; return; } while (0)
 #define GRID_BARRIER() do { if (grid_barrier(P.bar, bar_target, G, P.gmm + 5, __LINE__)) LAP_ABORT(); } while (0)
@@ -420,7 +412,6 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
             P.lambda[o] = capacity(o) > 0 ? 0 : kInf;          // a spot that takes no cell is priced out
             P.minslot[o] = capd ? __ldg(P.soff + o) : o;
             P.bidw[0][o] = 0ull; P.bidw[1][o] = 0ull; P.bidw[2][o] = 0ull;
-            P.cstamp[o] = 0;
             if (capd) for (int s = __ldg(P.soff + o); s < __ldg(P.soff + o + 1); ++s) P.slot_obj[s] = o;
         }
         for (int o = b * kThreads + t; o < no + kSapMax; o += G * kThreads) P.claim[o] = INT_MAX;
@@ -590,6 +581,7 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
         }
 
         // ---- shortest-augmenting-path finish -------------------------------------
+        long long step = eps;                    // frontier window of the searches, adapted round by round
         const long long ts0 = (b == 0 && t == 0) ? global_ns() : 0;
         if (F > 0) {
             if (t < F) ssrc[t] = __ldcg(P.list[cur] + t);
@@ -601,7 +593,8 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
             const int cbase = (kMaxSearch - searches) * kMultiMax;
             // S0: labels unreached, lists empty; shared memory switches from prices to g = lambda - d
             for (int o = b * kThreads + t; o < no; o += G * kThreads) P.dkey[o] = ~0ull;
-            if (b == 0 && t < 3) P.nchg[t] = 0;
+            for (int w = b * kThreads + t; w < 3 * ((no + 31) / 32); w += G * kThreads) P.chgbits[w / ((no + 31) / 32)][w % ((no + 31) / 32)] = 0u;
+            if (b == 0 && t < 24) { if ((t & 7) == 4 || (t & 7) == 5) P.rstat[t] = -1; else P.rstat[t] = 0; }      // dmin = all ones
             if (SMEMP) for (int o = t; o < no; o += kThreads) { const long long l = sarr[o]; sarr[o] = l >= kInf / 2 ? kGInf : l - kInf; }
             GRID_BARRIER();
             // (every CTA has finished applying the previous search's moves: their buffers can be reset)
@@ -647,23 +640,72 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
                 __syncthreads();
             }
             GRID_BARRIER();
-            // S2: search rounds.  The dirty list of round r is chg[r % 3] (round 1: every object).
+            // S2: search rounds.  The selection is DISTRIBUTED: every CTA classifies its own slice of the
+            // objects (one warp per 32-object word: label, lowered-bitmap word, holder), appends the candidates
+            // (eligible labels <= Tg) to a global list and adds its statistics; after a grid barrier every CTA
+            // reads the (short) candidate list, derives the same threshold T and frontier from it and takes the
+            // frontier entries of rank = b (mod G).  Two grid barriers per round; per-CTA work is a handful of
+            // loads.  A CTA's dirty words (lowered since their holders last relaxed) stay in its shared memory.
             long long D = kInf;
-            int lr = 0;
-            bool implicit = true;
+            int rr3 = 0;                         // round index mod 3: bitmap read / candidate list of this round
+            bool implicit = true;                // round 1: every reached object is dirty
+            const int nwords = (no + 31) / 32;
+            const int w0 = b * P.wpc, nmy = max(0, min(nwords, w0 + P.wpc) - w0);
+            for (int ww = t; ww < P.wpc; ww += kThreads) sdirty_loc[ww] = 0u;
+            long long Tg = -1;                   // this round's guess: candidates are the eligible labels <= Tg
             for (;;) {
                 ++rid;
                 const long long tq0 = (b == 0 && t == 0) ? global_ns() : 0;
-                const int lnext = lr == 2 ? 0 : lr + 1, lclear = lr == 0 ? 2 : lr - 1;
-                const int n = implicit ? no : __ldcg(P.nchg + lr);
-                const int32_t *L = P.chg[lr];
-                if (b == 0 && t == 0 && !implicit) P.nchg[lclear] = 0;      // read in the previous round, appended to in the next
-                // D = the want-th smallest label of an object with a free slot
+                const int nb = rr3 == 2 ? 0 : rr3 + 1, zb = rr3 == 0 ? 2 : rr3 - 1;
+                const unsigned *CB = P.chgbits[rr3];
+                unsigned *NB = P.chgbits[nb];
+                unsigned long long *CAND = P.cand[rr3];
+                int *RS = P.rstat + 8 * rr3;             // {ncand, wC, wE, -, dmin (64 bit), -, -}
+                // buffers of the previous round: read by nobody any more, written again in the next round
+                for (int w = b * kThreads + t; w < nwords; w += G * kThreads) P.chgbits[zb][w] = 0u;
+                if (b == 0 && t == 0) {
+                    int *Z = P.rstat + 8 * nb;
+                    Z[0] = 0; Z[1] = 0; Z[2] = 0; *reinterpret_cast<unsigned long long *>(Z + 4) = ~0ull;
+                }
+                // ---- phase 1: all the loads of the phase are requested first (one round trip) ----
                 if (t < nfo) { const unsigned long long key = __ldcg(P.dkey + sfo[t]); sfo_d[t] = key == ~0ull ? kInf : (long long)(key >> kPB); }
-                if (t == 0) { sh_ll[0] = kInf; sh_ll[1] = LLONG_MAX; sh_ll[2] = 0; sh_i[0] = 0; sh_i[1] = 0; }
+                const int o_pre = (w0 + warp) * 32 + lane;
+                const bool has_pre = warp < nmy && o_pre < no;
+                const unsigned long long key_pre = has_pre ? __ldcg(P.dkey + o_pre) : ~0ull;
+                const unsigned cbw_pre = (warp < nmy && !implicit) ? __ldcg(CB + w0 + warp) : ~0u;
+                if (t == 0) sh_ll[0] = kInf;
                 if (t < 256) hist[t] = 0;
-                for (int w = t; w < (no + 31) / 32; w += kThreads) sfront[w] = 0u;
-                __syncthreads();
+                // the objects the previous round lowered, as a bitmap in shared memory + prefix counts: their
+                // g = lambda - d and tree predecessor replicas are refreshed below
+                int nchg = 0;
+                if (SMEMP || SMEMO) {
+                    for (int wb = 0; wb < nwords; wb += kThreads) {
+                        const int w = wb + t;
+                        unsigned cw = 0;
+                        if (w < nwords) {
+                            cw = implicit ? ((w == nwords - 1 && (no & 31)) ? ((1u << (no & 31)) - 1u) : ~0u) : __ldcg(CB + w);
+                            sfront[w] = cw;
+                        }
+                        const int c = __popc(cw);
+                        int inc = c;
+#pragma unroll
+                        for (int dd = 1; dd < 32; dd <<= 1) { const int y = __shfl_up_sync(0xffffffffu, inc, dd); if (lane >= dd) inc += y; }
+                        if (lane == 31) wcnt[warp] = inc;
+                        __syncthreads();
+                        int wv = lane < kWarps ? wcnt[lane] : 0, winc = wv;
+#pragma unroll
+                        for (int dd = 1; dd < 32; dd <<= 1) { const int y = __shfl_up_sync(0xffffffffu, winc, dd); if (lane >= dd) winc += y; }
+                        const int woff = __shfl_sync(0xffffffffu, winc - wv, warp);
+                        const int tot = __shfl_sync(0xffffffffu, winc, 31);
+                        if (w < nwords) swbase[w] = nchg + woff + inc - c;
+                        nchg += tot;
+                        __syncthreads();
+                    }
+                } else {
+                    for (int w = t; w < nwords; w += kThreads) sfront[w] = 0u;      // frontier bitmask of the L2-label tie rule
+                    __syncthreads();
+                }
+                // D = the want-th smallest label of an object with a free slot
                 if (t < nfo) {
                     const long long dm = sfo_d[t];
                     int rank = 0;
@@ -672,67 +714,92 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
                 }
                 __syncthreads();
                 D = sh_ll[0];
-                // pass A: fetch entries, refresh the replicas, eligibility, label range
-                auto fetch = [&](int e, int &o, long long &d) -> bool {
-                    o = implicit ? e : __ldcg(L + e);
-                    const unsigned long long key = __ldcg(P.dkey + o);
-                    d = key == ~0ull ? kInf : (long long)(key >> kPB);
-                    if (key != ~0ull) {
-                        if (SMEMP) { const long long lam = __ldcg(P.lambda + o); sarr[o] = lam >= kInf / 2 ? kGInf : lam - d; }
-                        if (SMEMO) spred[o] = (int)(key & kPM);
+                if (D >= kInf / 2) { status = CYB_ERR_NOT_CONVERGED; break; }     // cannot happen: round 0 reaches every object
+                if (step > D) step = D;
+                if (step < 1) step = 1;
+                if (Tg > D - 1) Tg = D - 1;                                  // every eligible label is below D
+                // this CTA's slice: eligible = dirty, held and below D; candidates = eligible with label <= Tg
+                for (int ww = warp; ww < nmy; ww += kWarps) {
+                    const int w = w0 + ww, o = w * 32 + lane;
+                    const unsigned long long key = ww == warp ? key_pre : (o < no ? __ldcg(P.dkey + o) : ~0ull);
+                    const unsigned cbw = ww == warp ? cbw_pre : (implicit ? ~0u : __ldcg(CB + w));
+                    bool el = false; long long d = kInf;
+                    if (o < no && key != ~0ull) {
+                        d = (long long)(key >> kPB);
+                        if ((((cbw | sdirty_loc[ww]) >> lane) & 1u) && d < D) {
+                            if (!capd) el = owner_of(o) >= 0;
+                            else for (int sl = __ldg(P.soff + o); sl < __ldg(P.soff + o + 1); ++sl) el = el || owner_of(sl) >= 0;
+                        }
                     }
-                    if (!(d < D)) return false;
-                    if (!capd) return owner_of(o) >= 0;
-                    bool held = false;
-                    for (int s = __ldg(P.soff + o); s < __ldg(P.soff + o + 1); ++s) held = held || owner_of(s) >= 0;
-                    return held;
-                };
-                int eo[kEPT]; long long ed[kEPT]; bool ee[kEPT];
-                long long lmin = LLONG_MAX, lmax = LLONG_MIN; int lw = 0, lc = 0;
+                    sld[ww * 32 + lane] = d;
+                    const bool cnd = el && d <= Tg;
+                    const unsigned mel = __ballot_sync(0xffffffffu, el), mc = __ballot_sync(0xffffffffu, cnd);
+                    int base = 0;
+                    if (lane == 0) { sel_loc[ww] = mel; if (mc) base = atomicAdd(RS + 0, __popc(mc)); }
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (cnd) CAND[base + __popc(mc & ((1u << lane) - 1u))] = ((unsigned long long)d << kPB) | (unsigned)o;
+                    const int cap = el ? capacity(o) : 0;
+                    int lE = cap, lC = cnd ? cap : 0; long long lmin = el ? d : kInf;
 #pragma unroll
-                for (int j = 0; j < kEPT; ++j) {
-                    const int e = t + j * kThreads;
-                    ee[j] = false; eo[j] = 0; ed[j] = 0;
-                    if (e < n) {
-                        ee[j] = fetch(e, eo[j], ed[j]);
-                        if (ee[j]) { lmin = min(lmin, ed[j]); lmax = max(lmax, ed[j]); lw += capacity(eo[j]); ++lc; }
+                    for (int dd = 16; dd > 0; dd >>= 1) {
+                        lmin = min(lmin, __shfl_xor_sync(0xffffffffu, lmin, dd));
+                        lC += __shfl_xor_sync(0xffffffffu, lC, dd);
+                        lE += __shfl_xor_sync(0xffffffffu, lE, dd);
+                    }
+                    if (lane == 0 && lE > 0) {
+                        if (lC) atomicAdd(RS + 1, lC);
+                        atomicAdd(RS + 2, lE);
+                        atomicMin(reinterpret_cast<unsigned long long *>(RS + 4), (unsigned long long)lmin);
                     }
                 }
-                for (int e = t + kEPT * kThreads; e < n; e += kThreads) {
-                    int o; long long d;
-                    if (fetch(e, o, d)) { lmin = min(lmin, d); lmax = max(lmax, d); lw += capacity(o); ++lc; }
+                // replicas of the lowered objects (position i of the bitmap -> word by binary search over the prefix counts)
+                if (SMEMP || SMEMO) {
+#pragma unroll 2
+                    for (int i = t; i < nchg; i += kThreads) {
+                        int lo = 0, hi = nwords - 1;
+                        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (swbase[mid] <= i) lo = mid; else hi = mid - 1; }
+                        const int o = lo * 32 + (int)__fns(sfront[lo], 0, i - swbase[lo] + 1);
+                        const unsigned long long key = __ldcg(P.dkey + o);
+                        if (key != ~0ull) {
+                            if (SMEMP) { const long long lam = __ldcg(P.lambda + o); sarr[o] = lam >= kInf / 2 ? kGInf : lam - (long long)(key >> kPB); }
+                            if (SMEMO) spred[o] = (int)(key & kPM);
+                        }
+                    }
                 }
-#pragma unroll
-                for (int dd = 16; dd > 0; dd >>= 1) {
-                    lmin = min(lmin, __shfl_xor_sync(0xffffffffu, lmin, dd));
-                    lmax = max(lmax, __shfl_xor_sync(0xffffffffu, lmax, dd));
-                    lw += __shfl_xor_sync(0xffffffffu, lw, dd);
-                    lc += __shfl_xor_sync(0xffffffffu, lc, dd);
+                if (b == 0 && t == 0) st_acc[2] += global_ns() - tq0;
+                GRID_BARRIER();                                          // candidates and statistics are complete; labels may be lowered from here on
+                // ---- phase 2: every CTA derives the same threshold and frontier from the candidate list ----
+                const long long tq2 = (b == 0 && t == 0) ? global_ns() : 0;
+                unsigned long long e_pre = t < no ? __ldcg(CAND + t) : 0ull;            // (speculative: before the count is known)
+                if (t == 0) {
+                    sh_i[0] = __ldcg(RS + 0); sh_i[1] = __ldcg(RS + 1); sh_i[2] = __ldcg(RS + 2);
+                    sh_ll[1] = (long long)__ldcg(reinterpret_cast<unsigned long long *>(RS + 4));
                 }
-                if (lane == 0 && lc > 0) {
-                    atomicMin(reinterpret_cast<unsigned long long *>(&sh_ll[1]), (unsigned long long)lmin);     // labels are >= 0
-                    atomicMax(reinterpret_cast<unsigned long long *>(&sh_ll[2]), (unsigned long long)lmax);
-                    atomicAdd(&sh_i[0], lw); atomicAdd(&sh_i[1], lc);
-                }
+                if (!(SMEMP || SMEMO)) {} else { for (int w = t; w < nwords; w += kThreads) sfront[w] = 0u; }
                 __syncthreads();
-                const int nelig = sh_i[1];
-                if (nelig == 0) break;                                  // fixed point below D: the search is over
+                const int ncand = sh_i[0], wC = sh_i[1], wE = sh_i[2];
+                const long long dmin_el = sh_ll[1];
+                if (wE == 0) break;                                     // fixed point below D: the search is over
+                if (wC == 0) {
+                    // the guess selected nothing (first round of the search, or D moved below it): restart from the
+                    // smallest eligible label.  Nothing was relaxed: the next round sees the same labels.
+                    Tg = dmin_el + step;
+                    for (int ww = t; ww < nmy; ww += kThreads) sdirty_loc[ww] = sel_loc[ww];
+                    implicit = false;
+                    rr3 = nb;
+                    GRID_BARRIER();
+                    continue;
+                }
                 if (++srounds + rounds > P.max_rounds) { status = CYB_ERR_NOT_CONVERGED; break; }
-                // Other CTAs must not lower labels while this one still reads them: arrive as soon as the
-                // reads are done (entries cached in registers: now; otherwise after the last pass).
-                const bool cached = n <= kEPT * kThreads;
-                if (cached) grid_arrive(P.bar + 1, bar2_target, G);
-                const long long dmin = sh_ll[1], dmax = sh_ll[2];
-                long long T = dmax;
-                if (sh_i[0] > P.sap_k) {
-                    // 256 power-of-two bins over [dmin, dmax]: first bin where the cumulative slot count reaches K
+                // T = about K rows' worth of the smallest candidates: 256 power-of-two bins over [dmin_el, Tg], upper
+                // edge of the first bin where the cumulative slot count reaches K (Tg when the candidates hold fewer)
+                long long T = Tg;
+                if (wC > P.sap_k) {
                     int sh = 0;
-                    while (((dmax - dmin) >> sh) >= 256) ++sh;
-#pragma unroll
-                    for (int j = 0; j < kEPT; ++j) if (ee[j]) atomicAdd(&hist[(int)((ed[j] - dmin) >> sh)], capacity(eo[j]));
-                    for (int e = t + kEPT * kThreads; e < n; e += kThreads) {
-                        int o; long long d;
-                        if (fetch(e, o, d)) atomicAdd(&hist[(int)((d - dmin) >> sh)], capacity(o));
+                    while (((Tg - dmin_el) >> sh) >= 256) ++sh;
+                    for (int e = t; e < ncand; e += kThreads) {
+                        const unsigned long long ent = e == t ? e_pre : __ldcg(CAND + e);
+                        atomicAdd(&hist[(int)(((long long)(ent >> kPB) - dmin_el) >> sh)], capacity((int)(ent & kPM)));
                     }
                     __syncthreads();
                     if (warp == 0) {
@@ -747,52 +814,52 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
                         for (int q = 0; q < 8; ++q) { run += c8[q]; if (run >= P.sap_k && bsel == INT_MAX) bsel = lane * 8 + q; }
                         bsel = __reduce_min_sync(0xffffffffu, (unsigned)bsel);
                         if (bsel == INT_MAX) bsel = 255;
-                        if (lane == 0) sh_ll[3] = dmin + (((long long)bsel + 1) << sh) - 1;
+                        if (lane == 0) sh_ll[3] = min(Tg, dmin_el + (((long long)bsel + 1) << sh) - 1);
                     }
                     __syncthreads();
                     T = sh_ll[3];
                 }
-                // pass C: the frontier (label <= T), dealt to the CTAs by rank; the rest is carried over
-                int nfront = 0, myn = 0;
-                auto passC = [&](int e, bool el, int o, long long d, int base_e) {
-                    (void)base_e;
-                    const bool fr = el && d <= T;
-                    if (el && !fr && (e % G == b)) {
-                        if (atomicMax(P.cstamp + o, rid) < rid) P.chg[lnext][atomicAdd(P.nchg + lnext, 1)] = o;
-                    }
-                    if (fr && !SMEMP) atomicOr(&sfront[o >> 5], 1u << (o & 31));
+                // frontier = candidates with label <= T, dealt to the CTAs by their rank in the list
+                int nfront = 0;
+                for (int e0 = 0; e0 < ncand; e0 += kThreads) {
+                    const int e = e0 + t;
+                    const unsigned long long ent = e < ncand ? (e0 == 0 ? e_pre : __ldcg(CAND + e)) : ~0ull;
+                    const long long d = (long long)(ent >> kPB);
+                    const bool fr = e < ncand && d <= T;
                     int tot;
                     const int pos = nfront + block_excl_count(fr, wcnt, tot);
-                    if (fr && pos % G == b) { myq[pos / G] = o; myqd[pos / G] = d; }
+                    if (fr) {
+                        const int o = (int)(ent & kPM);
+                        if (pos % G == b) { myq[pos / G] = o; myqd[pos / G] = d; }
+                        if (!SMEMP) atomicOr(&sfront[o >> 5], 1u << (o & 31));
+                    }
                     nfront += tot;
-                };
-#pragma unroll
-                for (int j = 0; j < kEPT; ++j) {
-                    if (j * kThreads < n) passC(t + j * kThreads, ee[j], eo[j], ed[j], j);
                 }
-                for (int e0 = kEPT * kThreads; e0 < n; e0 += kThreads) {
-                    const int e = e0 + t;
-                    int o = 0; long long d = 0;
-                    const bool el = e < n ? fetch(e, o, d) : false;
-                    passC(e, el, o, d, 0);
+                // this CTA's dirty words: the eligible objects that were not selected
+                for (int ww = warp; ww < nmy; ww += kWarps) {
+                    const unsigned mf = __ballot_sync(0xffffffffu, sld[ww * 32 + lane] <= T);
+                    if (lane == 0) sdirty_loc[ww] = sel_loc[ww] & ~mf;
                 }
-                myn = nfront > b ? (nfront - b - 1) / G + 1 : 0;
-                if (!cached) grid_arrive(P.bar + 1, bar2_target, G);
+                // the window doubles when it held fewer than K although more was eligible, halves above 4K
+                if (wC < P.sap_k && wC < wE) step *= 2;
+                else if (wC > 4 * P.sap_k && step > 1) step /= 2;
+                Tg = T + step;
+                const int myn = nfront > b ? (nfront - b - 1) / G + 1 : 0;
                 __syncthreads();
                 const long long tq1 = (b == 0 && t == 0) ? global_ns() : 0;
+                if (b == 0 && t == 0) st_acc[8] += tq1 - tq2;
                 // relax: the holders of this CTA's frontier objects, kRowsMax rows at a time
                 int qi = 0, si = 0;          // next frontier object of this CTA, next slot inside it
-                bool waited = false;
                 while (qi < myn) {
                     __syncthreads();
                     if (t == 0) {
-                        // the next <= kRowsMax slots of the queue (holders are looked up in parallel below)
+                        // the next <= kRowsMax slots of the queue
                         int nr = 0;
                         while (qi < myn && nr < kRowsMax) {
                             const int o = myq[qi];
                             const int s0 = capd ? __ldg(P.soff + o) : o, s1 = capd ? __ldg(P.soff + o + 1) : o + 1;
                             int s = s0 + si;
-                            for (; s < s1 && nr < kRowsMax; ++s) { rw_slot[nr] = s; rw_person[nr] = qi; ++nr; }
+                            for (; s < s1 && nr < kRowsMax; ++s) { rw_slot[nr] = s; rw_qi[nr] = qi; ++nr; }
                             if (s >= s1) { ++qi; si = 0; } else si = s - s0;
                         }
                         sh_i[5] = nr; sh_i[6] = qi; sh_i[7] = si;
@@ -800,87 +867,112 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
                     __syncthreads();
                     const int nr = sh_i[5];
                     qi = sh_i[6]; si = sh_i[7];
-                    if (t < nr) {
-                        // thr = C[i,o] + lambda[o] - d[o] - eps;  a relaxation of k gives  nd = C[i,k] + lambda[k] - thr
-                        const int q = rw_person[t], o = myq[q];
-                        const int i = owner_of(rw_slot[t]);
-                        long long thr = 0;
-                        if (i >= 0) {
-                            const long long lam_minus_d = SMEMP ? sarr[o] : __ldcg(P.lambda + o) - myqd[q];
-                            thr = (long long)(__ldg(rowptr(i) + o) - cmin) * S + lam_minus_d - eps;
+                    // holders (empty slots are squeezed out), in slot order
+                    {
+                        const int i = t < nr ? owner_of(rw_slot[t]) : -1;
+                        const unsigned m = __ballot_sync(0xffffffffu, i >= 0);
+                        if (t < 32) {
+                            if (i >= 0) { const int p = __popc(m & ((1u << lane) - 1u)); rw_person[p] = i; rw_slot2[p] = rw_slot[t]; rw_qi2[p] = rw_qi[t]; }
+                            if (t == 0) sh_i[3] = __popc(m);
                         }
-                        rw_thr[t] = thr;
-                        rw_person[t] = i;            // (this thread's own entry: the queue index is no longer needed)
                     }
-                    if (!waited) { if (grid_wait(P.bar + 1, bar2_target, P.gmm + 5, __LINE__)) LAP_ABORT(); waited = true; }     // includes a __syncthreads
-                    else __syncthreads();
+                    __syncthreads();
+                    const int nrv = sh_i[3];
+                    srows += nrv;
+                    // the entry C[i, o] of every row (for its threshold) is requested together with the first
+                    // wave of row data: one round trip for both
+                    int cval = 0;
+                    if (t < nrv) cval = __ldg(rowptr(rw_person[t]) + myq[rw_qi2[t]]);
                     const unsigned long long pol = l2_policy_evict_first();
-                    for (int rr = 0; rr < nr; ++rr) {
-                        if (rw_person[rr] < 0) continue;                 // empty slot
-                        ++srows;
-                        const int32_t *r = rowptr(rw_person[rr]);
-                        const long long thr = rw_thr[rr];
-                        const unsigned long long slot = (unsigned long long)rw_slot[rr];
-                        auto relax = [&](int k, int c, long long gk_or_lam, unsigned long long curkey) {
-                            if (SMEMP) {
-                                // g form: strictly below the label of the round start
-                                const long long v = (long long)(c - cmin) * S;
-                                if (v + gk_or_lam < thr) {
-                                    const long long nd = v + __ldcg(P.lambda + k) - thr;
-                                    if (nd >= kBidLimit) { atomicExch(P.gmm + 2, CYB_ERR_OVERFLOW); return; }
-                                    const unsigned long long key = ((unsigned long long)nd << kPB) | slot;
-                                    const unsigned long long prev = atomicMin(P.dkey + k, key);
-                                    if (key < prev && atomicMax(P.cstamp + k, rid) < rid) P.chg[lnext][atomicAdd(P.nchg + lnext, 1)] = k;
-                                }
-                            } else {
-                                if (gk_or_lam >= kInf / 2) return;
-                                const long long nd = (long long)(c - cmin) * S + gk_or_lam - thr;
-                                const long long rd = curkey == ~0ull ? kInf : (long long)(curkey >> kPB);
-                                bool go = nd < rd;
-                                if (!go && nd == rd) {
-                                    // equal labels only displace an entry written in THIS round (its writer is in the frontier)
-                                    const int ps = (int)(curkey & kPM);
-                                    if (ps < np) { const int po = obj_of_slot(ps); go = (sfront[po >> 5] >> (po & 31)) & 1u; }
-                                }
-                                if (go) {
-                                    if (nd >= kBidLimit) { atomicExch(P.gmm + 2, CYB_ERR_OVERFLOW); return; }
-                                    const unsigned long long key = ((unsigned long long)nd << kPB) | slot;
-                                    const unsigned long long prev = atomicMin(P.dkey + k, key);
-                                    if (key < prev && atomicMax(P.cstamp + k, rid) < rid) P.chg[lnext][atomicAdd(P.nchg + lnext, 1)] = k;
-                                }
-                            }
-                        };
-                        int jtail = 0;
-                        if (vec_ok) {
-                            const int4 *r4 = reinterpret_cast<const int4 *>(r);
-                            const int n4 = no >> 2;
-#pragma unroll 4
-                            for (int q = t; q < n4; q += kThreads) {
-                                const int4 c = ld_stream(r4 + q, pol);
-                                const int j = q << 2;
-                                if (SMEMP) {
-                                    const longlong2 a = *reinterpret_cast<const longlong2 *>(sarr + j);
-                                    const longlong2 bb = *reinterpret_cast<const longlong2 *>(sarr + j + 2);
-                                    relax(j, c.x, a.x, 0); relax(j + 1, c.y, a.y, 0); relax(j + 2, c.z, bb.x, 0); relax(j + 3, c.w, bb.y, 0);
-                                } else {
-                                    const longlong2 a = __ldcg(reinterpret_cast<const longlong2 *>(P.lambda + j));
-                                    const longlong2 bb = __ldcg(reinterpret_cast<const longlong2 *>(P.lambda + j + 2));
-                                    const ulonglong2 ka = __ldcg(reinterpret_cast<const ulonglong2 *>(P.dkey + j));
-                                    const ulonglong2 kb = __ldcg(reinterpret_cast<const ulonglong2 *>(P.dkey + j + 2));
-                                    relax(j, c.x, a.x, ka.x); relax(j + 1, c.y, a.y, ka.y); relax(j + 2, c.z, bb.x, kb.x); relax(j + 3, c.w, bb.y, kb.y);
-                                }
-                            }
-                            jtail = n4 << 2;
+                    const int n4 = vec_ok ? (no >> 2) : 0;
+                    const long long total4 = (long long)nrv * n4;
+                    int4 wv0[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const long long idx = (long long)t + (long long)u * kThreads;
+                        wv0[u] = make_int4(0, 0, 0, 0);
+                        if (idx < total4) {
+                            const int row = (int)(idx / n4), q = (int)(idx - (long long)row * n4);
+                            wv0[u] = ld_stream(reinterpret_cast<const int4 *>(rowptr(rw_person[row])) + q, pol);
                         }
-                        for (int j = jtail + t; j < no; j += kThreads) {
-                            if (SMEMP) relax(j, __ldg(r + j), sarr[j], 0);
-                            else relax(j, __ldg(r + j), __ldcg(P.lambda + j), __ldcg(P.dkey + j));
+                    }
+                    if (t < nrv) {
+                        // thr = C[i,o] + lambda[o] - d[o] - eps;  a relaxation of k gives  nd = C[i,k] + lambda[k] - thr
+                        const int q = rw_qi2[t], o = myq[q];
+                        const long long lam_minus_d = SMEMP ? sarr[o] : __ldcg(P.lambda + o) - myqd[q];
+                        rw_thr[t] = (long long)(cval - cmin) * S + lam_minus_d - eps;
+                    }
+                    __syncthreads();
+                    auto relax = [&](int k, int c, long long thr, unsigned long long slot, long long gk_or_lam, unsigned long long curkey) {
+                        if (SMEMP) {
+                            // g form: strictly below the label of the round start
+                            const long long v = (long long)(c - cmin) * S;
+                            if (v + gk_or_lam < thr) {
+                                const long long nd = v + __ldcg(P.lambda + k) - thr;
+                                if (nd >= kBidLimit) { atomicExch(P.gmm + 2, CYB_ERR_OVERFLOW); return; }
+                                const unsigned long long key = ((unsigned long long)nd << kPB) | slot;
+                                const unsigned long long prev = atomicMin(P.dkey + k, key);
+                                if (key < prev) atomicOr(NB + (k >> 5), 1u << (k & 31));
+                            }
+                        } else {
+                            if (gk_or_lam >= kInf / 2) return;
+                            const long long nd = (long long)(c - cmin) * S + gk_or_lam - thr;
+                            const long long rd = curkey == ~0ull ? kInf : (long long)(curkey >> kPB);
+                            bool go = nd < rd;
+                            if (!go && nd == rd) {
+                                // equal labels only displace an entry written in THIS round (its writer is in the frontier)
+                                const int ps = (int)(curkey & kPM);
+                                if (ps < np) { const int po = obj_of_slot(ps); go = (sfront[po >> 5] >> (po & 31)) & 1u; }
+                            }
+                            if (go) {
+                                if (nd >= kBidLimit) { atomicExch(P.gmm + 2, CYB_ERR_OVERFLOW); return; }
+                                const unsigned long long key = ((unsigned long long)nd << kPB) | slot;
+                                const unsigned long long prev = atomicMin(P.dkey + k, key);
+                                if (key < prev) atomicOr(NB + (k >> 5), 1u << (k & 31));
+                            }
+                        }
+                    };
+                    auto relax4 = [&](int row, int q, const int4 &c) {
+                        const long long thr = rw_thr[row];
+                        const unsigned long long slot = (unsigned long long)rw_slot2[row];
+                        const int j = q << 2;
+                        if (SMEMP) {
+                            const longlong2 a = *reinterpret_cast<const longlong2 *>(sarr + j);
+                            const longlong2 bb = *reinterpret_cast<const longlong2 *>(sarr + j + 2);
+                            relax(j, c.x, thr, slot, a.x, 0); relax(j + 1, c.y, thr, slot, a.y, 0);
+                            relax(j + 2, c.z, thr, slot, bb.x, 0); relax(j + 3, c.w, thr, slot, bb.y, 0);
+                        } else {
+                            const longlong2 a = __ldcg(reinterpret_cast<const longlong2 *>(P.lambda + j));
+                            const longlong2 bb = __ldcg(reinterpret_cast<const longlong2 *>(P.lambda + j + 2));
+                            const ulonglong2 ka = __ldcg(reinterpret_cast<const ulonglong2 *>(P.dkey + j));
+                            const ulonglong2 kb = __ldcg(reinterpret_cast<const ulonglong2 *>(P.dkey + j + 2));
+                            relax(j, c.x, thr, slot, a.x, ka.x); relax(j + 1, c.y, thr, slot, a.y, ka.y);
+                            relax(j + 2, c.z, thr, slot, bb.x, kb.x); relax(j + 3, c.w, thr, slot, bb.y, kb.y);
+                        }
+                    };
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const long long idx = (long long)t + (long long)u * kThreads;
+                        if (idx < total4) { const int row = (int)(idx / n4); relax4(row, (int)(idx - (long long)row * n4), wv0[u]); }
+                    }
+#pragma unroll 4
+                    for (long long idx = (long long)t + 4ll * kThreads; idx < total4; idx += kThreads) {
+                        const int row = (int)(idx / n4), q = (int)(idx - (long long)row * n4);
+                        relax4(row, q, ld_stream(reinterpret_cast<const int4 *>(rowptr(rw_person[row])) + q, pol));
+                    }
+                    // columns beyond the vector part
+                    for (int row = 0; row < nrv; ++row) {
+                        const int32_t *r = rowptr(rw_person[row]);
+                        for (int j = (n4 << 2) + t; j < no; j += kThreads) {
+                            if (SMEMP) relax(j, __ldg(r + j), rw_thr[row], (unsigned long long)rw_slot2[row], sarr[j], 0);
+                            else relax(j, __ldg(r + j), rw_thr[row], (unsigned long long)rw_slot2[row], __ldcg(P.lambda + j), __ldcg(P.dkey + j));
                         }
                     }
                 }
                 if (b == 0 && t == 0) { st_acc[9] += tq1 - tq0; st_acc[10] += global_ns() - tq1; }
+                __threadfence();
                 implicit = false;
-                lr = lnext;
+                rr3 = nb;
                 GRID_BARRIER();
                 status = __ldcg(P.gmm + 2);
                 if (status) break;
@@ -908,7 +1000,7 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
                 }
                 if (SMEMP) sarr[o] = lam;
             }
-            // S3b: CTA 0 traces the candidate paths (one warp each) and publishes the accepted moves
+            // S3b: CTA 0 traces the candidate paths (one lane of warp 0 each) and publishes the accepted moves
             if (b == 0) {
                 // candidate c = the free object of rank c by (label, object)
                 if (t < nfo) {
@@ -919,35 +1011,35 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
                 }
                 __syncthreads();
                 auto pred_of = [&](int o) -> int { return SMEMO ? spred[o] : (int)(__ldcg(P.dkey + o) & kPM); };
-                if (warp < want && lane == 0) {
-                    int o = pth_obj[warp], len = 0;
+                if (t < want) {
+                    int o = pth_obj[t], len = 0;
                     for (;;) {
-                        atomicMin(P.claim + o, cbase + warp);
+                        atomicMin(P.claim + o, cbase + t);
                         const int s = pred_of(o);
                         ++len;
-                        if (s >= np) { atomicMin(P.claim + no + (s - np), cbase + warp); break; }
+                        if (s >= np) { atomicMin(P.claim + no + (s - np), cbase + t); break; }
                         o = obj_of_slot(s);
                         if (len > np) break;                         // cannot happen (the tree has no cycles)
                     }
-                    pth_len[warp] = len;
+                    pth_len[t] = len;
                 }
                 __syncthreads();
-                if (warp < want && lane == 0) {
-                    int o = pth_obj[warp], ok = 1, len = 0;
+                if (t < want) {
+                    int o = pth_obj[t], ok = 1, len = 0;
                     for (;;) {
-                        ok &= (__ldcg(P.claim + o) == cbase + warp);
+                        ok &= (__ldcg(P.claim + o) == cbase + t);
                         const int s = pred_of(o);
-                        if (s >= np) { ok &= (__ldcg(P.claim + no + (s - np)) == cbase + warp); break; }
+                        if (s >= np) { ok &= (__ldcg(P.claim + no + (s - np)) == cbase + t); break; }
                         o = obj_of_slot(s);
                         if (++len > np) { ok = 0; break; }
                     }
-                    pth_ok[warp] = ok;
+                    pth_ok[t] = ok;
                 }
                 __syncthreads();
-                if (warp < want && lane == 0 && pth_ok[warp]) {
+                if (t < want && pth_ok[t]) {
                     int base = 0;
-                    for (int u = 0; u < warp; ++u) if (pth_ok[u]) base += pth_len[u];
-                    int o = pth_obj[warp];
+                    for (int u = 0; u < t; ++u) if (pth_ok[u]) base += pth_len[u];
+                    int o = pth_obj[t];
                     int slot = -1;
                     {
                         const int s0 = capd ? __ldg(P.soff + o) : o, s1 = capd ? __ldg(P.soff + o + 1) : o + 1;
@@ -1029,11 +1121,12 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
         P.stats[12] = (phases - 1) * (long long)np; P.stats[14] = searches; P.stats[15] = srounds;
         P.stats[16] = st_acc[3]; P.stats[17] = st_acc[4]; P.stats[18] = st_acc[5]; P.stats[19] = st_acc[6]; P.stats[20] = st_acc[7];
         P.stats[21] = paths; P.stats[22] = st_acc[9]; P.stats[23] = st_acc[10]; P.stats[24] = st_acc[11];
+        P.stats[25] = st_acc[2]; P.stats[26] = st_acc[8];
     }
 }
 
 struct SapLayout {
-    size_t list[3], rec[3], bidw[3], flag, slot_price, person_slot, minslot, slot_obj, dkey, cstamp, chg[3], claim, moves, small, total;
+    size_t list[3], rec[3], bidw[3], flag, slot_price, person_slot, minslot, slot_obj, dkey, chgbits[3], cand[3], claim, moves, small, total;
 };
 
 SapLayout sap_layout(int64_t np, int64_t no) {
@@ -1049,8 +1142,8 @@ SapLayout sap_layout(int64_t np, int64_t no) {
     L.minslot = take((size_t)no * 4);
     L.slot_obj = take((size_t)np * 4);
     L.dkey = take((size_t)no * 8);
-    L.cstamp = take((size_t)no * 4);
-    for (int k = 0; k < 3; ++k) L.chg[k] = take((size_t)no * 4);
+    for (int k = 0; k < 3; ++k) L.chgbits[k] = take((size_t)((no + 31) / 32) * 4);
+    for (int k = 0; k < 3; ++k) L.cand[k] = take((size_t)no * 8);
     L.claim = take((size_t)(no + kSapMax) * 4);
     L.moves = take((size_t)np * 16);
     L.small = take(2048);
@@ -1116,7 +1209,8 @@ extern "C" int cyb_lap_solve_i32(const int32_t *cost_dev, int64_t ld, int64_t n_
         P.list[k] = reinterpret_cast<int32_t *>(ws + L.list[k]);
         P.rec[k] = reinterpret_cast<int4 *>(ws + L.rec[k]);
         P.bidw[k] = reinterpret_cast<unsigned long long *>(ws + L.bidw[k]);
-        P.chg[k] = reinterpret_cast<int32_t *>(ws + L.chg[k]);
+        P.chgbits[k] = reinterpret_cast<unsigned *>(ws + L.chgbits[k]);
+        P.cand[k] = reinterpret_cast<unsigned long long *>(ws + L.cand[k]);
     }
     P.flag = reinterpret_cast<int32_t *>(ws + L.flag);
     P.slot_price = reinterpret_cast<long long *>(ws + L.slot_price);
@@ -1124,13 +1218,12 @@ extern "C" int cyb_lap_solve_i32(const int32_t *cost_dev, int64_t ld, int64_t n_
     P.minslot = reinterpret_cast<int32_t *>(ws + L.minslot);
     P.slot_obj = reinterpret_cast<int32_t *>(ws + L.slot_obj);
     P.dkey = reinterpret_cast<unsigned long long *>(ws + L.dkey);
-    P.cstamp = reinterpret_cast<int32_t *>(ws + L.cstamp);
     P.claim = reinterpret_cast<int32_t *>(ws + L.claim);
     P.moves = reinterpret_cast<int4 *>(ws + L.moves);
     P.bar = reinterpret_cast<unsigned int *>(ws + L.small);
     P.gmm = reinterpret_cast<int *>(ws + L.small + 16);
-    P.nchg = reinterpret_cast<int *>(ws + L.small + 64);
     P.nmoves = reinterpret_cast<int *>(ws + L.small + 96);
+    P.rstat = reinterpret_cast<int *>(ws + L.small + 1280);              // 3 x 32 bytes
     P.srcdone = reinterpret_cast<int32_t *>(ws + L.small + 128);          // kSapMax ints = 1 KB
     P.qcap = (int)((np + G - 1) / G);
     P.max_rounds = 2000ll * np + 100000;
@@ -1141,7 +1234,8 @@ extern "C" int cyb_lap_solve_i32(const int32_t *cost_dev, int64_t ld, int64_t n_
     P.theta = 64; P.eps0_div = 4;
     if (const char *e = getenv("CYB_LAP_THETA")) P.theta = std::max(2, atoi(e));
     if (const char *e = getenv("CYB_LAP_EPS0")) P.eps0_div = std::max(1, atoi(e));
-    P.sap_t = std::min(G, kSapMax); P.sap_k = 2 * G; P.multi = kMultiMax;
+    // (constants, not functions of the grid: the assignment must not depend on the grid size)
+    P.sap_t = 148; P.sap_k = 296; P.multi = kMultiMax;
     if (const char *e = getenv("CYB_LAP_SAP_T")) P.sap_t = std::max(1, std::min(kSapMax, atoi(e)));
     if (const char *e = getenv("CYB_LAP_SAP_K")) P.sap_k = std::max(1, atoi(e));
     if (const char *e = getenv("CYB_LAP_SAP_MULTI")) P.multi = std::max(1, std::min(kMultiMax, atoi(e)));
@@ -1152,8 +1246,10 @@ extern "C" int cyb_lap_solve_i32(const int32_t *cost_dev, int64_t ld, int64_t n_
     CYB_CUDA_CHECK(cudaMemsetAsync(total_dev, 0, sizeof(int64_t), stream));
     CYB_CUDA_CHECK(cudaMemsetAsync(stats_dev, 0, sizeof(int64_t) * CYB_LAP_NSTATS, stream));
 
+    P.wpc = (int)(((no + 31) / 32 + G - 1) / G);
     const size_t base_bytes = cyb::align_up((size_t)P.qcap * 8, 16) + cyb::align_up((size_t)P.qcap * 4, 16) +
-                              cyb::align_up((size_t)((no + 31) / 32) * 4, 16);
+                              2 * cyb::align_up((size_t)((no + 31) / 32) * 4, 16) + (size_t)P.wpc * 32 * 8 +
+                              2 * cyb::align_up((size_t)P.wpc * 4, 16);
     const size_t price_bytes = cyb::align_up((size_t)no * 8, 16);
     const size_t owner_bytes = (size_t)((np + 3) & ~3) * 4 + (size_t)((no + 3) & ~3) * 4 +
                                (slot_offset_dev ? (size_t)((no + 3) & ~3) * 4 : 0) + 16;

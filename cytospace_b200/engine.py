@@ -27,7 +27,7 @@ METRICS = {"Pearson_correlation": 0, "Spearman_correlation": 1, "Euclidean": 2}
 STAT_NAMES = ("status", "phases", "rounds", "bids", "passes", "cost_min", "cost_max", "scale",
               "grid", "smem_prices", "tail_mode", "max_bidders", "phase_scans", "tail_bids", "tails", "list_hits",
               "small_rounds", "ns_bid", "ns_barrier", "ns_resolve", "ns_tail", "paths", "ns_select", "ns_relax",
-              "ns_augment")
+              "ns_augment", "ns_sel_pass", "ns_sel_scan", "reserved")
 #: with the default solver (auction rounds + shortest-augmenting-path finish, csrc/lap_sap.cu) the tail
 #: columns read: tail_bids = rows relaxed in searches, tails = searches, list_hits = search rounds
 

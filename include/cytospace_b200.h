@@ -73,7 +73,7 @@ extern "C" {
                                operand error ~2^-22, fp32-accumulation bound         */
 
 /* number of int64 entries written to stats_dev by cyb_lap_solve_i32 */
-#define CYB_LAP_NSTATS 25
+#define CYB_LAP_NSTATS 28
 /* stats_dev layout:
  *  [0] status (0 ok)        [1] eps-scaling phases      [2] bidding rounds
  *  [3] bids (= row scans in rounds)  [4] full-matrix row scans (phase starts)

@@ -142,6 +142,7 @@ int sap_model_i32(int P, int O, const int32_t *m, int64_t ld, const int32_t *cap
             for (int o = 0; o < O; ++o) if (soff[o + 1] > soff[o]) REFRESH(o);
         }
         const int ph = (int)st[0] - 1;
+        int64_t step = eps;                     /* frontier window of the searches, adapted round by round */
         int64_t ph0[8]; memcpy(ph0, st, sizeof(st));
         if (ph < 64) { memset(sap_phase_log[ph], 0, sizeof(sap_phase_log[ph])); sap_phase_log[ph][0] = nfree; }
         while (nfree > 0) {
@@ -175,43 +176,73 @@ int sap_model_i32(int P, int O, const int32_t *m, int64_t ld, const int32_t *cap
                 for (int o = 0; o < O; ++o) if (d[o] < SAP_INF / 2) { dirty[ndirty++] = o; indirty[o] = 1; }
                 int want = nfree < nfo ? nfree : nfo;
                 if (multi <= 0) want = 1; else if (want > multi) want = (int)multi;
-                int64_t D = SAP_INF;
+                int64_t D = SAP_INF, T = -1, Tg = -1, Tnext = -1;
                 for (;;) {
                     /* D = the want-th smallest label of an object with a free slot */
                     int nc = 0;
                     for (int q = 0; q < nfo; ++q) if (d[fo[q]] < SAP_INF / 2) { cand[nc].d = d[fo[q]]; cand[nc].o = fo[q]; ++nc; }
                     qsort(cand, (size_t)nc, sizeof(lab_t), lab_cmp);
                     D = nc >= want ? cand[want - 1].d : SAP_INF;
-                    /* dirty objects that still matter: label < D and somebody to scan */
-                    int nd2 = 0; int64_t dmin = INT64_MAX, dmax = INT64_MIN, wsum = 0;
+                    if (D >= SAP_INF / 2) { rc = -6; goto done; }           /* every object with capacity is reached in round 0 */
+                    if (step > D) step = D;
+                    if (step < 1) step = 1;
+                    /* dirty objects that still matter (eligible): label < D and somebody to scan */
+                    int nd2 = 0;
                     for (int q = 0; q < ndirty; ++q) {
                         const int o = dirty[q];
-                        if (d[o] < D && (soff[o + 1] - soff[o]) - nfreeslot[o] > 0) {
-                            dirty[nd2++] = o;
-                            if (d[o] < dmin) dmin = d[o];
-                            if (d[o] > dmax) dmax = d[o];
-                            wsum += soff[o + 1] - soff[o];
-                        } else indirty[o] = 0;
+                        if (d[o] < D && (soff[o + 1] - soff[o]) - nfreeslot[o] > 0) dirty[nd2++] = o;
+                        else indirty[o] = 0;
                     }
                     ndirty = nd2;
                     if (ndirty == 0) break;
-                    /* threshold: 256 power-of-two bins over [dmin, dmax], first bin where the cumulative slot count reaches K */
-                    int64_t T = dmax;
-                    if (wsum > K) {
-                        int sh = 0;
-                        while (((dmax - dmin) >> sh) >= 256) ++sh;
-                        int64_t hist[256]; memset(hist, 0, sizeof(hist));
-                        for (int q = 0; q < ndirty; ++q) hist[(d[dirty[q]] - dmin) >> sh] += soff[dirty[q] + 1] - soff[dirty[q]];
-                        int64_t cum = 0; int bsel = 255;
-                        for (int bb = 0; bb < 256; ++bb) { cum += hist[bb]; if (cum >= K) { bsel = bb; break; } }
-                        T = dmin + (((int64_t)bsel + 1) << sh) - 1;
+                    /* Frontier = about K rows' worth of the smallest eligible labels, found in ONE pass over the
+                     * labels: candidates are the eligible objects with label <= Tg (a guess fixed at the end of the
+                     * previous round: its threshold plus `step`), histogrammed in 256 power-of-two bins over
+                     * [smallest eligible label, Tg]; T = upper edge of the first bin where the cumulative slot count reaches K (Tg when
+                     * the candidates hold fewer).  `step` doubles when the window held fewer than K although more was eligible, halves
+                     * above 4K (state kept across the searches of a phase).  When the guess selects nothing (first
+                     * round of a search, D moved below it) it restarts from the smallest eligible label. */
+                    int64_t wC = 0, wE = 0, dmin_el = SAP_INF;
+                    for (int attempt = 0; attempt < 2; ++attempt) {
+                        dmin_el = SAP_INF; wC = 0; wE = 0;
+                        if (Tg > D - 1) Tg = D - 1;                        /* every eligible label is below D */
+                        for (int q = 0; q < ndirty; ++q) {
+                            const int o = dirty[q];
+                            if (d[o] <= Tg) wC += soff[o + 1] - soff[o];
+                            wE += soff[o + 1] - soff[o];
+                            if (d[o] < dmin_el) dmin_el = d[o];
+                        }
+                        if (wC > 0) break;
+                        Tg = dmin_el + step;
                     }
+                    {
+                        const int64_t base = dmin_el;
+                        int sh = 0;
+                        while (((Tg - base) >> sh) >= 256) ++sh;
+                        int64_t hist[256]; memset(hist, 0, sizeof(hist));
+                        for (int q = 0; q < ndirty; ++q) {
+                            const int o = dirty[q];
+                            if (d[o] <= Tg) hist[(d[o] - base) >> sh] += soff[o + 1] - soff[o];
+                        }
+                        int64_t Tq = Tg;
+                        if (wC > K) {
+                            int64_t cum = 0; int bsel = 255;
+                            for (int bb = 0; bb < 256; ++bb) { cum += hist[bb]; if (cum >= K) { bsel = bb; break; } }
+                            Tq = base + (((int64_t)bsel + 1) << sh) - 1;
+                            if (Tq > Tg) Tq = Tg;
+                        }
+                        T = Tq;
+                    }
+                    if (wC < K && wC < wE) step *= 2;                      /* the window was too small (not: too little left) */
+                    else if (wC > 4 * K && step > 1) step /= 2;
+                    Tnext = T + step;
                     ++st[4];
                     memcpy(snap, d, sizeof(int64_t) * (size_t)O);
                     int nkeep = 0, nfront = 0;
                     for (int q = 0; q < ndirty; ++q) { const int o = dirty[q]; if (snap[o] <= T) front[nfront++] = o; else dirty[nkeep++] = o; }
                     ndirty = nkeep;
                     for (int q = 0; q < nfront; ++q) indirty[front[q]] = 0;
+                    Tg = Tnext;
                     int64_t rows = 0;
                     for (int q = 0; q < nfront; ++q) {
                         const int o = front[q];
@@ -235,7 +266,6 @@ int sap_model_i32(int P, int O, const int32_t *m, int64_t ld, const int32_t *cap
                     }
                     st[5] += rows;
                 }
-                if (D >= SAP_INF / 2) { rc = -6; goto done; }
                 /* candidates: free objects with label <= D by (label, object); rank = position */
                 int nc = 0;
                 for (int q = 0; q < nfo; ++q) if (d[fo[q]] <= D) { cand[nc].d = d[fo[q]]; cand[nc].o = fo[q]; ++nc; }

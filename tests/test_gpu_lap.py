@@ -78,45 +78,46 @@ def _with_env(env, fn):
                 os.environ[k] = v
 
 
-@pytest.mark.parametrize("tail", [0, 2, 32])
-def test_matches_cpu_model_of_the_device_algorithm(engine, tail):
-    """Same tie-breaks as oracle/auction_model.c: identical assignment, not just identical total.  The
-    in-CTA tail runs the same synchronous rounds as the grid, so the result equals the pure-Jacobi
-    model wherever the switch to the tail happens."""
+SAP_KNOBS = [dict(theta=64, sap_t=148, K=296, multi=32),      # the defaults on a 148-SM device
+             dict(theta=4, sap_t=8, K=16, multi=1),            # one path per search, tiny rounds (threshold histogram in use)
+             dict(theta=256, sap_t=40, K=64, multi=8),
+             dict(theta=16, sap_t=256, K=100000, multi=32)]    # every dirty object each round (Bellman-Ford rounds)
+
+
+def _sap_env(k):
+    return {"CYB_LAP_THETA": k["theta"], "CYB_LAP_SAP_T": k["sap_t"], "CYB_LAP_SAP_K": k["K"], "CYB_LAP_SAP_MULTI": k["multi"]}
+
+
+@pytest.mark.parametrize("knobs", SAP_KNOBS, ids=lambda k: "t{sap_t}_k{K}_m{multi}_th{theta}".format(**k))
+def test_matches_cpu_model_of_the_device_algorithm(engine, knobs):
+    """Same rules as oracle/sap_model.c (auction rounds + shortest-augmenting-path finish: frontier threshold,
+    strict relaxations, (label, slot) tie-breaks, path claims): identical assignment, identical counters --
+    not just an identical total."""
     rng = np.random.default_rng(3)
     cap = rng.integers(0, 6, 70).astype(np.int32)
     m = rng.integers(-1000, 1000, (int(cap.sum()), 70), dtype=np.int32)
-    res, po = _with_env({"CYB_LAP_TAIL": tail, "CYB_LAP_TAIL_MODE": 1}, lambda: solve_and_check(engine, m, cap))
-    po_model, so_model, tot_model, _, _, _ = oracle.auction_model(m, cap, tail_t=0)
-    assert res.total == tot_model and np.array_equal(po, po_model)
-    assert np.array_equal(res.slot_owner.cpu().numpy(), so_model)
-    sq = rng.integers(0, 50, (90, 90), dtype=np.int32)                            # unit capacities, many ties
-    res, po = _with_env({"CYB_LAP_TAIL": tail, "CYB_LAP_TAIL_MODE": 1}, lambda: solve_and_check(engine, sq))
-    assert np.array_equal(po, oracle.auction_model(sq, tail_t=0)[0])
+    cases = [(m, cap), (rng.integers(0, 50, (90, 90), dtype=np.int32), None),          # unit capacities, many ties
+             (rng.integers(-100_000, 100_000, (700, 700), dtype=np.int32), None)]
+    for mat, cp in cases:
+        res, po = _with_env(_sap_env(knobs), lambda: solve_and_check(engine, mat, cp))
+        po_model, so_model, tot_model, lam_model, st, _ = oracle.sap_model(mat, cp, **knobs)
+        assert res.total == tot_model and np.array_equal(po, po_model)
+        assert np.array_equal(res.slot_owner.cpu().numpy(), so_model)
+        assert np.array_equal(res.price.cpu().numpy(), lam_model)
+        assert (res.stats["tails"], res.stats["list_hits"], res.stats["tail_bids"], res.stats["paths"]) == \
+            (st[3], st[4], st[5], st[6]), "searches / search rounds / rows relaxed / paths differ from the model"
 
 
-def test_gauss_seidel_tail_mode_matches_its_model(engine):
-    """The alternative tail (CYB_LAP_TAIL_MODE=0: one bid at a time, FIFO) against the model's FIFO tail."""
-    rng = np.random.default_rng(3)
-    cap = rng.integers(0, 6, 70).astype(np.int32)
-    m = rng.integers(-1000, 1000, (int(cap.sum()), 70), dtype=np.int32)
-    res, po = _with_env({"CYB_LAP_TAIL": 2, "CYB_LAP_TAIL_MODE": 0}, lambda: solve_and_check(engine, m, cap))
-    po_model, so_model, tot_model, _, _, _ = oracle.auction_model(m, cap, tail_t=2)
-    assert res.total == tot_model and np.array_equal(po, po_model)
-    assert np.array_equal(res.slot_owner.cpu().numpy(), so_model)
-
-
-@pytest.mark.parametrize("mode,tail", [(0, 8), (1, 8), (1, 32), (1, 0)])
-def test_tail_modes_reach_the_same_optimum(engine, mode, tail):
+@pytest.mark.parametrize("knobs", SAP_KNOBS[1:], ids=lambda k: "t{sap_t}_k{K}_m{multi}_th{theta}".format(**k))
+def test_search_knobs_reach_the_same_optimum(engine, knobs):
     sc, st, cn = syn.structured_counts(1200, 200, 800, 6, seed=1004)
     from oracle import cost_oracle as co
     compact = co.cost_matrix_i32(co.normalize_data(sc), co.normalize_data(st))
     m = np.ascontiguousarray(compact.T)
-    res, _ = _with_env({"CYB_LAP_TAIL": tail, "CYB_LAP_TAIL_MODE": mode},
-                       lambda: solve_and_check(engine, m, cn.astype(np.int32)))
+    res, _ = _with_env(_sap_env(knobs), lambda: solve_and_check(engine, m, cn.astype(np.int32)))
     assert res.total == oracle.lapjv_i32(compact, np.repeat(np.arange(200, dtype=np.int32), 6))[2][0]
     sq = syn.uniform_cost_i32(700, seed=3)
-    res, _ = _with_env({"CYB_LAP_TAIL": tail, "CYB_LAP_TAIL_MODE": mode}, lambda: solve_and_check(engine, sq))
+    res, _ = _with_env(_sap_env(knobs), lambda: solve_and_check(engine, sq))
     assert res.total == oracle.lapjv_i32(sq)[2][0]
 
 
@@ -240,47 +241,29 @@ def test_certificate_tiled_variant_above_12288_objects(engine):
     assert engine.lap_check(dev, res)["capacity_mismatch"] == 2
 
 
-@pytest.mark.parametrize("approx", [1, 0])
-@pytest.mark.parametrize("tail_mode", [0, 1])
-def test_l2_price_paths_on_small_problems(engine, lap_golden, approx, tail_mode):
-    """The code paths of problems too large for shared-memory prices (50k objects), forced on small
-    inputs: 64-bit prices streamed from L2 (approx=0) and the 32-bit price-prefix scan with exact
-    re-evaluation of the candidates (approx=1).  Same totals, same assignment as the default path."""
-    env = {"CYB_LAP_SMEM_PRICES": 0, "CYB_LAP_APPROX": approx, "CYB_LAP_TAIL_MODE": tail_mode}
+@pytest.mark.parametrize("smem_owner", [1, 0])
+@pytest.mark.parametrize("smem_prices", [1, 0])
+def test_memory_variants_on_small_problems(engine, lap_golden, smem_prices, smem_owner):
+    """The code paths of problems too large for shared memory, forced on small inputs: prices / search labels
+    streamed from L2 (50k objects: CYB_LAP_SMEM_PRICES=0) and slot owners / tree predecessors read from global
+    memory (25k and up: CYB_LAP_SMEM_OWNER=0).  Same totals AND the same assignment as the default path."""
+    env = {"CYB_LAP_SMEM_PRICES": smem_prices, "CYB_LAP_SMEM_OWNER": smem_owner}
     for name in LAP_NAMES:
         cost = lap_golden[f"{name}_cost"]
         res, po = _with_env(env, lambda: solve_and_check(engine, cost))
-        assert res.total == int(lap_golden[f"{name}_opt"]) and res.stats["smem_prices"] == 0
+        assert res.total == int(lap_golden[f"{name}_opt"]) and res.stats["smem_prices"] == smem_prices
     rng = np.random.default_rng(12)
     cap = rng.integers(0, 5, 300).astype(np.int32)
     m = rng.integers(-200_000, 200_000, (int(cap.sum()), 300), dtype=np.int32)
-    ref, po_ref = _with_env({"CYB_LAP_TAIL_MODE": tail_mode}, lambda: solve_and_check(engine, m, cap))
+    ref, po_ref = solve_and_check(engine, m, cap)
     res, po = _with_env(env, lambda: solve_and_check(engine, m, cap))
     assert res.total == ref.total and np.array_equal(po, po_ref)
-    sq = syn.uniform_cost_i32(1500, seed=9, high=3000)                    # many near-ties: exercises the fallback
-    ref, po_ref = _with_env({"CYB_LAP_TAIL_MODE": tail_mode}, lambda: solve_and_check(engine, sq))
+    row_map = np.repeat(np.arange(300, dtype=np.int32), cap)
+    assert res.total == oracle.lapjv_i32(np.ascontiguousarray(m.T), row_map)[2][0]
+    sq = syn.uniform_cost_i32(1500, seed=9, high=3000)                    # many near-ties
+    ref, po_ref = solve_and_check(engine, sq)
     res, po = _with_env(env, lambda: solve_and_check(engine, sq))
     assert res.total == ref.total == oracle.lapjv_i32(sq)[2][0] and np.array_equal(po, po_ref)
-    tie = np.zeros((200, 200), np.int32)                                   # every column ties: always falls back
+    tie = np.zeros((200, 200), np.int32)                                   # every column ties
     res, _ = _with_env(env, lambda: solve_and_check(engine, tie))
     assert res.total == 0
-
-
-@pytest.mark.parametrize("tail_mode", [0, 1])
-@pytest.mark.parametrize("smem_prices", [1, 0])
-def test_without_shared_memory_owner_replicas(engine, tail_mode, smem_prices):
-    """Problems too large for the slot-owner replicas (25k and up) read owners / cheapest slots from global
-    memory, kept identical by every CTA's replay: forced here on small capacitated and unit problems."""
-    env = {"CYB_LAP_SMEM_OWNER": 0, "CYB_LAP_SMEM_PRICES": smem_prices, "CYB_LAP_TAIL_MODE": tail_mode}
-    rng = np.random.default_rng(21)
-    cap = rng.integers(0, 7, 250).astype(np.int32)
-    m = rng.integers(-300_000, 300_000, (int(cap.sum()), 250), dtype=np.int32)
-    ref, po_ref = _with_env({"CYB_LAP_TAIL_MODE": tail_mode}, lambda: solve_and_check(engine, m, cap))
-    res, po = _with_env(env, lambda: solve_and_check(engine, m, cap))
-    assert res.total == ref.total and np.array_equal(po, po_ref)
-    row_map = np.repeat(np.arange(250, dtype=np.int32), cap)
-    assert res.total == oracle.lapjv_i32(np.ascontiguousarray(m.T), row_map)[2][0]
-    sq = syn.uniform_cost_i32(1200, seed=4)
-    ref, po_ref = _with_env({"CYB_LAP_TAIL_MODE": tail_mode}, lambda: solve_and_check(engine, sq))
-    res, po = _with_env(env, lambda: solve_and_check(engine, sq))
-    assert res.total == ref.total == oracle.lapjv_i32(sq)[2][0] and np.array_equal(po, po_ref)

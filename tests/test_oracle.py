@@ -79,6 +79,58 @@ def test_capacitated_auction_model_equals_expanded_jv(n_obj, seed, high, tail):
     assert max(h[i, po[i]] - min(h[i]) for i in range(n)) <= 1
 
 
+@settings(max_examples=80, deadline=None)
+@given(st.integers(1, 10), st.integers(0, 2 ** 31 - 1), st.sampled_from([2, 10, 1000, 2_000_000]),
+       st.sampled_from([(1, 1, 1), (4, 3, 1), (4, 8, 4), (64, 100000, 32), (2, 2, 32)]), st.sampled_from([2, 4, 64]))
+def test_sap_finish_model_equals_expanded_jv(n_obj, seed, high, knobs, theta):
+    """The hybrid the device runs (auction rounds + shortest-augmenting-path finish, oracle/sap_model.c) reaches
+    the optimum of the reference's expanded LAP (LAS:63-66) for every search schedule (switch point, rows per
+    round, paths per search), including empty spots, and leaves an eps = 1 certificate."""
+    sap_t, K, multi = knobs
+    rng = np.random.default_rng(seed)
+    cap = rng.integers(0, 5, n_obj).astype(np.int32)
+    if cap.sum() == 0:
+        cap[0] = 1
+    n = int(cap.sum())
+    compact = rng.integers(-high, high, (n_obj, n), dtype=np.int32)           # spots x cells (reference orientation)
+    row_map = np.repeat(np.arange(n_obj, dtype=np.int32), cap)
+    want = oracle.lapjv_i32(compact, row_map)[2][0]
+    po, so, tot, lam, stats, _ = oracle.sap_model(np.ascontiguousarray(compact.T), cap, theta=theta, sap_t=sap_t, K=K, multi=multi)
+    assert tot == want
+    assert np.array_equal(np.bincount(po, minlength=n_obj), cap)
+    soff = np.concatenate([[0], np.cumsum(cap)])
+    for o in range(n_obj):
+        assert sorted(so[soff[o]:soff[o + 1]].tolist()) == sorted(np.nonzero(po == o)[0].tolist())
+    h = (compact.T.astype(object) - int(compact.min())) * (n + 1) + np.array([int(x) for x in lam], dtype=object)[None, :]
+    assert max(h[i, po[i]] - min(h[i]) for i in range(n)) <= 1
+
+
+@pytest.mark.parametrize("name", LAP_NAMES)
+def test_sap_finish_model_on_golden_instances(lap_golden, name):
+    cost = lap_golden[f"{name}_cost"]
+    opt = int(lap_golden[f"{name}_opt"])
+    for kw in (dict(), dict(sap_t=4, K=8, multi=1, theta=4), dict(sap_t=0)):      # sap_t = 0: pure auction
+        po, so, tot, lam, stats, _ = oracle.sap_model(cost, **kw)
+        assert tot == opt and sorted(po.tolist()) == list(range(cost.shape[0]))
+        assert np.array_equal(so[po], np.arange(cost.shape[0]))
+
+
+def test_sap_finish_needs_far_fewer_dependent_steps_than_the_auction_tail():
+    """The measurement behind the device design: on a structured instance the Gauss-Seidel
+    auction tail makes thousands of dependent single bids; the search finish replaces them by a few hundred
+    grid-wide rounds."""
+    from cytospace_b200 import synthetic as syn
+    from oracle import cost_oracle as co
+    sc, st_, cn = syn.structured_counts(1500, 1500, 1500, 1, seed=1002)
+    cost = co.cost_matrix_i32(co.normalize_data(sc), co.normalize_data(st_))
+    a = oracle.auction_model(cost, tail_t=8)
+    s = oracle.sap_model(cost, theta=64, sap_t=148, K=296, multi=32)
+    assert a[2] == s[2] == oracle.lapjv_i32(cost)[2][0]
+    auction_dependent = int(a[4][1]) + int(a[4][5])           # grid rounds + tail bids
+    sap_dependent = int(s[4][1]) + int(s[4][4])               # grid rounds + search rounds
+    assert sap_dependent * 4 < auction_dependent, (sap_dependent, auction_dependent)
+
+
 def test_jv_row_map_equals_materialised_expansion():
     rng = np.random.default_rng(3)
     compact = rng.integers(-1000, 1000, (7, 21), dtype=np.int32)
