@@ -71,31 +71,81 @@ def assign_ranks(sizes, world: int) -> list[int]:
     return owner
 
 
-def _dist_state(group=None):
+class TorchTransport:
+    """Data plane over a ``torch.distributed`` process group (NCCL on GPUs, gloo in the CPU tests).
+    Ranks are GROUP ranks; they are translated to global ranks where the API wants them."""
+
+    def __init__(self, dist, group=None):
+        self.dist, self.group = dist, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+
+    def _g(self, r):
+        return r if self.group is None else self.dist.get_global_rank(self.group, r)
+
+    def bcast_object(self, obj, root=0):
+        box = [obj]
+        self.dist.broadcast_object_list(box, src=self._g(root), group=self.group)
+        return box[0]
+
+    def broadcast(self, t, root=0):
+        self.dist.broadcast(t, src=self._g(root), group=self.group)
+
+    def isend(self, t, dst):
+        return self.dist.isend(t, dst=self._g(dst), group=self.group)
+
+    def recv(self, t, src):
+        self.dist.recv(t, src=self._g(src), group=self.group)
+
+    def all_gather(self, send):
+        out = [torch.empty_like(send) for _ in range(self.world)]
+        self.dist.all_gather(out, send, group=self.group)
+        return out
+
+
+def _transport(group=None, transport=None):
+    if transport is not None:
+        return transport
     import torch.distributed as dist
-    if dist.is_available() and dist.is_initialized():
-        return dist, dist.get_rank(group), dist.get_world_size(group)
-    return None, 0, 1
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        return TorchTransport(dist, group)
+    return None
 
 
-def solve_chunks(engine, sc_np, st_np, plan: list[Chunk], log_tpm: bool = False, group=None, **assign_kw):
+#: bytes moved by the last distributed solve on this rank (bench.py reports them)
+last_traffic = {"bcast_bytes": 0, "p2p_bytes": 0, "gather_bytes": 0}
+
+
+def solve_chunks(engine, sc_np, st_np, plan: list[Chunk], log_tpm: bool = False, group=None, transport=None,
+                 **assign_kw):
     """Solve every chunk; returns ``mapped_st_index`` (list of int per cell, chunk-local spot index
     as in cytospace.py:455-459) for each chunk, on every rank.
 
-    Single process: chunks run back to back on ``engine``.  With a process group: rank 0 passes the
-    matrices (other ranks may pass ``None``), chunks are dealt by ``assign_ranks``.
-    ``assign_kw`` (``metric=``, ``cspr_seed=``) goes to ``engine.assign`` unchanged (rank 0's values)."""
-    dist, rank, world = _dist_state(group)
-    if world == 1:
+    Single process: chunks run back to back on ``engine``.  With a process group (or an explicit
+    ``transport``, e.g. ``dist_native.NativeTransport``: NCCL through the C ABI): rank 0 passes the
+    matrices -- host arrays or tensors already on its GPU; other ranks may pass ``None`` -- and chunks are
+    dealt by ``assign_ranks``.  ``assign_kw`` (``metric=``, ``cspr_seed=``) goes to ``engine.assign``
+    unchanged (rank 0's values)."""
+    tp = _transport(group, transport)
+    if tp is None:
         out = []
+        sc_dev = st_dev = None
+        if len(plan) > 1:
+            # upload once, slice the chunks' columns on the device
+            sc_dev, st_dev = engine.to_device(sc_np), engine.to_device(st_np)
         for ch in plan:
-            sc = sc_np[:, ch.sc_index] if len(ch.sc_index) != sc_np.shape[1] or not _is_arange(ch.sc_index) else sc_np
-            st = st_np if ch.st_index is None else st_np[:, ch.st_index]
-            spot_of_cell, _, _ = engine.assign(np.ascontiguousarray(sc), np.ascontiguousarray(st), ch.cn,
-                                               log_tpm=log_tpm, **assign_kw)
+            if sc_dev is None:
+                sc, st = sc_np, st_np
+                if len(ch.sc_index) != sc_np.shape[1] or not _is_arange(ch.sc_index):
+                    sc = _columns(engine, engine.to_device(sc_np), ch.sc_index)
+                if ch.st_index is not None:
+                    st = _columns(engine, engine.to_device(st_np), ch.st_index)
+            else:
+                sc = _columns(engine, sc_dev, ch.sc_index)
+                st = st_dev if ch.st_index is None else _columns(engine, st_dev, ch.st_index)
+            spot_of_cell, _, _ = engine.assign(sc, st, ch.cn, log_tpm=log_tpm, **assign_kw)
             out.append(spot_of_cell.cpu().numpy().tolist())
         return out
-    return _solve_chunks_distributed(dist, rank, world, engine, sc_np, st_np, plan, log_tpm, group, assign_kw)
+    return _solve_chunks_distributed(tp, engine, sc_np, st_np, plan, log_tpm, assign_kw)
 
 
 def _is_arange(idx) -> bool:
@@ -103,52 +153,79 @@ def _is_arange(idx) -> bool:
     return idx.size > 0 and idx[0] == 0 and np.array_equal(idx, np.arange(idx.size))
 
 
-def _solve_chunks_distributed(dist, rank, world, engine, sc_np, st_np, plan, log_tpm, group, assign_kw):
+def _columns(engine, x_dev, idx):
+    """x_dev[:, idx] as a contiguous device matrix (device gather: the host never touches the columns)."""
+    idx = np.asarray(idx)
+    if idx.size == x_dev.shape[1] and _is_arange(idx):
+        return x_dev
+    return x_dev.index_select(1, torch.from_numpy(idx.astype(np.int64)).to(x_dev.device))
+
+
+def _solve_chunks_distributed(tp, engine, sc_np, st_np, plan, log_tpm, assign_kw):
     dev = engine.device
+    rank, world = tp.rank, tp.world
+    traffic = {"bcast_bytes": 0, "p2p_bytes": 0, "gather_bytes": 0}
     # plan and shapes travel as one small object broadcast (host metadata, not the data path)
-    meta = [None]
+    meta = None
     if rank == 0:
-        meta[0] = (plan, int(sc_np.shape[0]), int(st_np.shape[1]), str(sc_np.dtype), dict(assign_kw))
-    dist.broadcast_object_list(meta, src=0, group=group)
-    plan, n_genes, n_spots, dt, assign_kw = meta[0]
+        # float32 stays float32; anything else (float64, integer counts) is float64 as in the reference
+        dt = "float32" if str(sc_np.dtype).endswith("float32") and str(st_np.dtype).endswith("float32") else "float64"
+        meta = (plan, int(sc_np.shape[0]), int(st_np.shape[1]), dt, dict(assign_kw))
+    plan, n_genes, n_spots, dt, assign_kw = tp.bcast_object(meta, root=0)
     tdt = torch.float64 if dt == "float64" else torch.float32
+    esz = 8 if dt == "float64" else 4
     owner = assign_ranks([c.n for c in plan], world)
     shared_st = any(c.st_index is None for c in plan)
+
+    # rank 0: ONE upload of each matrix (pinned staging ring); chunk columns are gathered on the device
+    sc_dev = st_dev = None
+    if rank == 0:
+        sc_dev = engine.to_device(sc_np, tdt)
+        st_dev = engine.to_device(st_np, tdt)
 
     st_all = None
     if shared_st:
         # ONE broadcast of the ST block every chunk reads (cytospace.py:438)
-        if rank == 0:
-            st_all = torch.from_numpy(np.ascontiguousarray(st_np)).to(tdt).to(dev)
-        else:
-            st_all = torch.empty((n_genes, n_spots), dtype=tdt, device=dev)
-        dist.broadcast(st_all, src=0, group=group)
+        st_all = st_dev if rank == 0 else torch.empty((n_genes, n_spots), dtype=tdt, device=dev)
+        tp.broadcast(st_all, root=0)
+        traffic["bcast_bytes"] += n_genes * n_spots * esz
 
-    # per-chunk column blocks: point-to-point from rank 0 to the owner
+    # per-chunk column blocks: point-to-point from rank 0 to the owner; at most two blocks in flight, each
+    # freed as soon as its send has completed
     mine = {}
-    pending = []
+    inflight = []
     for ch in plan:
         o = owner[ch.idx]
         need_st = ch.st_index is not None
         if rank == 0:
-            sc_blk = torch.from_numpy(np.ascontiguousarray(sc_np[:, ch.sc_index])).to(tdt).to(dev)
-            st_blk = torch.from_numpy(np.ascontiguousarray(st_np[:, ch.st_index])).to(tdt).to(dev) if need_st else None
+            blocks = [_columns(engine, sc_dev, ch.sc_index)]
+            if need_st:
+                blocks.append(_columns(engine, st_dev, ch.st_index))
             if o == 0:
-                mine[ch.idx] = (sc_blk, st_blk)
+                mine[ch.idx] = (blocks[0], blocks[1] if need_st else None)
             else:
-                pending.append((dist.isend(sc_blk, dst=o, group=group), sc_blk))
-                if need_st:
-                    pending.append((dist.isend(st_blk, dst=o, group=group), st_blk))
+                for blk in blocks:
+                    blk = blk.contiguous()
+                    inflight.append((tp.isend(blk, o), blk))
+                    traffic["p2p_bytes"] += blk.numel() * esz
+                while len(inflight) > 2:
+                    req, _blk = inflight.pop(0)
+                    req.wait()
         elif o == rank:
             sc_blk = torch.empty((n_genes, ch.n), dtype=tdt, device=dev)
-            dist.recv(sc_blk, src=0, group=group)
+            tp.recv(sc_blk, 0)
             st_blk = None
             if need_st:
                 st_blk = torch.empty((n_genes, len(ch.st_index)), dtype=tdt, device=dev)
-                dist.recv(st_blk, src=0, group=group)
+                tp.recv(st_blk, 0)
             mine[ch.idx] = (sc_blk, st_blk)
-    for req, _keep in pending:
+            traffic["p2p_bytes"] += (sc_blk.numel() + (st_blk.numel() if need_st else 0)) * esz
+    for req, _blk in inflight:
         req.wait()
+    inflight.clear()
+    if rank == 0 and not any(owner[c.idx] == 0 and c.st_index is None for c in plan):
+        st_dev = None
+    sc_dev = None                                  # rank 0 keeps only its own chunks' blocks
 
     # solve: no communication
     results = {}
@@ -159,6 +236,7 @@ def _solve_chunks_distributed(dist, rank, world, engine, sc_np, st_np, plan, log
         spot_of_cell, _, _ = engine.assign(sc_blk, st_all if st_blk is None else st_blk, ch.cn, log_tpm=log_tpm,
                                            **assign_kw)
         results[ch.idx] = spot_of_cell.to(torch.int32)
+        del sc_blk, st_blk
 
     # one all-gather of the assignment indices (padded to the largest per-rank total)
     per_rank = [sum(c.n for c in plan if owner[c.idx] == r) for r in range(world)]
@@ -169,8 +247,8 @@ def _solve_chunks_distributed(dist, rank, world, engine, sc_np, st_np, plan, log
         if owner[ch.idx] == rank:
             send[pos:pos + ch.n] = results[ch.idx]
             pos += ch.n
-    gathered = [torch.empty_like(send) for _ in range(world)]
-    dist.all_gather(gathered, send, group=group)
+    gathered = tp.all_gather(send)
+    traffic["gather_bytes"] += send.numel() * 4 * world
     host = [g.cpu().numpy() for g in gathered]
     cursor = [0] * world
     out = []
@@ -178,4 +256,5 @@ def _solve_chunks_distributed(dist, rank, world, engine, sc_np, st_np, plan, log
         r = owner[ch.idx]
         out.append(host[r][cursor[r]:cursor[r] + ch.n].tolist())
         cursor[r] += ch.n
+    last_traffic.update(traffic)
     return out

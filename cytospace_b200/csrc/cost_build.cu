@@ -35,7 +35,8 @@ constexpr int kStatRows = 8;        // row lanes per stats CTA
 template <typename T>
 __device__ __forceinline__ double load_clean(const T *p) {
     const double v = (double)__ldg(p);
-    return (v != v) ? 0.0 : v;      // np.nan_to_num on the input (common.py:143)
+    if (v != v) return 0.0;                                          // np.nan_to_num on the input (common.py:143):
+    return isinf(v) ? copysign(1.7976931348623157e308, v) : v;       // nan -> 0, +-inf -> +-DBL_MAX
 }
 
 // normalize_data (common.py:142-147): x * (1e6 / colsum), log2(. + 1), nan -> 0.

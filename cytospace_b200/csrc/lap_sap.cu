@@ -163,6 +163,9 @@ __device__ __forceinline__ Best combine(const Best &a, const Best &b) {
     else       { r.b1 = a.b1; r.j1 = a.j1; r.b2 = b.b1 < a.b2 ? b.b1 : a.b2; }
     return r;
 }
+__device__ __noinline__ void report_timeout(int line, unsigned v, unsigned target) {
+    printf("[cyb lap] CTA %d: wait at line %d timed out (counter %u, target %u)\n", blockIdx.x, line, v, target);
+}
 // Grid barrier with a watchdog.  `abortf` is a global flag: a CTA that waits longer than 5 s (only a
 // protocol bug can do that) raises it, every other CTA leaves its wait when it sees it, and the kernel
 // returns CYB_ERR_NOT_CONVERGED instead of hanging the GPU.  Returns true when the launch is aborted.
@@ -179,7 +182,7 @@ __device__ __forceinline__ bool spin_until(unsigned int *bar, unsigned int targe
             const long long now = global_ns();
             if (!t0) t0 = now;
             if (a != 0 || now - t0 > 5000000000ll) {
-                if (a == 0) printf("[cyb lap] CTA %d: wait at line %d timed out (counter %u, target %u)\n", blockIdx.x, line, v, target);
+                if (a == 0) report_timeout(line, v, target);
                 atomicExch(abortf, 1);
                 dead = true;
                 break;
@@ -192,11 +195,11 @@ __device__ __forceinline__ bool grid_barrier(unsigned int *bar, unsigned int &ta
     __syncthreads();
     bool dead = false;
     if (threadIdx.x == 0) {
+        // release / acquire on the counter itself (no separate fences): the CTA's writes, ordered before this
+        // thread by the bar.sync above, are published by the release; the acquire load in spin_until pairs with it
         target += G;
-        __threadfence();
-        atomicAdd(bar, 1u);
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
         dead = spin_until(bar, target, abortf, line);
-        __threadfence();
     }
     return __syncthreads_or(dead);
 }
@@ -363,6 +366,7 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
 
     __shared__ long long red_b1[32], red_b2[32];
     __shared__ int red_j[32], wcnt[32];
+    __shared__ long long st_tm[8];
     __shared__ long long st_acc[12];   // bids, max bidders, -, small rounds, ns bid / barrier / replay / sap, relax hits, sap ns select, sap ns trace
     __shared__ int ssrc[kSapMax], sfo[kSapMax];
     __shared__ long long sfo_d[kSapMax];
@@ -582,7 +586,7 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
 
         // ---- shortest-augmenting-path finish -------------------------------------
         long long step = eps;                    // frontier window of the searches, adapted round by round
-        const long long ts0 = (b == 0 && t == 0) ? global_ns() : 0;
+        if (b == 0 && t == 0) st_tm[0] = global_ns();
         if (F > 0) {
             if (t < F) ssrc[t] = __ldcg(P.list[cur] + t);
             __syncthreads();
@@ -655,7 +659,7 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
             long long Tg = -1;                   // this round's guess: candidates are the eligible labels <= Tg
             for (;;) {
                 ++rid;
-                const long long tq0 = (b == 0 && t == 0) ? global_ns() : 0;
+                if (b == 0 && t == 0) st_tm[1] = global_ns();
                 const int nb = rr3 == 2 ? 0 : rr3 + 1, zb = rr3 == 0 ? 2 : rr3 - 1;
                 const unsigned *CB = P.chgbits[rr3];
                 unsigned *NB = P.chgbits[nb];
@@ -766,10 +770,10 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
                         }
                     }
                 }
-                if (b == 0 && t == 0) st_acc[2] += global_ns() - tq0;
+                if (b == 0 && t == 0) st_acc[2] += global_ns() - st_tm[1];
                 GRID_BARRIER();                                          // candidates and statistics are complete; labels may be lowered from here on
                 // ---- phase 2: every CTA derives the same threshold and frontier from the candidate list ----
-                const long long tq2 = (b == 0 && t == 0) ? global_ns() : 0;
+                if (b == 0 && t == 0) st_tm[2] = global_ns();
                 unsigned long long e_pre = t < no ? __ldcg(CAND + t) : 0ull;            // (speculative: before the count is known)
                 if (t == 0) {
                     sh_i[0] = __ldcg(RS + 0); sh_i[1] = __ldcg(RS + 1); sh_i[2] = __ldcg(RS + 2);
@@ -846,8 +850,7 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
                 Tg = T + step;
                 const int myn = nfront > b ? (nfront - b - 1) / G + 1 : 0;
                 __syncthreads();
-                const long long tq1 = (b == 0 && t == 0) ? global_ns() : 0;
-                if (b == 0 && t == 0) st_acc[8] += tq1 - tq2;
+                if (b == 0 && t == 0) { st_tm[3] = global_ns(); st_acc[8] += st_tm[3] - st_tm[2]; }
                 // relax: the holders of this CTA's frontier objects, kRowsMax rows at a time
                 int qi = 0, si = 0;          // next frontier object of this CTA, next slot inside it
                 while (qi < myn) {
@@ -969,8 +972,7 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
                         }
                     }
                 }
-                if (b == 0 && t == 0) { st_acc[9] += tq1 - tq0; st_acc[10] += global_ns() - tq1; }
-                __threadfence();
+                if (b == 0 && t == 0) { st_acc[9] += st_tm[3] - st_tm[1]; st_acc[10] += global_ns() - st_tm[3]; }
                 implicit = false;
                 rr3 = nb;
                 GRID_BARRIER();
@@ -979,7 +981,7 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
             }
             if (status) break;
             if (D >= kInf / 2) { status = CYB_ERR_NOT_CONVERGED; break; }
-            const long long tr0 = (b == 0 && t == 0) ? global_ns() : 0;
+            if (b == 0 && t == 0) st_tm[4] = global_ns();
             // S3a: price update -- lambda[o] += D - d[o] below D; shared memory goes back to prices
             for (int o = t; o < no; o += kThreads) {
                 const bool mine = (o % G == b);
@@ -1087,11 +1089,11 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
                 F = tot;
                 __syncthreads();
             }
-            if (b == 0 && t == 0) st_acc[11] += global_ns() - tr0;
+            if (b == 0 && t == 0) st_acc[11] += global_ns() - st_tm[4];
             if (status) break;
             if (F > 0 && !SMEMO) GRID_BARRIER();     // the next search reads slot owners from global memory
         }
-        if (b == 0 && t == 0) st_acc[7] += global_ns() - ts0;
+        if (b == 0 && t == 0) st_acc[7] += global_ns() - st_tm[0];
         if (status) break;
         GRID_BARRIER();        // moves / prices of the last search become visible
         status = __ldcg(P.gmm + 2);

@@ -13,6 +13,8 @@ Reference path replaced (paths relative to the CytoSPACE repo):
 """
 from __future__ import annotations
 
+import os
+from concurrent.futures import ThreadPoolExecutor
 from dataclasses import dataclass
 
 import numpy as np
@@ -34,6 +36,18 @@ STAT_NAMES = ("status", "phases", "rounds", "bids", "passes", "cost_min", "cost_
 
 def _round_up(x: int, a: int) -> int:
     return (x + a - 1) // a * a
+
+
+def _on_engine_device(fn):
+    """Run a method with the engine's device current: the native library queries and launches on the
+    current CUDA device."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(self, *a, **k):
+        with torch.cuda.device(self.device):
+            return fn(self, *a, **k)
+    return wrapper
 
 
 @dataclass
@@ -71,16 +85,19 @@ class AssignmentEngine:
         self.lib = _native.load()
         self.ffi = _native.ffi()
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         if precision not in PRECISIONS:
             raise ValueError(f"precision must be one of {sorted(PRECISIONS)}")
         self.precision = precision
         self.cost_scale = float(cost_scale)
         self._ws = {}
+        self._stage = None
         self.profile = False          # True: bracket the cost-build and LAP launches with CUDA events
         self._events = {}
         sm, maj, mnr, mem = (self.ffi.new("int *"), self.ffi.new("int *"), self.ffi.new("int *"),
                              self.ffi.new("size_t *"))
-        _native.check(self.lib.cyb_device_info(self.device.index or 0, sm, maj, mnr, mem))
+        _native.check(self.lib.cyb_device_info(self.device.index, sm, maj, mnr, mem))
         self.sm_count, self.cc, self.total_mem = sm[0], (maj[0], mnr[0]), mem[0]
         if self.cc[0] != 10:
             raise RuntimeError(f"cytospace_b200 is built for sm_100a; device is cc {self.cc[0]}.{self.cc[1]}")
@@ -109,15 +126,81 @@ class AssignmentEngine:
         b.synchronize()
         return a.elapsed_time(b)
 
+    #: host arrays at least this large go through the pinned staging ring
+    STAGE_MIN_BYTES = 32 << 20
+    STAGE_SLAB_BYTES = 64 << 20
+    STAGE_SLABS = 3
+
+    @_on_engine_device
     def to_device(self, x, dtype=None) -> torch.Tensor:
-        """numpy / CPU tensor -> device tensor (pinned staging is the caller's choice)."""
-        if isinstance(x, np.ndarray):
-            x = torch.from_numpy(np.ascontiguousarray(x))
-        if dtype is not None and x.dtype != dtype:
-            x = x.to(dtype)
-        return x.to(self.device, non_blocking=True)
+        """Host array (numpy / CPU tensor) -> device tensor.
+
+        Expression matrices reach ``solve_linear_assignment_problem`` as pageable numpy arrays
+        (cytospace.py:398-409).  Anything that is not float32 / float64 (``read_csv`` count matrices are
+        int64) is cast to float64 on the host as the reference's ``normalize_data`` does
+        (common.py:143: ``np.nan_to_num(data).astype(float)``).  Large arrays are uploaded through a ring of
+        pinned slabs: worker threads copy pageable -> pinned while the previous slab's DMA is in flight
+        (a plain ``cudaMemcpy`` from pageable memory runs at a fraction of the PCIe rate)."""
+        if torch.is_tensor(x):
+            if x.is_cuda:
+                return x if dtype is None or x.dtype == dtype else x.to(dtype)
+            x = x.numpy()
+        x = np.asarray(x)
+        if dtype is not None:
+            want = {torch.float64: np.float64, torch.float32: np.float32, torch.int32: np.int32,
+                    torch.int64: np.int64}[dtype]
+            if x.dtype != want:
+                x = x.astype(want)
+        elif x.dtype not in (np.float32, np.float64):
+            x = x.astype(np.float64)
+        if not x.flags.c_contiguous:
+            x = np.ascontiguousarray(x)
+        if x.nbytes < self.STAGE_MIN_BYTES:
+            return torch.from_numpy(x).to(self.device)
+        return self._staged_upload(x)
+
+    def _staged_upload(self, x: np.ndarray) -> torch.Tensor:
+        out = torch.empty(x.shape, dtype=torch.from_numpy(x[:0]).dtype, device=self.device)
+        src = x.reshape(-1).view(np.uint8)
+        dst = out.view(-1).view(torch.uint8)
+        st = self._stage
+        if st is None:
+            n_thr = max(1, min(8, (os.cpu_count() or 2)))
+            st = self._stage = {
+                "slabs": [torch.empty(self.STAGE_SLAB_BYTES, dtype=torch.uint8).pin_memory() for _ in range(self.STAGE_SLABS)],
+                "events": [None] * self.STAGE_SLABS,
+                "stream": torch.cuda.Stream(device=self.device),
+                "pool": ThreadPoolExecutor(n_thr), "threads": n_thr}
+        slab, k, thr = self.STAGE_SLAB_BYTES, self.STAGE_SLABS, st["threads"]
+        main = torch.cuda.current_stream(self.device)
+
+        def fill(buf, lo, hi):
+            # pageable -> pinned, split over the worker threads (numpy releases the GIL for plain copies)
+            n = hi - lo
+            part = -(-n // thr)
+            futs = [st["pool"].submit(np.copyto, buf[a:min(a + part, n)], src[lo + a:lo + min(a + part, n)])
+                    for a in range(0, n, part)]
+            for f in futs:
+                f.result()
+
+        with torch.cuda.stream(st["stream"]):
+            st["stream"].wait_stream(main)
+            for i, lo in enumerate(range(0, src.size, slab)):
+                hi = min(lo + slab, src.size)
+                j = i % k
+                if st["events"][j] is not None:
+                    st["events"][j].synchronize()                 # the slab's previous DMA has drained
+                buf = st["slabs"][j].numpy()
+                fill(buf, lo, hi)
+                dst[lo:hi].copy_(st["slabs"][j][:hi - lo], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(st["stream"])
+                st["events"][j] = ev
+        main.wait_stream(st["stream"])
+        return out
 
     # --------------------------------------------------------------- cost build
+    @_on_engine_device
     def cost_build(self, sc: torch.Tensor, st: torch.Tensor, log_tpm: bool = False, out: torch.Tensor | None = None,
                    return_colstats: bool = False, check_variance: bool = True, layout: str = "cells_x_spots",
                    metric: str = "Pearson_correlation"):
@@ -203,6 +286,7 @@ class AssignmentEngine:
             raise ValueError(f"{nz} cell/spot column(s) have zero variance: correlation undefined "
                              "(the reference would hand NaN costs to the solver)")
 
+    @_on_engine_device
     def rank_columns(self, x: torch.Tensor, log_tpm: bool = False) -> torch.Tensor:
         """``pd.DataFrame(x).rank().values`` (common.py:207-208) for a [G x n] float64 / float32 device
         matrix: float32 [G x n] average ranks."""
@@ -223,6 +307,7 @@ class AssignmentEngine:
         self._mark("rank", 1)
         return out
 
+    @_on_engine_device
     def expand_with_noise(self, cost: torch.Tensor, n_cols: int, row_map, seed: int, noise_lo: int = 1,
                           noise_span: int = 10) -> torch.Tensor:
         """``cost[location_repeat, :]`` (linear_assignment_solvers.py:63-66) plus the integer tie noise
@@ -237,6 +322,7 @@ class AssignmentEngine:
             self._stream()))
         return out
 
+    @_on_engine_device
     def quantise(self, cost_f64: torch.Tensor, scale: float) -> torch.Tensor:
         """int32 ``rint(scale * cost)`` of a float64 device matrix (entry P2)."""
         n_rows, n_cols = cost_f64.shape
@@ -265,6 +351,7 @@ class AssignmentEngine:
         np.cumsum(cap, out=soff[1:])
         return torch.from_numpy(soff).to(self.device), int(soff[-1])
 
+    @_on_engine_device
     def lap_solve(self, cost: torch.Tensor, capacities=None, n_persons: int | None = None,
                   n_objects: int | None = None, grid: int = 0) -> LapResult:
         """Exact assignment on the int32 device matrix ``cost[person, object]``: every person gets one
@@ -304,6 +391,7 @@ class AssignmentEngine:
             raise RuntimeError(f"LAP solve failed on device: {names.get(stats['status'], stats['status'])}")
         return LapResult(person_obj, slot_owner, price, int(host[0]), stats, soff)
 
+    @_on_engine_device
     def lap_check(self, cost: torch.Tensor, res: LapResult) -> dict:
         """On-device optimality certificate; ``max_violation <= 1`` (scaled units) with no invalid
         person / capacity mismatch proves the assignment optimal for the integer matrix.  One
@@ -324,6 +412,7 @@ class AssignmentEngine:
         return {"max_violation": v, "total": t, "invalid_rows": bad, "capacity_mismatch": badcap}
 
     # --------------------------------------------------------------- whole path
+    @_on_engine_device
     def assign(self, sc, st, cell_number_to_node_assignment, log_tpm: bool = False,
                metric: str = "Pearson_correlation", cspr_seed: int | None = None):
         """cost build + LAP + ``location_repeat[assignment]`` (cytospace.py:319-331).
@@ -338,6 +427,9 @@ class AssignmentEngine:
         cn = np.asarray(cell_number_to_node_assignment).astype(np.int64).ravel()
         sc = self.to_device(sc) if not (torch.is_tensor(sc) and sc.is_cuda) else sc
         st = self.to_device(st) if not (torch.is_tensor(st) and st.is_cuda) else st
+        if sc.dtype != st.dtype or sc.dtype not in (torch.float64, torch.float32):
+            # e.g. int64 counts on one side, float32 on the other: compute in float64 like the reference
+            sc, st = sc.to(torch.float64), st.to(torch.float64)
         N, S = int(sc.shape[1]), int(st.shape[1])
         if cn.shape[0] != S:
             raise ValueError(f"cell_number_to_node_assignment has {cn.shape[0]} entries for {S} spots")
@@ -365,10 +457,18 @@ class AssignmentEngine:
             spot_of_cell = res.slot_owner.long()
         else:
             # location_repeat (linear_assignment_solvers.py:63-65) becomes the spots' capacities:
-            # the cells bid for spots that hold cn[s] cells each
+            # the cells bid for spots that hold cn[s] cells each.  Spots that take no cell
+            # (--sampling-sub-spots hands bincount(minlength=n_spots) vectors, cytospace.py:650-660) never
+            # enter location_repeat in the reference; here they are dropped before the cost build, which also
+            # keeps objects <= persons when there are more spots than cells in a chunk.
+            keep = np.flatnonzero(cn > 0)
+            if keep.size < S:
+                st = st.index_select(1, torch.from_numpy(keep).to(self.device))
             cost = self.cost_build(sc, st, log_tpm=log_tpm, check_variance=False, layout="cells_x_spots",
                                    metric=metric)
-            res = self.lap_solve(cost, cn, n_persons=N, n_objects=S)
+            res = self.lap_solve(cost, cn[keep], n_persons=N, n_objects=int(keep.size))
             spot_of_cell = res.person_obj.long()
+            if keep.size < S:
+                spot_of_cell = torch.from_numpy(keep).to(self.device)[spot_of_cell]
         self.check_zero_variance()                   # one sync, after the solve
         return spot_of_cell, res, cost

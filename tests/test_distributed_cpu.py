@@ -17,6 +17,12 @@ class OracleEngine:
     """Test double with the AssignmentEngine.assign contract, CPU tensors, oracle arithmetic."""
     device = torch.device("cpu")
 
+    def to_device(self, x, dtype=None):
+        t = x if torch.is_tensor(x) else torch.from_numpy(np.ascontiguousarray(x))
+        if dtype is None and t.dtype not in (torch.float32, torch.float64):
+            dtype = torch.float64
+        return t if dtype is None else t.to(dtype)
+
     def assign(self, sc, st, cn, log_tpm=False, metric="Pearson_correlation", cspr_seed=None):
         import oracle
         from oracle import cost_oracle as co
@@ -51,6 +57,16 @@ def _problem(mode):
         subs = [np.bincount(p, minlength=20) for p in parts]
         plan = chunking.plan_chunks(60, 20, cn, isc, subsampled_cell_number_to_node_assignment_list=subs)
     return sc, st, plan
+
+
+def test_integer_count_matrices_travel_as_float64():
+    """read_csv count matrices are int64: the distributed path must not down-cast them."""
+    sys.path.insert(0, ROOT)
+    from cytospace_b200 import chunking
+    sc, st, plan = _problem("single_cell")
+    a = chunking.solve_chunks(OracleEngine(), sc, st, plan, log_tpm=True)
+    b = chunking.solve_chunks(OracleEngine(), sc.astype(np.int64), st.astype(np.int64), plan, log_tpm=True)
+    assert a == b
 
 
 KW = {"single_cell": {}, "sub_spots": {}, "single_cell_spearman": {"metric": "Spearman_correlation"},
