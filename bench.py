@@ -21,6 +21,7 @@ chunks are independent, cytospace.py:430-451), one all-gather of the assignment 
 from __future__ import annotations
 
 import argparse
+import contextlib
 import json
 import os
 import subprocess
@@ -120,43 +121,78 @@ def reference_step(sc_n, st_n, cn, seed=1):
     return location_repeat[colsol], total
 
 
+def _reference_worker(q, n, n_spots, wl, steps, warmup, threads):
+    """One ``-nop`` worker of the reference arm: its own copy of the sample, BLAS limited to its share of the cores."""
+    from threadpoolctl import threadpool_limits
+    from oracle import cost_oracle as co
+    from cytospace_b200 import synthetic as syn
+    with threadpool_limits(limits=threads):
+        sc, st, cn = syn.structured_counts(n, n_spots, wl["n_genes"], wl["cps"], seed=wl["seed"])
+        sc_n, st_n = co.normalize_data(sc), co.normalize_data(st)
+        del sc, st
+        for _ in range(warmup):
+            reference_step(sc_n, st_n, cn)
+        q.put(("ready", None))
+        t0 = time.perf_counter()
+        total = None
+        for _ in range(steps):
+            _, total = reference_step(sc_n, st_n, cn)
+        q.put(("done", (time.perf_counter() - t0, float(total))))
+
+
 def run_reference(args, wl):
+    """The reference's own CPU formulation on this box's host cores.  N > 1 mirrors ``-nop N``
+    (cytospace.py:430: one worker process per chunk, ``min(num_chunks, nop)`` at a time): N independent copies of
+    the sample on ``min(N, cores)`` worker processes sharing the cores."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    import multiprocessing as mp
     import oracle
-    from oracle import cost_oracle as co
-    from cytospace_b200 import synthetic as syn
     oracle.build()
     cores = os.cpu_count() or 1
-    budget_s = 150.0 / max(1, args.steps + args.warmup)
-    est_full = 45.0 * (wl["n_cells"] / 10000.0) ** 2.6 * (wl["n_genes"] / 20000.0) ** 0.5
-    n = wl["n_cells"]
-    for cand in (wl["n_cells"], 7000, 5000, 4000, 3000, 2000, 1000, 500):
+    n_units = max(1, args.gpus)
+    workers = min(n_units, cores)
+    threads = max(1, cores // workers)
+    # CPU code needs no warm-up: at most one untimed step, so that the timed ones can be as large as possible
+    warmup = min(args.warmup, 1)
+    budget_s = 240.0 / max(1, args.steps + warmup) / -(-n_units // workers)
+    est_full = 45.0 * (wl["n_cells"] / 10000.0) ** 2.6 * (wl["n_genes"] / 20000.0) ** 0.5 * (8.0 / min(8, threads)) ** 0.5
+    n = min(500, wl["n_cells"])
+    for cand in (wl["n_cells"], 8000, 7000, 6000, 5000, 4000, 3000, 2000, 1000, 500):
         if cand <= wl["n_cells"] and est_full * (cand / wl["n_cells"]) ** 2.6 <= budget_s:
             n = cand
             break
-    else:
-        n = min(500, wl["n_cells"])
     n_spots = max(1, n // wl["cps"])
     n = n_spots * wl["cps"]
-    sc, st, cn = syn.structured_counts(n, n_spots, wl["n_genes"], wl["cps"], seed=wl["seed"])
-    sc_n, st_n = co.normalize_data(sc), co.normalize_data(st)
-    del sc, st
-    for _ in range(args.warmup):
-        reference_step(sc_n, st_n, cn)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        _, total = reference_step(sc_n, st_n, cn)
-    dt = (time.perf_counter() - t0) / max(1, args.steps)
-    value = n / dt
+    # torchrun exports OMP_NUM_THREADS=1 to its children: the reference arm is a CPU job and uses the cores
+    for var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[var] = str(threads)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    dt, total = 0.0, None
+    for wave in range(0, n_units, workers):
+        procs = [ctx.Process(target=_reference_worker, args=(q, n, n_spots, wl, args.steps, warmup, threads))
+                 for _ in range(min(workers, n_units - wave))]
+        for p_ in procs:
+            p_.start()
+        got = [q.get() for _ in range(2 * len(procs))]
+        for p_ in procs:
+            p_.join()
+        times = [v[0] for k, v in got if k == "done"]
+        total = [v[1] for k, v in got if k == "done"][0]
+        dt += max(times)                                   # the waves run one after the other
+    dt /= max(1, args.steps)
+    value = n * n_units / dt
     sample = (f"{n} cells x {n_spots} spots x {wl['n_genes']} genes block of {args.workload} "
-              f"(full problem {wl['n_cells']} x {wl['n_spots']}); float64 numpy cost build on {cores} threads + "
-              "restated float64 JV (1 thread; lapjv wheel absent)")
+              f"(full problem {wl['n_cells']} x {wl['n_spots']}); per step: float64 numpy cost build + 1e-16 tie noise + "
+              f"restated float64 JV (single-threaded like lapjv; the wheel is absent); {n_units} independent unit(s) on "
+              f"{workers} worker process(es) x {threads} BLAS thread(s) (mirrors -nop {n_units}); {warmup} untimed warm-up step(s)")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {wl['desc']}", "sample_n": n},
+            "config": {"workload": f"{args.workload}: {wl['desc']}", "sample_n": n, "same_config": bool(n == wl["n_cells"]),
+                       "units": n_units, "worker_processes": workers, "blas_threads_per_worker": threads},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "total_cost_f64": total}
@@ -166,7 +202,8 @@ def run_reference(args, wl):
 # ----------------------------------------------------------------------------------- B200 arm
 def cpu_baseline(cost_np, row_map, sc_host, st_host, wl, total_gpu, with_scipy=False):
     """Oracle on this box's host cores: restated JV (int32, 1 thread) on the GPU-built matrix (full
-    size up to 10k, else its leading 10k block) + numpy float64 cost build on a 2k x 2k x G block."""
+    size up to 10k, else its leading 8k block) + numpy float64 cost build on a 2k x 2k x G block, which is also
+    compared entry by entry with the same block of the GPU-built matrix (cost-build tolerance at the full G)."""
     import oracle
     from oracle import cost_oracle as co
     oracle.build()
@@ -174,15 +211,18 @@ def cpu_baseline(cost_np, row_map, sc_host, st_host, wl, total_gpu, with_scipy=F
     n = cost_np.shape[1]
     b = min(2000, sc_host.shape[1], st_host.shape[1])
     t0 = time.perf_counter()
-    co.cost_matrix_i32(sc_host[:, :b].numpy(), st_host[:, :b].numpy())
+    blk = co.cost_matrix_i32(sc_host[:, :b], st_host[:, :b])          # spots x cells (reference orientation)
     t_cost_blk = time.perf_counter() - t0
     t_cost = t_cost_blk * (sc_host.shape[1] / b) * (st_host.shape[1] / b)
     out = {"unit": UNIT, "cores": cores, "kind": "port", "lap_threads": 1, "cost_build_threads": cores}
+    if row_map is None:
+        diff = np.abs(blk.astype(np.int64) - cost_np[:b, :b].astype(np.int64))
+        out["cost_block_max_abs_diff"] = int(diff.max())
+        out["cost_block_frac_within_1"] = float((diff <= 1).mean())
     if n <= 10000:
         t0 = time.perf_counter()
         total_cpu = oracle.lapjv_i32(cost_np, row_map)[2][0]
         t_lap = time.perf_counter() - t0
-        # an independent implementation on the same integer matrix (SURVEY 8c pin (i)): SciPy's JV variant
         try:
             if with_scipy and n <= 10000 and row_map is None:           # ~90 s at 10k: opt-in (--cpu-scipy)
                 from scipy.optimize import linear_sum_assignment
@@ -207,15 +247,88 @@ def cpu_baseline(cost_np, row_map, sc_host, st_host, wl, total_gpu, with_scipy=F
             t0 = time.perf_counter(); oracle.lapjv_i32(sub); t_blk = time.perf_counter() - t0
         t_lap = t_blk * (n / m) ** 2.6
         out.update(value=n / (t_cost + t_lap), lap_s=t_lap, cost_build_s_scaled=t_cost, total_equal=None,
-                   sample=f"LAP: restated JV on the leading {m}x{m} block, extrapolated with n^2.6; cost build: "
-                          f"numpy float64 on a {b}x{b} block scaled")
+                   sample=f"LAP: restated JV on the leading {m}x{m} block, extrapolated with n^2.6 (full-size totals: "
+                          f"profiles/r02_parity_*.json); cost build: numpy float64 on a {b}x{b} block scaled")
     return out
+
+
+def strong_cfg5(eng, dev, rank, world, args):
+    """BASELINE configs[4]: 200k cells x 200k spots as 8 matched sub-LAPs of 25k (--single-cell -noss 25000,
+    cytospace.py:605-633) through chunking.solve_chunks -- rank 0 holds the expression matrices in HBM, the blocks
+    are gathered on its GPU and travel point-to-point over NCCL INSIDE the timed region, one all-gather returns the
+    indices.  Also timed: the same plan on rank 0's GPU alone (the 1-GPU reference of the speed-up)."""
+    import torch
+    import torch.distributed as dist
+    from cytospace_b200 import chunking, synthetic as syn
+    from cytospace_b200.cytospace import partition_indices
+    wl = WORKLOADS["cfg5"]
+    n_chunk, n_chunks, G = wl["n_cells"], wl["chunks"], wl["n_genes"]
+    n = n_chunk * n_chunks
+    if args.cfg5_cells:
+        n = int(args.cfg5_cells); n_chunk = n // n_chunks
+    plan = None
+    sc = st = None
+    if rank == 0:
+        sc, st, cn = syn.structured_counts_torch(n, n, G, 1, seed=wl["seed"], device=dev)
+        for x in (sc, st):                                          # normalize_data in place, block by block (32 GB each)
+            for c0 in range(0, n, 8192):
+                x[:, c0:c0 + 8192] = syn.normalize_data_torch(x[:, c0:c0 + 8192])
+        isc = partition_indices(np.arange(n), split_by_interval_int=n_chunk, shuffle=False)
+        ist = partition_indices(np.arange(n), split_by_interval_int=n_chunk, shuffle=False)
+        plan = chunking.plan_chunks(n, n, cn, isc, index_st_list=ist)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()) / steps, out
+
+    dist_fn = lambda: chunking.solve_chunks(eng, sc, st, plan)
+    dist_fn()                                                      # warm-up (NCCL connections, workspaces)
+    ms_n, out_n = timed(dist_fn, 2)
+    res = {"workload": f"{n} cells x {n} spots x {G} genes, {n_chunks} sub-LAPs of {n_chunk} (float64 inputs resident in "
+                       f"rank 0's HBM; distribution inside the timed region)",
+           "n_gpus": world, "ms_per_step": ms_n, "value": n / (ms_n / 1e3), "unit": UNIT, "scaling": "strong",
+           **{k: int(v) for k, v in chunking.last_traffic.items()}} if world > 1 else \
+          {"workload": f"{n} cells x {n} spots x {G} genes, {n_chunks} sub-LAPs of {n_chunk} back to back on one GPU",
+           "n_gpus": 1, "ms_per_step": ms_n, "value": n / (ms_n / 1e3), "unit": UNIT, "scaling": "strong",
+           "bcast_bytes": 0, "p2p_bytes": 0, "gather_bytes": 0}
+    if world > 1:
+        # the 1-GPU time of the same plan, on rank 0 (the other ranks wait at the barrier)
+        ms_1 = None
+        if rank == 0:
+            t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(dev)
+            t0.record()
+            out_1 = chunking.solve_chunks(eng, sc, st, plan, transport=chunking.SOLO)
+            t1.record(); torch.cuda.synchronize(dev)
+            ms_1 = t0.elapsed_time(t1)
+            res["ms_per_step_1gpu"] = ms_1
+            res["speedup_vs_1gpu"] = ms_1 / ms_n
+            res["same_assignment_as_1gpu"] = bool(out_1 == out_n)
+        barrier()
+    return res
 
 
 def run_b200(args, wl):
     import torch
     import torch.distributed as dist
+    import cytospace_b200
     from cytospace_b200 import synthetic as syn
+    from cytospace_b200 import linear_assignment_solvers as las
     from cytospace_b200.engine import AssignmentEngine
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -227,28 +340,30 @@ def run_b200(args, wl):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     eng = AssignmentEngine(device=dev, precision=args.precision)
+    las._engine = eng                      # the engine behind the plugin entry points of this process
+    if world > 1:                          # the host cores are shared by the ranks' staging threads
+        eng._stage_threads = max(1, (os.cpu_count() or 1) // world)
     eng.profile = True
     n_cells, n_spots, n_genes, cps = wl["n_cells"], wl["n_spots"], wl["n_genes"], wl["cps"]
-    n_chunks = wl.get("chunks", 0)          # cfg5: a fixed number of independent sub-LAPs dealt to the ranks
+    n_chunks = wl.get("chunks", 0)          # --workload cfg5: sub-LAPs dealt round-robin, inputs resident per rank
     strong = n_chunks > 0
     my_chunks = [c for c in range(n_chunks) if c % world == rank] if strong else [rank]
-    in_dtype = torch.float32 if strong else torch.float64      # cfg5 keeps 8 chunks resident: float32 inputs
 
     # ---- synthetic inputs (sampled on the device, normalised like CYT:398-399) -- not timed
     units = []
     for c in my_chunks:
         # weak scaling: every rank gets the SAME instance (per-GPU work fixed as N grows; the solve time of an
-        # instance is data-dependent, 70-91 ms over seeds at cfg2); the strong-scaling chunks are all different
+        # instance is data-dependent); the strong-scaling chunks are all different
         sc_raw, st_raw, cn = syn.structured_counts_torch(n_cells, n_spots, n_genes, cps,
                                                          seed=wl["seed"] + (17 * c if strong else 0), device=dev)
-        sc_dev = syn.normalize_data_torch(sc_raw).to(in_dtype); del sc_raw
-        st_dev = syn.normalize_data_torch(st_raw).to(in_dtype); del st_raw
+        sc_dev = syn.normalize_data_torch(sc_raw); del sc_raw
+        st_dev = syn.normalize_data_torch(st_raw); del st_raw
         units.append((sc_dev, st_dev, cn))
-    esz = 4 if strong else 8
-    # pinned host image of one unit (e2e re-sends it for every unit: same bytes over PCIe)
-    sc_host = units[0][0].cpu().pin_memory()
-    st_host = units[0][1].cpu().pin_memory()
-    h2d = (sc_host.numel() + st_host.numel()) * esz * len(units)
+    # host image of one unit: plain (pageable) numpy arrays, what solve_linear_assignment_problem receives from
+    # apply_linear_assignment (cytospace.py:398-409)
+    sc_np = units[0][0].cpu().numpy()
+    st_np = units[0][1].cpu().numpy()
+    h2d = (sc_np.nbytes + st_np.nbytes) * len(units)
     d2h = n_cells * 8 * len(units)
     n_out = n_cells * max(1, len(units))
     gathered = [torch.empty(n_out, dtype=torch.int64, device=dev) for _ in range(world)] if world > 1 else None
@@ -266,40 +381,13 @@ def run_b200(args, wl):
         finish(spots)
         return spot, res, cost
 
-    # e2e: double-buffered uploads on a copy stream -- the H2D of unit k+1 overlaps the solve of unit k
-    copy_stream = torch.cuda.Stream(device=dev)
-    bufs = [(torch.empty_like(units[0][0]), torch.empty_like(units[0][1])) for _ in range(2)]
-    ready = [torch.cuda.Event() for _ in range(2)]
-    freed = [torch.cuda.Event() for _ in range(2)]
-    state = {"k": 0, "primed": False}
-
-    def upload(slot):
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(freed[slot])
-            bufs[slot][0].copy_(sc_host, non_blocking=True)
-            bufs[slot][1].copy_(st_host, non_blocking=True)
-            ready[slot].record(copy_stream)
-
     def step_e2e():
-        cur_stream = torch.cuda.current_stream(dev)
-        spots, outs = [], None
-        for u in range(len(units)):
-            k = state["k"]
-            if not state["primed"]:
-                for sl in range(2):
-                    freed[sl].record(cur_stream)
-                upload(k % 2)
-                state["primed"] = True
-            cur_stream.wait_event(ready[k % 2])
-            upload((k + 1) % 2)                         # next unit's inputs, overlapping this solve
-            spot, res, cost = eng.assign(bufs[k % 2][0], bufs[k % 2][1], units[u][2], metric=args.distance_metric)
-            freed[k % 2].record(cur_stream)
-            spots.append(spot)
-            state["k"] = k + 1
-            outs = (spot, res, cost)
-        finish(spots)
-        host = [sp.cpu() for sp in spots]               # D2H of the result
-        return host[-1], outs[1], outs[2]
+        # the call a user of the reference makes: host numpy arrays in, Python list out
+        out = None
+        for _sc_d, _st_d, cn in units:
+            out = cytospace_b200.solve_linear_assignment_problem(sc_np, st_np, cn, "lapjv_b200", None, 1,
+                                                                 args.distance_metric)
+        return out
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -307,34 +395,43 @@ def run_b200(args, wl):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def timed(fn, steps, warmup):
+    def timed(fn, steps, warmup, track=True):
         for _ in range(warmup):
             out = fn()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         lap_ms, cost_ms = [], []
+        l0 = eng.launches
         e0.record()
         for _ in range(steps):
             out = fn()
-            lap_ms.append(eng.last_ms("lap")); cost_ms.append(eng.last_ms("cost"))
+            if track:
+                lap_ms.append(eng.last_ms("lap")); cost_ms.append(eng.last_ms("cost"))
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item()), out, float(np.mean(lap_ms)), float(np.mean(cost_ms))
+        return float(ms.item()), out, (float(np.mean(lap_ms)) if track else 0.0), (float(np.mean(cost_ms)) if track else 0.0), eng.launches - l0
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    tot_ms, (spot, res, cost), lap_ms, cost_ms = timed(step_resident, args.steps, args.warmup)
+    tot_ms, (spot, res, cost), lap_ms, cost_ms, launches = timed(step_resident, args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
-    e2e_ms, _, _, _ = timed(step_e2e, args.steps, min(args.warmup, 1))
+    with contextlib.redirect_stdout(sys.stderr):
+        e2e_ms, _, _, _, _ = timed(step_e2e, args.steps, min(args.warmup, 1), track=False)
     # certificate = one coalesced read of the whole cost matrix: the row-scan bandwidth probe, and a
     # full-size optimality proof of the last solve
     for _ in range(3):
         cert = eng.lap_check(cost, res)
     check_ms = eng.last_ms("check")
+    cfg5 = None
+    if not strong and not args.no_cfg5:
+        units.clear()
+        del sc_dev, st_dev
+        torch.cuda.empty_cache()
+        cfg5 = strong_cfg5(eng, dev, rank, world, args)
 
     if rank == 0:
         hbm, tf_burst, tf_sus, peak_src = measured_peaks()
@@ -343,14 +440,15 @@ def run_b200(args, wl):
         value = total_cells / (ms_per_step / 1e3)
         e2e_value = total_cells / (e2e_ms / args.steps / 1e3)
         n_per, n_obj = int(res.person_obj.numel()), int(res.price.numel())
-        # logical row scans of one solve: every bid scans one bidder's row (n_obj int32); bids served from a
-        # candidate list are counted too (the list is a cache of that scan) and reported separately
-        scans = res.row_scans + n_per                # + the min/max pass over every row
+        # row scans of one solve: every auction bid scans one row (n_obj int32), every relaxed row of a search is
+        # one scan, every phase start re-checks every row; + the min/max pass over every row
+        scans = res.row_scans + n_per
         lap_bytes = scans * n_obj * 4
         ach = lap_bytes / (lap_ms / 1e3) / 1e9
         kop = n_genes if args.precision == "f16" else 3 * n_genes
         gemm_flop_alg = 2.0 * n_spots * n_cells * n_genes
         scan_bytes = n_per * n_obj * 4
+        traffic = ncu_traffic(args.workload, "lap_sap_kernel")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -359,18 +457,20 @@ def run_b200(args, wl):
             "data": "synthetic",
             "config": {"workload": f"{args.workload}: {wl['desc']}", "n_cells": n_cells, "n_spots": n_spots,
                        "n_genes": n_genes, "cells_per_spot": cps, "precision": args.precision,
-                       "distance_metric": args.distance_metric,
-                       "input_dtype": str(in_dtype).replace("torch.", ""),
+                       "distance_metric": args.distance_metric, "input_dtype": "float64",
                        "l2": "inputs larger than L2 (expression matrices %.1f GB, cost matrix %.2f GB per sub-problem)"
-                             % ((sc_host.numel() + st_host.numel()) * esz / 1e9, n_spots * n_cells * 4 / 1e9),
+                             % ((sc_np.nbytes + st_np.nbytes) / 1e9, n_spots * n_cells * 4 / 1e9),
                        "per_rank": (f"{n_chunks} independent sub-LAPs dealt round-robin to {world} rank(s)" if strong else
                                     ("each rank solves its own independent copy of the same sub-problem instance" if world > 1 else "single GPU")),
-                       "e2e": "double-buffered pinned H2D on a copy stream overlaps the previous solve"},
-            "roofline": {"kernel": "lap_auction_kernel", "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s",
-                         "frac": ach / hbm, "traffic": ncu_traffic(args.workload, "lap_auction_kernel"), "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)",
+                       "e2e": "cytospace_b200.solve_linear_assignment_problem(sc_np, st_np, cn, 'lapjv_b200', ...) with pageable "
+                              "host numpy arrays (pinned staging ring inside the call), Python list out"},
+            "roofline": {"kernel": "lap_sap_kernel", "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s",
+                         "frac": ach / hbm, "traffic": traffic, "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)",
                          "row_scans": scans, "bytes_per_scan": n_obj * 4, "kernel_ms": lap_ms,
-                         "scans_served_from_candidate_lists": int(res.stats["list_hits"]),
-                         "note": "latency-bound: sequential price-war chains; see DESIGN.md 4.3"},
+                         "algorithmic_bytes": lap_bytes,
+                         "traffic_over_algorithmic": (traffic / lap_bytes if traffic else None),
+                         "note": "dependency-bound: ~%d dependent grid rounds per solve; see DESIGN.md 4.3"
+                                 % (int(res.stats["rounds"]) + int(res.stats["list_hits"]))},
             "roofline_row_scan": {"kernel": ("lap_rowcheck_whole_kernel" if n_obj <= 12288 else "lap_rowmin_kernel") +
                                             " (certificate: one pass over the cost matrix)",
                                   "bound": "hbm", "bytes": scan_bytes, "ms": check_ms,
@@ -385,18 +485,22 @@ def run_b200(args, wl):
                                     "note": "ms covers standardise pre-pass + GEMM; f16x3 executes 3x the algorithmic flop"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / args.steps},
-            "gpu_launches": args.steps * 8 * len(units),
+            "gpu_launches": launches,
             "clocks": clocks,
             "certificate": cert,
-            "lap_stats": {k: res.stats[k] for k in ("phases", "rounds", "bids", "tail_bids", "tails", "list_hits",
-                                                    "max_bidders", "grid", "smem_prices", "tail_mode")},
+            "lap_stats": {"phases": res.stats["phases"], "auction_rounds": res.stats["rounds"], "auction_bids": res.stats["bids"],
+                          "searches": res.stats["tails"], "search_rounds": res.stats["list_hits"],
+                          "search_rows": res.stats["tail_bids"], "paths": res.stats["paths"],
+                          "grid": res.stats["grid"], "smem_prices": res.stats["smem_prices"], "variant": res.stats["tail_mode"]},
             "total_cost": res.total, "lap_ms": lap_ms, "cost_build_ms": cost_ms,
         }
+        if cfg5 is not None:
+            line["strong_cfg5"] = cfg5
         if world == 1 and not strong and not args.no_cpu_baseline and args.distance_metric == "Pearson_correlation":
             row_map = None if cps == 1 else np.repeat(np.arange(n_spots, dtype=np.int32), cn)
             # the oracle takes the reference's orientation (spots x cells)
             cost_np = np.ascontiguousarray((cost[:, :n_cells] if cps == 1 else cost[:, :n_spots].T).cpu().numpy())
-            line["cpu_baseline"] = cpu_baseline(cost_np, row_map, sc_host, st_host, wl, res.total, args.cpu_scipy)
+            line["cpu_baseline"] = cpu_baseline(cost_np, row_map, sc_np, st_np, wl, res.total, args.cpu_scipy)
         emit(line)
     if world > 1:
         dist.barrier()
@@ -432,6 +536,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-scipy", action="store_true",
                     help="also time scipy.optimize.linear_sum_assignment on the GPU-built matrix (n <= 10k; ~90 s)")
+    ap.add_argument("--no-cfg5", action="store_true", help="skip the strong_cfg5 object (200k x 200k chunked problem)")
+    ap.add_argument("--cfg5-cells", type=int, default=0, help="total cells of the strong_cfg5 problem (default 200000)")
     ap.add_argument("--distance-metric", default="Pearson_correlation",
                     choices=["Pearson_correlation", "Spearman_correlation", "Euclidean"])
     args = ap.parse_args()

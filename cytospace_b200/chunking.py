@@ -102,7 +102,13 @@ class TorchTransport:
         return out
 
 
+#: pass as ``transport=`` to run every chunk on the calling rank although a process group is up
+SOLO = "solo"
+
+
 def _transport(group=None, transport=None):
+    if transport is SOLO:
+        return None
     if transport is not None:
         return transport
     import torch.distributed as dist
@@ -153,11 +159,14 @@ def _is_arange(idx) -> bool:
     return idx.size > 0 and idx[0] == 0 and np.array_equal(idx, np.arange(idx.size))
 
 
-def _columns(engine, x_dev, idx):
-    """x_dev[:, idx] as a contiguous device matrix (device gather: the host never touches the columns)."""
+def _columns(engine, x_dev, idx, tp=None):
+    """x_dev[:, idx] as a contiguous device matrix (device gather: the host never touches the columns);
+    through the C ABI (``cyb_gather_columns``) when the transport offers it."""
     idx = np.asarray(idx)
     if idx.size == x_dev.shape[1] and _is_arange(idx):
         return x_dev
+    if tp is not None and hasattr(tp, "gather_columns") and x_dev.is_cuda and x_dev.stride(1) == 1:
+        return tp.gather_columns(x_dev, idx)
     return x_dev.index_select(1, torch.from_numpy(idx.astype(np.int64)).to(x_dev.device))
 
 
@@ -198,9 +207,9 @@ def _solve_chunks_distributed(tp, engine, sc_np, st_np, plan, log_tpm, assign_kw
         o = owner[ch.idx]
         need_st = ch.st_index is not None
         if rank == 0:
-            blocks = [_columns(engine, sc_dev, ch.sc_index)]
+            blocks = [_columns(engine, sc_dev, ch.sc_index, tp)]
             if need_st:
-                blocks.append(_columns(engine, st_dev, ch.st_index))
+                blocks.append(_columns(engine, st_dev, ch.st_index, tp))
             if o == 0:
                 mine[ch.idx] = (blocks[0], blocks[1] if need_st else None)
             else:

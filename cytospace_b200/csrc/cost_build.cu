@@ -15,7 +15,7 @@
 //      cost[s, c] = rint(-(1e6/G) * acc)  stored as int32 -- the integer matrix
 //      the LAP solves (scale precedent: cytospace/cytospace.py:337).
 // The `cost[location_repeat, :]` row expansion of linear_assignment_solvers.py:63-66
-// is never materialised (lap_auction.cu resolves it by index).
+// is never materialised (lap_sap.cu turns it into object capacities).
 #include <cuda.h>
 #include <cuda_fp16.h>
 

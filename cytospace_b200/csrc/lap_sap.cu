@@ -10,7 +10,9 @@
 // rows of the matrix, OBJECTS the columns, object o has cap[o] SLOTS:
 //     min sum_i M[i, obj(i)]   s.t.  object o holds exactly cap[o] persons.
 //
-// Auction part (unchanged from round 1; lap_auction.cu keeps the long description).
+// Auction part (synchronous Jacobi rounds over the grid, one grid barrier per round: [bid] every CTA scans the
+// rows of its share of the free list and posts a 64-bit atomicMax (bid | ~person) per object plus a record;
+// [resolve] every CTA replays all records, so each CTA's view of the state is complete without a second barrier).
 // C = (M - cmin) * (P+1) >= 0; every slot has a price and a holder, the object's price lambda[o] is
 // its cheapest slot; a free person bids lambda[o*] + (w - v1) + eps for the cheapest slot of its
 // best object, the highest bid per object wins.  Invariant (eps-CS): for every assigned (i, o)
@@ -53,8 +55,7 @@
 //
 // Tuning knobs (environment, read at launch): CYB_LAP_SAP_T (free persons at which the search
 // takes over), CYB_LAP_SAP_K (rows per search round), CYB_LAP_SAP_MULTI (paths per search, <= 32),
-// CYB_LAP_THETA, CYB_LAP_EPS0, CYB_LAP_SMEM_PRICES=0 / CYB_LAP_SMEM_OWNER=0 (force the L2 paths),
-// CYB_LAP_SOLVER=auction (the round-1 solver, kept for A/B measurements).
+// CYB_LAP_THETA, CYB_LAP_EPS0, CYB_LAP_SMEM_PRICES=0 / CYB_LAP_SMEM_OWNER=0 (force the L2 paths).
 
 #include <algorithm>
 #include <climits>
@@ -66,12 +67,7 @@
 #include "common.h"
 
 namespace cyb {
-// round-1 solver (lap_auction.cu)
-int lap_solve_auction(const int32_t *cost_dev, int64_t ld, int64_t n_persons, int64_t n_objects,
-                      const int32_t *slot_offset_dev, int32_t *person_obj_dev, int32_t *slot_owner_dev,
-                      int64_t *price_dev, int64_t *total_dev, int64_t *stats_dev, void *workspace_dev,
-                      size_t workspace_bytes, int grid_hint, void *stream_v);
-size_t lap_auction_workspace_bytes(int64_t n_persons, int64_t n_objects);
+size_t lap_check_workspace_bytes(int64_t n_persons, int64_t n_objects);      // lap_check.cu
 }  // namespace cyb
 
 namespace {
@@ -544,7 +540,7 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
                         const long long bid = (long long)(key >> kPB);
                         const bool mine = (k % G == b);
                         int ms; long long mp;
-                        // sibling slot prices FIRST (loads before the stores to the same line, see lap_auction.cu)
+                        // sibling slot prices FIRST (loads before the stores to the same line, 148 CTAs storing to one line and then loading from it serialise at the L2 slice)
                         cheapest_slot(P, rc.x, rc.y, bid, ms, mp);
                         if (mine || !SMEMO) {
                             P.slot_owner[rc.y] = i;
@@ -1157,7 +1153,7 @@ SapLayout sap_layout(int64_t np, int64_t no) {
 
 extern "C" size_t cyb_lap_workspace_bytes(int64_t n_persons, int64_t n_objects) {
     if (n_persons <= 0 || n_objects <= 0) return 256;
-    return std::max(sap_layout(n_persons, n_objects).total, cyb::lap_auction_workspace_bytes(n_persons, n_objects));
+    return std::max(sap_layout(n_persons, n_objects).total, cyb::lap_check_workspace_bytes(n_persons, n_objects));
 }
 
 extern "C" int cyb_lap_solve_i32(const int32_t *cost_dev, int64_t ld, int64_t n_persons, int64_t n_objects,
@@ -1165,10 +1161,6 @@ extern "C" int cyb_lap_solve_i32(const int32_t *cost_dev, int64_t ld, int64_t n_
                                  int32_t *slot_owner_dev, int64_t *price_dev, int64_t *total_dev,
                                  int64_t *stats_dev, void *workspace_dev, size_t workspace_bytes,
                                  int grid_hint, void *stream_v) {
-    if (const char *e = getenv("CYB_LAP_SOLVER"))
-        if (!strcmp(e, "auction"))
-            return cyb::lap_solve_auction(cost_dev, ld, n_persons, n_objects, slot_offset_dev, person_obj_dev, slot_owner_dev,
-                                          price_dev, total_dev, stats_dev, workspace_dev, workspace_bytes, grid_hint, stream_v);
     cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
     const int64_t np = n_persons, no = n_objects;
     if (np <= 0 || np >= (1ll << kPB) - kSapMax || no <= 0 || no > np)
@@ -1237,7 +1229,9 @@ extern "C" int cyb_lap_solve_i32(const int32_t *cost_dev, int64_t ld, int64_t n_
     if (const char *e = getenv("CYB_LAP_THETA")) P.theta = std::max(2, atoi(e));
     if (const char *e = getenv("CYB_LAP_EPS0")) P.eps0_div = std::max(1, atoi(e));
     // (constants, not functions of the grid: the assignment must not depend on the grid size)
-    P.sap_t = 148; P.sap_k = 296; P.multi = kMultiMax;
+    // measured on B200 (profiles/r02_lap_knob_sweep.txt): 64 / 296 / 16 is the best single setting over 10k x 10k,
+    // 30k x 5k and 25k x 25k (auction rounds cost ~7 us, search rounds ~19 us: the search should start late)
+    P.sap_t = 64; P.sap_k = 296; P.multi = 16;
     if (const char *e = getenv("CYB_LAP_SAP_T")) P.sap_t = std::max(1, std::min(kSapMax, atoi(e)));
     if (const char *e = getenv("CYB_LAP_SAP_K")) P.sap_k = std::max(1, atoi(e));
     if (const char *e = getenv("CYB_LAP_SAP_MULTI")) P.multi = std::max(1, std::min(kMultiMax, atoi(e)));

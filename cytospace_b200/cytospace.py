@@ -38,12 +38,10 @@ def solve_linear_assignment_problem(scRNA_norm_data, st_norm_data, cell_number_t
     if distance_metric not in DISTANCE_METRICS:
         raise ValueError(f"Invalid distance_metric provided: {distance_metric}")
     eng = get_engine()
-    print("Building cost matrix ...")
-    print("Solving linear assignment problem ...")
     t0 = time.perf_counter()
     spot_of_cell, res, _ = eng.assign(np.asarray(scRNA_norm_data), np.asarray(st_norm_data),
                                       cell_number_to_node_assignment, metric=distance_metric,
-                                      cspr_seed=(seed if solver_method == "lap_CSPR" else None))
+                                      cspr_seed=(seed if solver_method == "lap_CSPR" else None), progress=print)
     mapped_st_index = spot_of_cell.cpu().numpy().tolist()
     print(f"Time to build cost matrix and solve linear assignment problem: "
           f"{round(time.perf_counter() - t0, 2)} seconds")

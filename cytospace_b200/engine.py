@@ -26,6 +26,11 @@ COST_SCALE = 10 ** 6           # integer scale of the correlation distance; prec
 PRECISIONS = {"f16": 0, "f16x3": 1}
 #: ``--distance-metric`` values (argument_parser.py:72-74) -> CYB_METRIC_*
 METRICS = {"Pearson_correlation": 0, "Spearman_correlation": 1, "Euclidean": 2}
+#: kernels one C-ABI call launches (profiles/r02_ncu_launches_cfg2.csv lists them): colsum + colstat_finalize +
+#: standardise_write per matrix and one GEMM for a Pearson cost build; one more column-sum pass per matrix with the
+#: fused normalize_data; a rank kernel per matrix (and the statistics passes of the ranks) for Spearman
+KERNELS_PER_CALL = {"cost_pearson": 7, "cost_log_tpm_extra": 2, "cost_spearman_extra": 2, "lap_solve": 1,
+                    "lap_check_whole": 1, "lap_check_tiled": 3, "rank_columns": 1, "expand": 1, "quantise": 1}
 STAT_NAMES = ("status", "phases", "rounds", "bids", "passes", "cost_min", "cost_max", "scale",
               "grid", "smem_prices", "tail_mode", "max_bidders", "phase_scans", "tail_bids", "tails", "list_hits",
               "small_rounds", "ns_bid", "ns_barrier", "ns_resolve", "ns_tail", "paths", "ns_select", "ns_relax",
@@ -93,6 +98,8 @@ class AssignmentEngine:
         self.cost_scale = float(cost_scale)
         self._ws = {}
         self._stage = None
+        #: kernels of this library launched so far (every C-ABI call launches a fixed number: see KERNELS_PER_CALL)
+        self.launches = 0
         self.profile = False          # True: bracket the cost-build and LAP launches with CUDA events
         self._events = {}
         sm, maj, mnr, mem = (self.ffi.new("int *"), self.ffi.new("int *"), self.ffi.new("int *"),
@@ -165,7 +172,7 @@ class AssignmentEngine:
         dst = out.view(-1).view(torch.uint8)
         st = self._stage
         if st is None:
-            n_thr = max(1, min(8, (os.cpu_count() or 2)))
+            n_thr = getattr(self, "_stage_threads", None) or max(1, min(8, (os.cpu_count() or 2)))
             st = self._stage = {
                 "slabs": [torch.empty(self.STAGE_SLAB_BYTES, dtype=torch.uint8).pin_memory() for _ in range(self.STAGE_SLABS)],
                 "events": [None] * self.STAGE_SLABS,
@@ -269,6 +276,8 @@ class AssignmentEngine:
                 _native.ptr("int32_t *", zero_var), self.ffi.cast("void *", ws.data_ptr() + off), ws_bytes,
                 self._stream()))
         self._mark("cost", 1)
+        self.launches += (KERNELS_PER_CALL["cost_pearson"] + (KERNELS_PER_CALL["cost_log_tpm_extra"] if log_tpm else 0) +
+                          (KERNELS_PER_CALL["cost_spearman_extra"] if metric == "Spearman_correlation" else 0))
         self._zero_var = zero_var
         self._zero_var_metric = metric
         if check_variance:
@@ -305,6 +314,7 @@ class AssignmentEngine:
                                                 _native.ptr("float *", out), out.stride(0),
                                                 self.ffi.cast("void *", ws.data_ptr() + off), ws_bytes, self._stream()))
         self._mark("rank", 1)
+        self.launches += KERNELS_PER_CALL["rank_columns"]
         return out
 
     @_on_engine_device
@@ -384,6 +394,7 @@ class AssignmentEngine:
             self.ffi.cast("int64_t *", small.data_ptr()), self.ffi.cast("int64_t *", small.data_ptr() + 8),
             self.ffi.cast("void *", ws.data_ptr() + off), ws_bytes, int(grid), self._stream()))
         self._mark("lap", 1)
+        self.launches += KERNELS_PER_CALL["lap_solve"]
         host = small.cpu().tolist()            # one D2H: total + stats (synchronises the stream)
         stats = dict(zip(STAT_NAMES, host[1:1 + len(STAT_NAMES)]))
         if stats["status"] != 0:
@@ -408,22 +419,28 @@ class AssignmentEngine:
             _native.ptr("int64_t *", res.price), _native.ptr("int64_t *", out),
             self.ffi.cast("void *", ws.data_ptr() + off), ws_bytes, self._stream()))
         self._mark("check", 1)
+        self.launches += KERNELS_PER_CALL["lap_check_whole" if n_objects <= 12288 else "lap_check_tiled"]
         v, t, bad, badcap = out.cpu().tolist()
         return {"max_violation": v, "total": t, "invalid_rows": bad, "capacity_mismatch": badcap}
 
     # --------------------------------------------------------------- whole path
     @_on_engine_device
     def assign(self, sc, st, cell_number_to_node_assignment, log_tpm: bool = False,
-               metric: str = "Pearson_correlation", cspr_seed: int | None = None):
+               metric: str = "Pearson_correlation", cspr_seed: int | None = None, progress=None):
         """cost build + LAP + ``location_repeat[assignment]`` (cytospace.py:319-331).
 
         ``cspr_seed`` not None selects the integerised lap_CSPR formulation (cytospace.py:334-347):
         the slot expansion is materialised with per-(slot, cell) integer noise in [1, 10] and solved
         as a square LAP (slots bid for cells).
 
+        ``progress`` (a callable taking one string) receives the reference's progress lines
+        (cytospace.py:321-322) as the corresponding stage is reached.
+
         Returns ``(spot_of_cell int64 device tensor [N], LapResult, cost int32 device matrix)``; the
         matrix is persons x objects of the solve: spots x cells when every spot takes one cell, cells x
         spots otherwise."""
+        say = progress or (lambda _msg: None)
+        say("Building cost matrix ...")
         cn = np.asarray(cell_number_to_node_assignment).astype(np.int64).ravel()
         sc = self.to_device(sc) if not (torch.is_tensor(sc) and sc.is_cuda) else sc
         st = self.to_device(st) if not (torch.is_tensor(st) and st.is_cuda) else st
@@ -444,6 +461,7 @@ class AssignmentEngine:
                                       metric=metric)
             location_repeat = np.repeat(np.arange(S), cn)
             cost = self.expand_with_noise(compact, N, location_repeat, cspr_seed)
+            say("Solving linear assignment problem ...")
             res = self.lap_solve(cost, None, n_persons=N, n_objects=N)
             lr = torch.from_numpy(location_repeat).to(self.device)
             spot_of_cell = lr[res.slot_owner.long()]
@@ -453,6 +471,7 @@ class AssignmentEngine:
             # gaps between a bidder's best and second-best object, shorter price wars.
             cost = self.cost_build(sc, st, log_tpm=log_tpm, check_variance=False, layout="spots_x_cells",
                                    metric=metric)
+            say("Solving linear assignment problem ...")
             res = self.lap_solve(cost, None, n_persons=S, n_objects=N)
             spot_of_cell = res.slot_owner.long()
         else:
@@ -466,6 +485,7 @@ class AssignmentEngine:
                 st = st.index_select(1, torch.from_numpy(keep).to(self.device))
             cost = self.cost_build(sc, st, log_tpm=log_tpm, check_variance=False, layout="cells_x_spots",
                                    metric=metric)
+            say("Solving linear assignment problem ...")
             res = self.lap_solve(cost, cn[keep], n_persons=N, n_objects=int(keep.size))
             spot_of_cell = res.person_obj.long()
             if keep.size < S:

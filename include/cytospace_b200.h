@@ -47,7 +47,7 @@
 extern "C" {
 #endif
 
-#define CYB_ABI_VERSION 5
+#define CYB_ABI_VERSION 6
 
 /* status codes */
 #define CYB_OK                 0
@@ -258,6 +258,34 @@ int cyb_lap_check_i32(const int32_t *cost_dev, int64_t ld, int64_t n_persons, in
                       const int32_t *slot_offset_dev, const int32_t *person_obj_dev,
                       const int64_t *price_dev, int64_t *out_dev, void *workspace_dev,
                       size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------ multi-GPU data plane */
+
+/* The chunked problem (apply_linear_assignment, cytospace/cytospace.py:430-467) on one rank per GPU: the
+ * reference pickles per-chunk column blocks `scRNA_norm_np[:, index_sc_list[i]]` / `st_norm_np[:, index_st_list[i]]`
+ * (:434-443; all spots for --sampling-sub-spots, :438) to worker processes and collects the index lists as they
+ * complete (:453-467).  Here: cyb_gather_columns cuts the blocks on rank 0's GPU, cyb_dist_send / cyb_dist_recv
+ * move them over NVLink (cyb_dist_broadcast for the shared ST block), cyb_dist_all_gather returns the indices.
+ * NCCL is bound at run time (libnccl.so.2); a communicator is an opaque handle owned by the caller.
+ * Sizes are in bytes; calls are asynchronous on `stream` like NCCL's own. */
+#define CYB_DIST_ID_BYTES 128
+
+/* rank 0: a fresh communicator id (ncclGetUniqueId) to hand to every rank out of band. */
+int cyb_dist_unique_id(void *id_out);
+/* every rank, on its current CUDA device: join the communicator (collective; ncclCommInitRank). */
+int cyb_dist_init(const void *id_bytes, int n_ranks, int rank, void **comm_out);
+int cyb_dist_destroy(void *comm);
+int cyb_dist_broadcast(void *comm, void *buf_dev, size_t bytes, int root, void *stream);
+int cyb_dist_send(void *comm, const void *buf_dev, size_t bytes, int peer, void *stream);
+int cyb_dist_recv(void *comm, void *buf_dev, size_t bytes, int peer, void *stream);
+/* recv_dev holds n_ranks * bytes_per_rank bytes, rank r's part at r * bytes_per_rank. */
+int cyb_dist_all_gather(void *comm, const void *send_dev, void *recv_dev, size_t bytes_per_rank, void *stream);
+
+/* out[r, j] = x[r, cols[j]]: the columns of one chunk (cytospace.py:434-443) as a dense block.
+ *   x_dev [n_rows x ld_x] float64 / float32 row-major, cols_dev int32[n_cols_out], out_dev [n_rows x ld_out]. */
+int cyb_gather_columns(const void *x_dev, int x_dtype, int64_t n_rows, int64_t ld_x,
+                       const int32_t *cols_dev, int64_t n_cols_out, void *out_dev, int64_t ld_out,
+                       void *stream);
 
 #ifdef __cplusplus
 }

@@ -1,8 +1,7 @@
-"""CPU: numpy models of three pieces of device arithmetic whose correctness is an identity or a
+"""CPU: numpy models of two pieces of device arithmetic whose correctness is an identity or a
 combinatorial argument (the GPU tests then check the kernels against the oracle):
   * the all-ascending bitonic network with virtual padding (metrics.cu: bitonic_sort_smem),
-  * the Euclidean epilogue (cost_build.cu: EPI 1),
-  * the candidate rule of the approximate-price row scan (lap_auction.cu: scan_row_approx)."""
+  * the Euclidean epilogue (cost_build.cu: EPI 1)."""
 import numpy as np
 import pytest
 from hypothesis import given, settings, strategies as st
@@ -58,33 +57,3 @@ def test_euclidean_identity_from_standardised_operands():
               + 2 * sd_b[:, None] * sd_a[None, :] * (1 - r))
     want = co.euclidean_distance(a, b)
     np.testing.assert_allclose(np.sqrt(np.maximum(d2, 0)), want, rtol=1e-10, atol=1e-9)
-
-
-def approx_scan(row, cmin, S, price, shift=15):
-    """scan_row_approx: candidates = columns whose a = ((c-cmin)*S >> shift) + (price >> shift) is <= (second
-    smallest a) + 1; the exact (min, argmin, second min) is taken over the candidates only."""
-    x = (row.astype(np.int64) - cmin) * S
-    a = (x >> shift) + (price >> shift)
-    m2 = np.partition(a, 1)[1] if a.size > 1 else np.iinfo(np.int64).max - 1
-    cand = np.nonzero(a <= m2 + 1)[0]
-    h = x[cand] + price[cand]
-    order = np.lexsort((cand, h))
-    j1 = int(cand[order[0]]); b1 = int(h[order[0]])
-    b2 = int(h[order[1]]) if cand.size > 1 else None
-    return b1, j1, b2, cand.size
-
-
-@settings(max_examples=300, deadline=None)
-@given(st.integers(2, 400), st.integers(0, 2 ** 31 - 1), st.sampled_from([3, 1000, 2_000_000]),
-       st.sampled_from([1, 1 << 10, 1 << 20, 1 << 40]))
-def test_approximate_price_candidate_rule_is_exact(n, seed, cost_range, price_range):
-    rng = np.random.default_rng(seed)
-    S = n + 1
-    row = rng.integers(-cost_range, cost_range, n).astype(np.int32)
-    cmin = -cost_range
-    price = rng.integers(0, price_range, n).astype(np.int64)
-    h = (row.astype(np.int64) - cmin) * S + price
-    order = np.lexsort((np.arange(n), h))
-    b1, j1, b2, ncand = approx_scan(row, cmin, S, price)
-    assert (b1, j1) == (int(h[order[0]]), int(order[0])) and b2 == int(h[order[1]])
-    assert 2 <= ncand <= n

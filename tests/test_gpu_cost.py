@@ -95,3 +95,21 @@ def test_errors(engine):
     y = x.clone(); y[:, 2] = 3.0                                   # zero-variance spot
     with pytest.raises(ValueError, match="zero variance"):
         engine.cost_build(x, y)
+
+
+@pytest.mark.parametrize("n_genes", [20000, 30000])
+def test_tolerance_at_the_baseline_gene_counts(engine, n_genes):
+    """BASELINE configs 2-5 use 20 000 / 30 000 genes: the chunked tcgen05 accumulation (K = 3 * G fp16 products
+    per entry) against the float64 oracle on a block small enough for numpy.  Same tolerance as above: every
+    entry within 4 units of 1e-6, 90 % within 1 unit."""
+    sc, st, _ = syn.structured_counts(320, 256, n_genes, 1, seed=77)
+    sc_n, st_n = co.normalize_data(sc), co.normalize_data(st)
+    got, _, _ = build(engine, sc_n, st_n)
+    want = co.cost_matrix_i32(sc_n, st_n)
+    d = np.abs(got.astype(np.int64) - want)
+    assert d.max() <= TOL["f16x3"], d.max()
+    assert (d <= 1).mean() >= 0.90
+    # and with the fused normalize_data on raw counts
+    got2, _, _ = build(engine, sc, st, log_tpm=True)
+    d2 = np.abs(got2.astype(np.int64) - want)
+    assert d2.max() <= TOL["f16x3"] and (d2 <= 1).mean() >= 0.90

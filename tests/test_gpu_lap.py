@@ -78,7 +78,8 @@ def _with_env(env, fn):
                 os.environ[k] = v
 
 
-SAP_KNOBS = [dict(theta=64, sap_t=148, K=296, multi=32),      # the defaults on a 148-SM device
+SAP_KNOBS = [dict(theta=64, sap_t=64, K=296, multi=16),       # the defaults
+             dict(theta=64, sap_t=148, K=296, multi=32),
              dict(theta=4, sap_t=8, K=16, multi=1),            # one path per search, tiny rounds (threshold histogram in use)
              dict(theta=256, sap_t=40, K=64, multi=8),
              dict(theta=16, sap_t=256, K=100000, multi=32)]    # every dirty object each round (Bellman-Ford rounds)
@@ -267,3 +268,63 @@ def test_memory_variants_on_small_problems(engine, lap_golden, smem_prices, smem
     tie = np.zeros((200, 200), np.int32)                                   # every column ties
     res, _ = _with_env(env, lambda: solve_and_check(engine, tie))
     assert res.total == 0
+
+
+def test_permutation_equals_jv_oracle_when_the_optimum_is_unique(engine):
+    """North-star: "permutation identical up to documented tie-breaks".  Where the optimum is unique there is no
+    tie to break: the device assignment must BE the JV oracle's.  Uniqueness is certified by the oracle's own
+    duals: every arc outside the optimal assignment has a strictly positive reduced cost."""
+    found = 0
+    for seed in range(40):
+        rng = np.random.default_rng(1000 + seed)
+        n = int(rng.integers(40, 400))
+        cost = rng.integers(-2_000_000, 2_000_000, (n, n), dtype=np.int32)
+        rowsol, colsol, (total, u, v) = oracle.lapjv_i32(cost)
+        red = cost.astype(np.int64) - u[:, None] - v[None, :]
+        red[np.arange(n), rowsol] = 1
+        if red.min() <= 0:
+            continue                                   # a zero reduced cost off the assignment: maybe not unique
+        found += 1
+        res, po = solve_and_check(engine, cost)
+        assert res.total == total
+        assert np.array_equal(po, rowsol), "unique optimum, different permutation"
+        assert np.array_equal(res.slot_owner.cpu().numpy(), colsol)
+    assert found >= 10
+
+
+def test_capacitated_permutation_equals_jv_oracle_when_unique(engine):
+    """Same with spot capacities: the expanded problem has cn[s] identical rows per spot, so only the cell -> spot
+    map can be unique; it must equal location_repeat[oracle assignment] (cytospace.py:331)."""
+    found = 0
+    for seed in range(40):
+        rng = np.random.default_rng(2000 + seed)
+        n_obj = int(rng.integers(5, 60))
+        cap = rng.integers(0, 4, n_obj).astype(np.int32); cap[0] += 1
+        n = int(cap.sum())
+        compact = rng.integers(-2_000_000, 2_000_000, (n_obj, n), dtype=np.int32)          # spots x cells
+        row_map = np.repeat(np.arange(n_obj, dtype=np.int32), cap)
+        rowsol, colsol, (total, u, v) = oracle.lapjv_i32(compact, row_map)
+        red = compact[row_map].astype(np.int64) - u[:, None] - v[None, :]
+        same_spot = row_map[:, None] == row_map[colsol][None, :]                            # arcs into a sibling slot of the own spot
+        red[same_spot] = 1
+        if red.min() <= 0:
+            continue
+        found += 1
+        res, po = solve_and_check(engine, np.ascontiguousarray(compact.T), cap)
+        assert res.total == total and np.array_equal(po, row_map[colsol])
+    assert found >= 10
+
+
+def test_price_overflow_is_reported_not_returned(engine):
+    """|cost| up to 2^30 times (P + 1) exceeds the 46-bit bid / label field for P >~ 32k (e.g. Euclidean costs at
+    the 2^30 clamp): the solve must fail loudly with the overflow status, never return a wrong 'optimum'."""
+    n = 33000
+    gen = torch.Generator(device=engine.device); gen.manual_seed(5)
+    dev = torch.randint(0, 2 ** 30 - 1, (n, (n + 31) // 32 * 32), generator=gen, device=engine.device, dtype=torch.int32)
+    with pytest.raises(RuntimeError, match="overflow"):
+        engine.lap_solve(dev, None, n_persons=n, n_objects=n)
+    # a matrix wider than the documented |cost| < 2^30 contract is refused as well
+    bad = torch.zeros((64, 64), dtype=torch.int32, device=engine.device)
+    bad[0, 0] = 2 ** 30 + 5; bad[1, 1] = -(2 ** 30) - 5
+    with pytest.raises(RuntimeError, match="overflow"):
+        engine.lap_solve(bad, None, n_persons=64, n_objects=64)

@@ -133,3 +133,45 @@ def test_apply_linear_assignment_sub_spots(engine):
     counts = locs.index.value_counts()
     assert all(counts[f"spot{s}"] == cn[s] for s in range(80))
     assert sorted(cells.tolist()) == sorted(sc_df.columns.tolist())
+
+
+def test_more_spots_than_cells_and_integer_counts(engine):
+    """--sampling-sub-spots hands every chunk a bincount(minlength=n_spots) capacity vector (cytospace.py:650-660):
+    most spots take no cell and there can be more spots than cells in the chunk.  Count matrices read with
+    read_csv are int64.  (both used to raise.)"""
+    rng = np.random.default_rng(4)
+    n_spots, n_cells = 300, 120
+    sc, st, _ = syn.structured_counts(n_cells, n_spots, 500, 1, seed=31)
+    cn = np.bincount(rng.integers(0, n_spots, n_cells), minlength=n_spots)
+    assert (cn == 0).sum() > n_spots - n_cells - 1
+    sc_n, st_n = co.normalize_data(sc), co.normalize_data(st)
+    mapped, _ = cytospace_b200.solve_linear_assignment_problem(sc_n, st_n, cn, "lapjv_b200", None, 1, "Pearson_correlation")
+    assert np.array_equal(np.bincount(mapped, minlength=n_spots), cn)
+    keep = np.flatnonzero(cn > 0)
+    want_cost = co.cost_matrix_i32(sc_n, st_n[:, keep])
+    row_map = np.repeat(np.arange(keep.size, dtype=np.int32), cn[keep])
+    _, res, cost = engine.assign(sc_n, st_n, cn)
+    assert res.total == oracle_total_on(np.ascontiguousarray(cost[:, :keep.size].T.cpu().numpy()), row_map)
+    assert abs(res.total - oracle_total_on(want_cost, row_map)) <= 4 * n_cells
+    # integer count matrices through the DataFrame entry point
+    sc_i, st_i = sc.astype(np.int64), st.astype(np.int64)
+    cells = [f"c{i}" for i in range(n_cells)]
+    sc_df = pd.DataFrame(sc_i, columns=cells); st_df = pd.DataFrame(st_i, columns=[f"s{i}" for i in range(n_spots)])
+    coords = pd.DataFrame({"row": np.arange(n_spots), "col": np.arange(n_spots)}, index=st_df.columns)
+    loc_i, ids_i = cytospace_b200.apply_linear_assignment(sc_df, st_df, coords, cn, "lapjv_b200", None, 1,
+                                                          "Pearson_correlation", 1, [np.arange(n_cells)])
+    loc_f, ids_f = cytospace_b200.apply_linear_assignment(sc_df.astype(np.float64), st_df.astype(np.float64), coords, cn,
+                                                          "lapjv_b200", None, 1, "Pearson_correlation", 1, [np.arange(n_cells)])
+    assert loc_i.index.tolist() == loc_f.index.tolist() and list(ids_i) == list(ids_f)
+
+
+def test_staged_upload_equals_plain_copy(engine):
+    """Host arrays above STAGE_MIN_BYTES travel through the pinned ring: byte-identical on the device."""
+    rng = np.random.default_rng(9)
+    x = rng.standard_normal((3000, 5001))                      # 120 MB, not a multiple of the slab size
+    assert x.nbytes > engine.STAGE_MIN_BYTES
+    d = engine.to_device(x)
+    torch.cuda.synchronize()
+    assert torch.equal(d.cpu(), torch.from_numpy(x))
+    xi = rng.integers(0, 50, (2000, 3000))                     # int64 -> float64 on the host
+    assert torch.equal(engine.to_device(xi).cpu(), torch.from_numpy(xi.astype(np.float64)))
