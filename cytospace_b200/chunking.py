@@ -106,15 +106,28 @@ class TorchTransport:
 SOLO = "solo"
 
 
-def _transport(group=None, transport=None):
+_native_transports = {}
+
+
+def _transport(group=None, transport=None, engine=None):
+    """The data plane of a distributed solve: an explicit transport, else -- with a process group of more than one
+    rank -- NCCL through the C ABI (``dist_native.NativeTransport``, bootstrapped over the group) when the group's
+    backend is NCCL and the engine lives on a GPU, ``TorchTransport`` otherwise (gloo in the CPU tests)."""
     if transport is SOLO:
         return None
     if transport is not None:
         return transport
     import torch.distributed as dist
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        return TorchTransport(dist, group)
-    return None
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1):
+        return None
+    dev = getattr(engine, "device", None)
+    if dist.get_backend(group) == "nccl" and dev is not None and dev.type == "cuda":
+        key = (id(engine), id(group))
+        if key not in _native_transports:
+            from . import dist_native
+            _native_transports[key] = dist_native.NativeTransport.from_torch_group(engine, group)
+        return _native_transports[key]
+    return TorchTransport(dist, group)
 
 
 #: bytes moved by the last distributed solve on this rank (bench.py reports them)
@@ -131,7 +144,7 @@ def solve_chunks(engine, sc_np, st_np, plan: list[Chunk], log_tpm: bool = False,
     matrices -- host arrays or tensors already on its GPU; other ranks may pass ``None`` -- and chunks are
     dealt by ``assign_ranks``.  ``assign_kw`` (``metric=``, ``cspr_seed=``) goes to ``engine.assign``
     unchanged (rank 0's values)."""
-    tp = _transport(group, transport)
+    tp = _transport(group, transport, engine)
     if tp is None:
         out = []
         sc_dev = st_dev = None

@@ -236,7 +236,7 @@ extern "C" int cyb_lap_check_i32(const int32_t *cost_dev, int64_t ld, int64_t n_
                                  size_t workspace_bytes, void *stream_v) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
     const int64_t np = n_persons, no = n_objects;
-    if (np <= 0 || np >= (1ll << kPersonBits) || no <= 0 || no > np)
+    if (np <= 0 || np >= (1ll << kPersonBits) || no <= 0 || no >= (1ll << kPersonBits))
         return cyb::set_error(CYB_ERR_INVALID, "cyb_lap_check_i32: persons=%lld objects=%lld out of range",
                               (long long)np, (long long)no);
     if (!cost_dev || !person_obj_dev || !price_dev || !out_dev || !workspace_dev)

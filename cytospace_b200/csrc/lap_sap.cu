@@ -1163,9 +1163,10 @@ extern "C" int cyb_lap_solve_i32(const int32_t *cost_dev, int64_t ld, int64_t n_
                                  int grid_hint, void *stream_v) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
     const int64_t np = n_persons, no = n_objects;
-    if (np <= 0 || np >= (1ll << kPB) - kSapMax || no <= 0 || no > np)
+    // (more objects than persons is legal with capacities: spots that take no cell are priced out)
+    if (np <= 0 || np >= (1ll << kPB) - kSapMax || no <= 0 || no >= (1ll << kPB) - kSapMax)
         return cyb::set_error(CYB_ERR_INVALID,
-                              "cyb_lap_solve_i32: persons=%lld objects=%lld outside 1 <= objects <= persons < 2^18 - 256",
+                              "cyb_lap_solve_i32: persons=%lld objects=%lld outside 1 <= persons, objects < 2^18 - 256",
                               (long long)np, (long long)no);
     if (!slot_offset_dev && no != np)
         return cyb::set_error(CYB_ERR_INVALID, "cyb_lap_solve_i32: without capacities the problem must be square");
@@ -1219,7 +1220,7 @@ extern "C" int cyb_lap_solve_i32(const int32_t *cost_dev, int64_t ld, int64_t n_
     P.nmoves = reinterpret_cast<int *>(ws + L.small + 96);
     P.rstat = reinterpret_cast<int *>(ws + L.small + 1280);              // 3 x 32 bytes
     P.srcdone = reinterpret_cast<int32_t *>(ws + L.small + 128);          // kSapMax ints = 1 KB
-    P.qcap = (int)((np + G - 1) / G);
+    P.qcap = (int)((std::max(np, no) + G - 1) / G);
     P.max_rounds = 2000ll * np + 100000;
     P.prefetch = no * 4 > 131072 ? 1 : 0;
     if (const char *e = getenv("CYB_LAP_PREFETCH")) P.prefetch = atoi(e) ? 1 : 0;

@@ -41,18 +41,17 @@ def _worker(rank, world, port, mode, native, q):
         from cytospace_b200 import chunking
         from cytospace_b200.engine import AssignmentEngine
         eng = AssignmentEngine(device=f"cuda:{rank}")
-        tp = None
-        if native:
-            from cytospace_b200 import dist_native
-            tp = dist_native.NativeTransport.from_torch_group(eng)
+        # default on GPUs: NCCL through the C ABI (dist_native.NativeTransport); the other variant sends the same
+        # tensors through torch.distributed's own NCCL process group
+        tp = None if native else chunking.TorchTransport(dist)
         sc, st, plan = _problem(mode)
         if rank == 0:
             out = chunking.solve_chunks(eng, sc, st, plan, log_tpm=True, transport=tp)
         else:
             out = chunking.solve_chunks(eng, None, None, None, log_tpm=True, transport=tp)
-        q.put((rank, out, dict(chunking.last_traffic)))
-        if tp is not None:
-            tp.close()
+        q.put((rank, out, dict(chunking.last_traffic), type(chunking._transport(None, tp, eng)).__name__))
+        for t_ in chunking._native_transports.values():
+            t_.close()
     finally:
         dist.destroy_process_group()
 
@@ -73,7 +72,8 @@ def test_two_gpu_chunk_distribution_matches_single_process(engine, mode, native)
         p.start()
     got = {}
     for _ in range(2):
-        r, out, traffic = q.get(timeout=300)
+        r, out, traffic, kind = q.get(timeout=300)
+        assert kind == ("NativeTransport" if native else "TorchTransport")
         got[r] = (out, traffic)
     for p in procs:
         p.join(timeout=120)

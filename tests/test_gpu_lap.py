@@ -270,20 +270,31 @@ def test_memory_variants_on_small_problems(engine, lap_golden, smem_prices, smem
     assert res.total == 0
 
 
+def _unique_optimum(compact, row_map, spot_of_cell):
+    """Is the optimal cell -> spot map unique?  Decided by the oracle itself: scale the costs by n + 1 and add 1 to
+    every arc of the optimum found -- any other optimal map would now be strictly cheaper and JV would return it."""
+    n = compact.shape[1]
+    pert = compact.astype(np.int64) * (n + 1)
+    pert[spot_of_cell, np.arange(n)] += 1
+    assert np.abs(pert).max() < 2 ** 30
+    _, colsol2, _ = oracle.lapjv_i32(pert.astype(np.int32), row_map)
+    spots2 = colsol2 if row_map is None else row_map[colsol2]
+    return np.array_equal(spots2, spot_of_cell)
+
+
 def test_permutation_equals_jv_oracle_when_the_optimum_is_unique(engine):
     """North-star: "permutation identical up to documented tie-breaks".  Where the optimum is unique there is no
-    tie to break: the device assignment must BE the JV oracle's.  Uniqueness is certified by the oracle's own
-    duals: every arc outside the optimal assignment has a strictly positive reduced cost."""
+    tie to break: the device assignment must BE the JV oracle's.  (Uniqueness is decided by the oracle, see
+    _unique_optimum; instances with ties -- small cost ranges -- are skipped and counted.)"""
     found = 0
-    for seed in range(40):
+    for seed in range(30):
         rng = np.random.default_rng(1000 + seed)
         n = int(rng.integers(40, 400))
-        cost = rng.integers(-2_000_000, 2_000_000, (n, n), dtype=np.int32)
+        high = int(rng.choice([50, 5000, 1_000_000]))
+        cost = rng.integers(-high, high, (n, n), dtype=np.int32)               # rows = slots, columns = cells
         rowsol, colsol, (total, u, v) = oracle.lapjv_i32(cost)
-        red = cost.astype(np.int64) - u[:, None] - v[None, :]
-        red[np.arange(n), rowsol] = 1
-        if red.min() <= 0:
-            continue                                   # a zero reduced cost off the assignment: maybe not unique
+        if not _unique_optimum(cost, None, colsol):
+            continue
         found += 1
         res, po = solve_and_check(engine, cost)
         assert res.total == total
@@ -296,18 +307,15 @@ def test_capacitated_permutation_equals_jv_oracle_when_unique(engine):
     """Same with spot capacities: the expanded problem has cn[s] identical rows per spot, so only the cell -> spot
     map can be unique; it must equal location_repeat[oracle assignment] (cytospace.py:331)."""
     found = 0
-    for seed in range(40):
+    for seed in range(30):
         rng = np.random.default_rng(2000 + seed)
         n_obj = int(rng.integers(5, 60))
         cap = rng.integers(0, 4, n_obj).astype(np.int32); cap[0] += 1
         n = int(cap.sum())
-        compact = rng.integers(-2_000_000, 2_000_000, (n_obj, n), dtype=np.int32)          # spots x cells
+        compact = rng.integers(-1_000_000, 1_000_000, (n_obj, n), dtype=np.int32)          # spots x cells
         row_map = np.repeat(np.arange(n_obj, dtype=np.int32), cap)
         rowsol, colsol, (total, u, v) = oracle.lapjv_i32(compact, row_map)
-        red = compact[row_map].astype(np.int64) - u[:, None] - v[None, :]
-        same_spot = row_map[:, None] == row_map[colsol][None, :]                            # arcs into a sibling slot of the own spot
-        red[same_spot] = 1
-        if red.min() <= 0:
+        if not _unique_optimum(compact, row_map, row_map[colsol]):
             continue
         found += 1
         res, po = solve_and_check(engine, np.ascontiguousarray(compact.T), cap)
