@@ -83,8 +83,9 @@ __global__ void __launch_bounds__(kChkThreads) lap_rowmin_kernel(
 constexpr int kChkWholeMax = 12288;              // 96 KB of prices -> two CTAs per SM
 constexpr int kTeam = 128;                       // threads per row team (measured: 256-thread teams are slower, 148 vs 102 us at 10k)
 constexpr int kTeams = kChkThreads / kTeam;
+constexpr int kBatch = 4;                        // 16-byte row loads in flight per thread
 
-__global__ void __launch_bounds__(kChkThreads) lap_rowcheck_whole_kernel(
+__global__ void __launch_bounds__(kChkThreads, 2) lap_rowcheck_whole_kernel(
     const int32_t *__restrict__ cost, long long ld, int np, int no, const int32_t *__restrict__ person_obj,
     const long long *__restrict__ price, long long S, int32_t *__restrict__ count, long long *__restrict__ acc,
     const int32_t *__restrict__ soff, long long *__restrict__ out, unsigned int *__restrict__ done) {
@@ -111,15 +112,25 @@ __global__ void __launch_bounds__(kChkThreads) lap_rowcheck_whole_kernel(
         const int c_o = (tt == 0 && o_ok) ? __ldg(r + o_cur) : 0;
         long long m = LLONG_MAX;
         const int4 *r4 = reinterpret_cast<const int4 *>(r);
-#pragma unroll 8
-        for (int q = tt; q < n4; q += kTeam) {
-            const int4 c = ld_stream(r4 + q, pol);
-            const longlong2 a = *reinterpret_cast<const longlong2 *>(spw + 4 * q);
-            const longlong2 bb = *reinterpret_cast<const longlong2 *>(spw + 4 * q + 2);
-            m = min(m, (long long)c.x * S + a.x);
-            m = min(m, (long long)c.y * S + a.y);
-            m = min(m, (long long)c.z * S + bb.x);
-            m = min(m, (long long)c.w * S + bb.y);
+        // four 16-byte loads per thread are requested before the first one is consumed (ncu, round 1: the loop was
+        // stalled on its own loads -- 9.5 long-scoreboard stalls per issue, 54.8 % DRAM throughput)
+        for (int q0 = tt; q0 < n4; q0 += kBatch * kTeam) {
+            int4 c[kBatch];
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) {
+                const int q = q0 + u * kTeam;
+                c[u] = q < n4 ? ld_stream(r4 + q, pol) : make_int4(INT_MAX, INT_MAX, INT_MAX, INT_MAX);
+            }
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) {
+                const int q = min(q0 + u * kTeam, n4 - 1);            // (a padded lane re-reads a valid price: its cost is INT_MAX)
+                const longlong2 a = *reinterpret_cast<const longlong2 *>(spw + 4 * q);
+                const longlong2 bb = *reinterpret_cast<const longlong2 *>(spw + 4 * q + 2);
+                m = min(m, (long long)c[u].x * S + a.x);
+                m = min(m, (long long)c[u].y * S + a.y);
+                m = min(m, (long long)c[u].z * S + bb.x);
+                m = min(m, (long long)c[u].w * S + bb.y);
+            }
         }
         for (int j = (n4 << 2) + tt; j < no; j += kTeam) m = min(m, (long long)__ldg(r + j) * S + spw[j]);
 #pragma unroll

@@ -718,6 +718,20 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
                 if (step > D) step = D;
                 if (step < 1) step = 1;
                 if (Tg > D - 1) Tg = D - 1;                                  // every eligible label is below D
+                // replicas of the lowered objects: position i of the bitmap -> word by binary search over the prefix counts.
+                // The first object of every thread is requested NOW, so that its round trip overlaps the atomicAdd
+                // round trip of the classification below.
+                auto lowered_object = [&](int i) -> int {
+                    int lo = 0, hi = nwords - 1;
+                    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (swbase[mid] <= i) lo = mid; else hi = mid - 1; }
+                    return lo * 32 + (int)__fns(sfront[lo], 0, i - swbase[lo] + 1);
+                };
+                int ro = -1; unsigned long long rkey = ~0ull; long long rlam = 0;
+                if ((SMEMP || SMEMO) && t < nchg) {
+                    ro = lowered_object(t);
+                    rkey = __ldcg(P.dkey + ro);
+                    if (SMEMP) rlam = __ldcg(P.lambda + ro);
+                }
                 // this CTA's slice: eligible = dirty, held and below D; candidates = eligible with label <= Tg
                 for (int ww = warp; ww < nmy; ww += kWarps) {
                     const int w = w0 + ww, o = w * 32 + lane;
@@ -752,13 +766,15 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
                         atomicMin(reinterpret_cast<unsigned long long *>(RS + 4), (unsigned long long)lmin);
                     }
                 }
-                // replicas of the lowered objects (position i of the bitmap -> word by binary search over the prefix counts)
+                // (the replicas of the lowered objects: loads requested above, stored here; the rest of a long list follows)
                 if (SMEMP || SMEMO) {
+                    if (ro >= 0 && rkey != ~0ull) {
+                        if (SMEMP) sarr[ro] = rlam >= kInf / 2 ? kGInf : rlam - (long long)(rkey >> kPB);
+                        if (SMEMO) spred[ro] = (int)(rkey & kPM);
+                    }
 #pragma unroll 2
-                    for (int i = t; i < nchg; i += kThreads) {
-                        int lo = 0, hi = nwords - 1;
-                        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (swbase[mid] <= i) lo = mid; else hi = mid - 1; }
-                        const int o = lo * 32 + (int)__fns(sfront[lo], 0, i - swbase[lo] + 1);
+                    for (int i = t + kThreads; i < nchg; i += kThreads) {
+                        const int o = lowered_object(i);
                         const unsigned long long key = __ldcg(P.dkey + o);
                         if (key != ~0ull) {
                             if (SMEMP) { const long long lam = __ldcg(P.lambda + o); sarr[o] = lam >= kInf / 2 ? kGInf : lam - (long long)(key >> kPB); }

@@ -29,6 +29,7 @@ class NativeTransport:
         with torch.cuda.device(engine.device):
             _native.check(self.lib.cyb_dist_init(self.ffi.from_buffer(id_bytes), world, rank, comm))
         self.comm = comm[0]
+        self.send_stream = None
 
     @classmethod
     def from_torch_group(cls, engine, group=None):
@@ -66,11 +67,20 @@ class NativeTransport:
                                                       root, self._stream()))
 
     def isend(self, t, dst):
+        """Asynchronous with respect to the compute stream: the send runs on a side stream behind everything queued
+        so far, so that the column gather of the next block overlaps it."""
         assert t.is_contiguous()
+        cur = torch.cuda.current_stream(self.engine.device)
+        if self.send_stream is None:
+            self.send_stream = torch.cuda.Stream(device=self.engine.device)
+        self.send_stream.wait_stream(cur)
         with torch.cuda.device(self.engine.device):
             _native.check(self.lib.cyb_dist_send(self.comm, _native.ptr("void *", t), t.numel() * t.element_size(), dst,
-                                                 self._stream()))
-        return self._event()
+                                                 _native.stream_ptr(self.send_stream)))
+        t.record_stream(self.send_stream)
+        ev = torch.cuda.Event()
+        ev.record(self.send_stream)
+        return _Done(ev)
 
     def recv(self, t, src):
         assert t.is_contiguous()
