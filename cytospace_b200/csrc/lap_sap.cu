@@ -82,7 +82,6 @@ constexpr long long kBidLimit = 1ll << 45;                     // 46-bit bid / l
 constexpr int kSapMax = 256;                                   // free persons a search can start from
 constexpr int kMultiMax = 32;                                  // augmenting paths per search (one warp each)
 constexpr int kRowsMax = 32;                                   // rows a CTA relaxes per chunk
-constexpr int kWave = 6;                                       // 16-byte row loads a thread requests before the first is consumed (two 10k rows = 5 per thread)
 constexpr int kMaxSearch = 1 << 24;
 
 struct SapParams {
@@ -171,9 +170,10 @@ __device__ __forceinline__ bool spin_until(unsigned int *bar, unsigned int targe
     long long t0 = 0;
     bool dead = false;
     for (;;) {
-        // relaxed polls, ONE acquire once the counter is there (an acquire load per poll invalidates the L1 every time)
-        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
-        if ((int)(v - target) >= 0) { asm volatile("fence.acq_rel.gpu;" ::: "memory"); break; }
+        // (relaxed polls + one acquire fence at the end measured slower: 50.6 -> 54 ms at cfg2 together with a 6-deep
+        // first wave in the relax; both reverted)
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+        if ((int)(v - target) >= 0) break;
         if ((++spins & 0x3FFu) == 0) {
             int a;
             asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(a) : "l"(abortf) : "memory");
@@ -903,9 +903,9 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
                     const unsigned long long pol = l2_policy_evict_first();
                     const int n4 = vec_ok ? (no >> 2) : 0;
                     const long long total4 = (long long)nrv * n4;
-                    int4 wv0[kWave];
+                    int4 wv0[4];
 #pragma unroll
-                    for (int u = 0; u < kWave; ++u) {
+                    for (int u = 0; u < 4; ++u) {
                         const long long idx = (long long)t + (long long)u * kThreads;
                         wv0[u] = make_int4(0, 0, 0, 0);
                         if (idx < total4) {
@@ -968,12 +968,12 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
                         }
                     };
 #pragma unroll
-                    for (int u = 0; u < kWave; ++u) {
+                    for (int u = 0; u < 4; ++u) {
                         const long long idx = (long long)t + (long long)u * kThreads;
                         if (idx < total4) { const int row = (int)(idx / n4); relax4(row, (int)(idx - (long long)row * n4), wv0[u]); }
                     }
 #pragma unroll 4
-                    for (long long idx = (long long)t + (long long)kWave * kThreads; idx < total4; idx += kThreads) {
+                    for (long long idx = (long long)t + 4ll * kThreads; idx < total4; idx += kThreads) {
                         const int row = (int)(idx / n4), q = (int)(idx - (long long)row * n4);
                         relax4(row, q, ld_stream(reinterpret_cast<const int4 *>(rowptr(rw_person[row])) + q, pol));
                     }
