@@ -102,6 +102,9 @@ class TorchTransport:
         return out
 
 
+#: owners fed concurrently by one NCCL group of sends (rank 0 holds the blocks of two groups at most)
+SEND_GROUP = 4
+
 #: pass as ``transport=`` to run every chunk on the calling rank although a process group is up
 SOLO = "solo"
 
@@ -212,10 +215,21 @@ def _solve_chunks_distributed(tp, engine, sc_np, st_np, plan, log_tpm, assign_kw
         tp.broadcast(st_all, root=0)
         traffic["bcast_bytes"] += n_genes * n_spots * esz
 
-    # per-chunk column blocks: point-to-point from rank 0 to the owner; at most two blocks in flight, each
-    # freed as soon as its send has completed
+    # per-chunk column blocks: point-to-point from rank 0 to the owner.  With a grouping transport the blocks of up to
+    # SEND_GROUP chunks (different owners) leave as one NCCL group, so that rank 0's whole NVLink egress is used; at
+    # most two groups (or two single blocks) are in flight, each freed as soon as its send has completed.
     mine = {}
     inflight = []
+    batch = []
+
+    def flush():
+        if batch:
+            inflight.append((tp.send_group(list(batch)), list(batch)))
+            batch.clear()
+        while len(inflight) > 2:
+            req, _keep = inflight.pop(0)
+            req.wait()
+
     for ch in plan:
         o = owner[ch.idx]
         need_st = ch.st_index is not None
@@ -225,6 +239,12 @@ def _solve_chunks_distributed(tp, engine, sc_np, st_np, plan, log_tpm, assign_kw
                 blocks.append(_columns(engine, st_dev, ch.st_index, tp))
             if o == 0:
                 mine[ch.idx] = (blocks[0], blocks[1] if need_st else None)
+            elif hasattr(tp, "send_group"):
+                for blk in blocks:
+                    batch.append((blk.contiguous(), o))
+                    traffic["p2p_bytes"] += blk.numel() * esz
+                if len({d for _b, d in batch}) >= SEND_GROUP:
+                    flush()
             else:
                 for blk in blocks:
                     blk = blk.contiguous()
@@ -242,6 +262,8 @@ def _solve_chunks_distributed(tp, engine, sc_np, st_np, plan, log_tpm, assign_kw
                 tp.recv(st_blk, 0)
             mine[ch.idx] = (sc_blk, st_blk)
             traffic["p2p_bytes"] += (sc_blk.numel() + (st_blk.numel() if need_st else 0)) * esz
+    if rank == 0:
+        flush()
     for req, _blk in inflight:
         req.wait()
     inflight.clear()

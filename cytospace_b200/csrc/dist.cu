@@ -33,6 +33,8 @@ struct NcclApi {
     ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
     ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t);
     const char *(*GetErrorString)(ncclResult_t);
+    ncclResult_t (*GroupStart)();
+    ncclResult_t (*GroupEnd)();
     bool ok = false;
 };
 
@@ -52,9 +54,11 @@ NcclApi &api() {
         CYB_SYM(Recv, "ncclRecv");
         CYB_SYM(AllGather, "ncclAllGather");
         CYB_SYM(GetErrorString, "ncclGetErrorString");
+        CYB_SYM(GroupStart, "ncclGroupStart");
+        CYB_SYM(GroupEnd, "ncclGroupEnd");
 #undef CYB_SYM
         a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.Broadcast && a.Send && a.Recv && a.AllGather &&
-               a.GetErrorString;
+               a.GetErrorString && a.GroupStart && a.GroupEnd;
     });
     return a;
 }
@@ -131,6 +135,18 @@ extern "C" int cyb_dist_recv(void *comm, void *buf_dev, size_t bytes, int peer, 
     CYB_NCCL_READY();
     if (!comm || (!buf_dev && bytes)) return cyb::set_error(CYB_ERR_INVALID, "cyb_dist_recv: null pointer");
     CYB_NCCL_CHECK(api().Recv(buf_dev, bytes, ncclUint8, peer, static_cast<ncclComm_t>(comm), static_cast<cudaStream_t>(stream)));
+    return CYB_OK;
+}
+
+extern "C" int cyb_dist_group_start(void) {
+    CYB_NCCL_READY();
+    CYB_NCCL_CHECK(api().GroupStart());
+    return CYB_OK;
+}
+
+extern "C" int cyb_dist_group_end(void) {
+    CYB_NCCL_READY();
+    CYB_NCCL_CHECK(api().GroupEnd());
     return CYB_OK;
 }
 

@@ -82,6 +82,26 @@ class NativeTransport:
         ev.record(self.send_stream)
         return _Done(ev)
 
+    def send_group(self, blocks):
+        """``blocks`` = [(tensor, dst), ...] sent as ONE NCCL group on the side stream: transfers to different owners
+        progress concurrently (a single peer-to-peer pair does not fill rank 0's NVLink egress)."""
+        cur = torch.cuda.current_stream(self.engine.device)
+        if self.send_stream is None:
+            self.send_stream = torch.cuda.Stream(device=self.engine.device)
+        self.send_stream.wait_stream(cur)
+        with torch.cuda.device(self.engine.device):
+            _native.check(self.lib.cyb_dist_group_start())
+            for t, dst in blocks:
+                assert t.is_contiguous()
+                _native.check(self.lib.cyb_dist_send(self.comm, _native.ptr("void *", t), t.numel() * t.element_size(), dst,
+                                                     _native.stream_ptr(self.send_stream)))
+            _native.check(self.lib.cyb_dist_group_end())
+        for t, _dst in blocks:
+            t.record_stream(self.send_stream)
+        ev = torch.cuda.Event()
+        ev.record(self.send_stream)
+        return _Done(ev)
+
     def recv(self, t, src):
         assert t.is_contiguous()
         with torch.cuda.device(self.engine.device):

@@ -278,6 +278,10 @@ int cyb_dist_destroy(void *comm);
 int cyb_dist_broadcast(void *comm, void *buf_dev, size_t bytes, int root, void *stream);
 int cyb_dist_send(void *comm, const void *buf_dev, size_t bytes, int peer, void *stream);
 int cyb_dist_recv(void *comm, void *buf_dev, size_t bytes, int peer, void *stream);
+/* sends / receives issued between the two calls progress concurrently (ncclGroupStart / ncclGroupEnd): rank 0
+ * feeds several owners at once, so that its NVLink egress -- not one peer-to-peer channel set -- is the limit. */
+int cyb_dist_group_start(void);
+int cyb_dist_group_end(void);
 /* recv_dev holds n_ranks * bytes_per_rank bytes, rank r's part at r * bytes_per_rank. */
 int cyb_dist_all_gather(void *comm, const void *send_dev, void *recv_dev, size_t bytes_per_rank, void *stream);
 
