@@ -55,7 +55,7 @@
 //
 // Tuning knobs (environment, read at launch): CYB_LAP_SAP_T (free persons at which the search
 // takes over), CYB_LAP_SAP_K (rows per search round), CYB_LAP_SAP_MULTI (paths per search, <= 32),
-// CYB_LAP_THETA, CYB_LAP_EPS0, CYB_LAP_SMEM_PRICES=0 / CYB_LAP_SMEM_OWNER=0 (force the L2 paths).
+// CYB_LAP_THETA, CYB_LAP_EPS0, CYB_LAP_SMEM_PRICES=0 / CYB_LAP_SMEM_OWNER=0 / CYB_LAP_APPROX=0 (force the L2 paths).
 
 #include <algorithm>
 #include <climits>
@@ -335,15 +335,28 @@ __device__ __forceinline__ void cheapest_slot(const SapParams &P, int o, int t_n
     }
 }
 
+constexpr int kApxShift = 16;
+// 32-bit prefix of g = lambda - label: floor(g / 2^16), clamped; floor(a) + floor(b) <= floor(a + b), so
+// (v >> 16) + apx <= (thr >> 16) is NECESSARY for v + g < thr -- the filter never drops a relaxation.
+__device__ __forceinline__ int apx_of(long long lam, long long d) {
+    if (lam >= kInf / 2) return INT_MAX;
+    const long long h = (lam - d) >> kApxShift;
+    return (int)max((long long)(INT_MIN + 1), min((long long)(INT_MAX - 1), h));
+}
+
 // SMEMP: prices (auction) / g (search) in shared memory.  SMEMO: slot-owner, tree-predecessor and
 // (capacitated) cheapest-slot replicas in shared memory.
-template <bool SMEMP, bool SMEMO>
+// APX (only without SMEMP): 32-bit prefixes g >> 16 of the search snapshot in shared memory, a conservative filter in front
+// of the exact test (50k objects: 200 KB instead of 16 bytes of lambda / label per row element through L2).
+template <bool SMEMP, bool SMEMO, bool APX>
 __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int np = P.P, no = P.O;
     size_t off = 0;
     long long *sarr = reinterpret_cast<long long *>(smem_raw);
+    int *sh32 = reinterpret_cast<int *>(smem_raw);                     // APX: [O]
     if (SMEMP) off += ((size_t)no * 8 + 15) / 16 * 16;
+    else if (APX) off += ((size_t)no * 4 + 15) / 16 * 16;
     long long *myqd = reinterpret_cast<long long *>(smem_raw + off);   // [qcap] labels of this CTA's frontier objects
     off += ((size_t)P.qcap * 8 + 15) / 16 * 16;
     int *myq = reinterpret_cast<int *>(smem_raw + off);                // [qcap] work queue (persons / frontier objects)
@@ -598,6 +611,7 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
             for (int w = b * kThreads + t; w < 3 * ((no + 31) / 32); w += G * kThreads) P.chgbits[w / ((no + 31) / 32)][w % ((no + 31) / 32)] = 0u;
             if (b == 0 && t < 24) { if ((t & 7) == 4 || (t & 7) == 5) P.rstat[t] = -1; else P.rstat[t] = 0; }      // dmin = all ones
             if (SMEMP) for (int o = t; o < no; o += kThreads) { const long long l = sarr[o]; sarr[o] = l >= kInf / 2 ? kGInf : l - kInf; }
+            if (APX) for (int o = t; o < no; o += kThreads) sh32[o] = capacity(o) > 0 ? INT_MIN : INT_MAX;      // unreached: always a candidate; priced out: never
             GRID_BARRIER();
             // (every CTA has finished applying the previous search's moves: their buffers can be reset)
             if (b == 0 && t == 0) P.nmoves[0] = 0;
@@ -680,7 +694,7 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
                 // the objects the previous round lowered, as a bitmap in shared memory + prefix counts: their
                 // g = lambda - d and tree predecessor replicas are refreshed below
                 int nchg = 0;
-                if (SMEMP || SMEMO) {
+                if (SMEMP || SMEMO || APX) {
                     for (int wb = 0; wb < nwords; wb += kThreads) {
                         const int w = wb + t;
                         unsigned cw = 0;
@@ -729,10 +743,10 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
                     return lo * 32 + (int)__fns(sfront[lo], 0, i - swbase[lo] + 1);
                 };
                 int ro = -1; unsigned long long rkey = ~0ull; long long rlam = 0;
-                if ((SMEMP || SMEMO) && t < nchg) {
+                if ((SMEMP || SMEMO || APX) && t < nchg) {
                     ro = lowered_object(t);
                     rkey = __ldcg(P.dkey + ro);
-                    if (SMEMP) rlam = __ldcg(P.lambda + ro);
+                    if (SMEMP || APX) rlam = __ldcg(P.lambda + ro);
                 }
                 // this CTA's slice: eligible = dirty, held and below D; candidates = eligible with label <= Tg
                 for (int ww = warp; ww < nmy; ww += kWarps) {
@@ -769,9 +783,10 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
                     }
                 }
                 // (the replicas of the lowered objects: loads requested above, stored here; the rest of a long list follows)
-                if (SMEMP || SMEMO) {
+                if (SMEMP || SMEMO || APX) {
                     if (ro >= 0 && rkey != ~0ull) {
                         if (SMEMP) sarr[ro] = rlam >= kInf / 2 ? kGInf : rlam - (long long)(rkey >> kPB);
+                        if (APX) sh32[ro] = apx_of(rlam, (long long)(rkey >> kPB));
                         if (SMEMO) spred[ro] = (int)(rkey & kPM);
                     }
 #pragma unroll 2
@@ -780,6 +795,7 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
                         const unsigned long long key = __ldcg(P.dkey + o);
                         if (key != ~0ull) {
                             if (SMEMP) { const long long lam = __ldcg(P.lambda + o); sarr[o] = lam >= kInf / 2 ? kGInf : lam - (long long)(key >> kPB); }
+                            if (APX) sh32[o] = apx_of(__ldcg(P.lambda + o), (long long)(key >> kPB));
                             if (SMEMO) spred[o] = (int)(key & kPM);
                         }
                     }
@@ -793,7 +809,7 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
                     sh_i[0] = __ldcg(RS + 0); sh_i[1] = __ldcg(RS + 1); sh_i[2] = __ldcg(RS + 2);
                     sh_ll[1] = (long long)__ldcg(reinterpret_cast<unsigned long long *>(RS + 4));
                 }
-                if (!(SMEMP || SMEMO)) {} else { for (int w = t; w < nwords; w += kThreads) sfront[w] = 0u; }
+                if (SMEMP || SMEMO || APX) for (int w = t; w < nwords; w += kThreads) sfront[w] = 0u;       // (held the lowered bitmap in phase 1)
                 __syncthreads();
                 const int ncand = sh_i[0], wC = sh_i[1], wE = sh_i[2];
                 const long long dmin_el = sh_ll[1];
@@ -902,14 +918,15 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
                     if (t < nrv) cval = __ldg(rowptr(rw_person[t]) + myq[rw_qi2[t]]);
                     const unsigned long long pol = l2_policy_evict_first();
                     const int n4 = vec_ok ? (no >> 2) : 0;
-                    const long long total4 = (long long)nrv * n4;
+                    const unsigned total4 = (unsigned)nrv * (unsigned)n4;          // <= 32 rows x 65k int4: 32-bit index arithmetic
+                    const unsigned un4 = (unsigned)max(n4, 1);
                     int4 wv0[4];
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
-                        const long long idx = (long long)t + (long long)u * kThreads;
+                        const unsigned idx = (unsigned)t + (unsigned)u * kThreads;
                         wv0[u] = make_int4(0, 0, 0, 0);
                         if (idx < total4) {
-                            const int row = (int)(idx / n4), q = (int)(idx - (long long)row * n4);
+                            const int row = (int)(idx / un4), q = (int)(idx - (unsigned)row * un4);
                             wv0[u] = ld_stream(reinterpret_cast<const int4 *>(rowptr(rw_person[row])) + q, pol);
                         }
                     }
@@ -958,6 +975,14 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
                             const longlong2 bb = *reinterpret_cast<const longlong2 *>(sarr + j + 2);
                             relax(j, c.x, thr, slot, a.x, 0); relax(j + 1, c.y, thr, slot, a.y, 0);
                             relax(j + 2, c.z, thr, slot, bb.x, 0); relax(j + 3, c.w, thr, slot, bb.y, 0);
+                        } else if (APX) {
+                            // conservative 32-bit filter; the rare survivors take the exact test against lambda / label in L2
+                            const int4 h = *reinterpret_cast<const int4 *>(sh32 + j);
+                            const long long ts = thr >> kApxShift;
+                            if ((((long long)(c.x - cmin) * S) >> kApxShift) + h.x <= ts) relax(j, c.x, thr, slot, __ldcg(P.lambda + j), __ldcg(P.dkey + j));
+                            if ((((long long)(c.y - cmin) * S) >> kApxShift) + h.y <= ts) relax(j + 1, c.y, thr, slot, __ldcg(P.lambda + j + 1), __ldcg(P.dkey + j + 1));
+                            if ((((long long)(c.z - cmin) * S) >> kApxShift) + h.z <= ts) relax(j + 2, c.z, thr, slot, __ldcg(P.lambda + j + 2), __ldcg(P.dkey + j + 2));
+                            if ((((long long)(c.w - cmin) * S) >> kApxShift) + h.w <= ts) relax(j + 3, c.w, thr, slot, __ldcg(P.lambda + j + 3), __ldcg(P.dkey + j + 3));
                         } else {
                             const longlong2 a = __ldcg(reinterpret_cast<const longlong2 *>(P.lambda + j));
                             const longlong2 bb = __ldcg(reinterpret_cast<const longlong2 *>(P.lambda + j + 2));
@@ -969,20 +994,22 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
                     };
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
-                        const long long idx = (long long)t + (long long)u * kThreads;
-                        if (idx < total4) { const int row = (int)(idx / n4); relax4(row, (int)(idx - (long long)row * n4), wv0[u]); }
+                        const unsigned idx = (unsigned)t + (unsigned)u * kThreads;
+                        if (idx < total4) { const int row = (int)(idx / un4); relax4(row, (int)(idx - (unsigned)row * un4), wv0[u]); }
                     }
 #pragma unroll 4
-                    for (long long idx = (long long)t + 4ll * kThreads; idx < total4; idx += kThreads) {
-                        const int row = (int)(idx / n4), q = (int)(idx - (long long)row * n4);
+                    for (unsigned idx = (unsigned)t + 4u * kThreads; idx < total4; idx += kThreads) {
+                        const int row = (int)(idx / un4), q = (int)(idx - (unsigned)row * un4);
                         relax4(row, q, ld_stream(reinterpret_cast<const int4 *>(rowptr(rw_person[row])) + q, pol));
                     }
                     // columns beyond the vector part
                     for (int row = 0; row < nrv; ++row) {
                         const int32_t *r = rowptr(rw_person[row]);
                         for (int j = (n4 << 2) + t; j < no; j += kThreads) {
-                            if (SMEMP) relax(j, __ldg(r + j), rw_thr[row], (unsigned long long)rw_slot2[row], sarr[j], 0);
-                            else relax(j, __ldg(r + j), rw_thr[row], (unsigned long long)rw_slot2[row], __ldcg(P.lambda + j), __ldcg(P.dkey + j));
+                            const int cj = __ldg(r + j);
+                            if (SMEMP) relax(j, cj, rw_thr[row], (unsigned long long)rw_slot2[row], sarr[j], 0);
+                            else if (!APX || (((long long)(cj - cmin) * S) >> kApxShift) + sh32[j] <= (rw_thr[row] >> kApxShift))
+                                relax(j, cj, rw_thr[row], (unsigned long long)rw_slot2[row], __ldcg(P.lambda + j), __ldcg(P.dkey + j));
                         }
                     }
                 }
@@ -1133,7 +1160,7 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
     if (b == 0 && t == 0) {
         P.stats[0] = status; P.stats[1] = phases; P.stats[2] = rounds; P.stats[3] = st_acc[0];
         P.stats[4] = phases - 1; P.stats[5] = cmin; P.stats[6] = cmax; P.stats[7] = S;
-        P.stats[8] = G; P.stats[9] = SMEMP ? 1 : 0; P.stats[10] = 2 + (SMEMO ? 1 : 0); P.stats[11] = st_acc[1];
+        P.stats[8] = G; P.stats[9] = SMEMP ? 1 : 0; P.stats[10] = 2 + (SMEMO ? 1 : 0) + (APX ? 2 : 0); P.stats[11] = st_acc[1];
         P.stats[12] = (phases - 1) * (long long)np; P.stats[14] = searches; P.stats[15] = srounds;
         P.stats[16] = st_acc[3]; P.stats[17] = st_acc[4]; P.stats[18] = st_acc[5]; P.stats[19] = st_acc[6]; P.stats[20] = st_acc[7];
         P.stats[21] = paths; P.stats[22] = st_acc[9]; P.stats[23] = st_acc[10]; P.stats[24] = st_acc[11];
@@ -1276,8 +1303,16 @@ extern "C" int cyb_lap_solve_i32(const int32_t *cost_dev, int64_t ld, int64_t n_
     if (const char *e = getenv("CYB_LAP_SMEM_OWNER")) smemo = smemo && atoi(e);
     if (smemo) dyn += owner_bytes;
 
-    const void *fn = smemp ? (smemo ? (const void *)lap_sap_kernel<true, true> : (const void *)lap_sap_kernel<true, false>)
-                           : (const void *)lap_sap_kernel<false, false>;
+    // without room for the 8-byte prices their 32-bit search prefixes may still fit (50k objects: 200 KB)
+    // (OFF by default, CYB_LAP_APPROX=1 enables it.  Measured at 50k x 50k: the relax drops 217 -> 153 ms, but
+    // refreshing the prefixes costs 40 ms in the classification and the 200 KB carve-out slows the bid scans and the
+    // replay by 11 ms: 565 -> 590 ms in total.)
+    bool apx = false;
+    if (const char *e = getenv("CYB_LAP_APPROX"))
+        apx = atoi(e) && !smemp && dyn + cyb::align_up((size_t)no * 4, 16) + static_smem <= (size_t)max_smem;
+    if (apx) dyn += cyb::align_up((size_t)no * 4, 16);
+    const void *fn = smemp ? (smemo ? (const void *)lap_sap_kernel<true, true, false> : (const void *)lap_sap_kernel<true, false, false>)
+                           : (apx ? (const void *)lap_sap_kernel<false, false, true> : (const void *)lap_sap_kernel<false, false, false>);
     CYB_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
     int occ = 0;
     CYB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kThreads, dyn));
