@@ -44,8 +44,8 @@
 // i): eps-CS is kept exactly, so auction rounds and searches mix freely inside a phase.
 //
 // Determinism.  A relaxation only counts if it is STRICTLY below the label the object had when the
-// round started (shared-memory snapshot g[k] = lambda[k] - d[k]; without shared-memory prices: the
-// racy global label plus "equal labels only displace an entry written this round"), so the labels
+// round started (snapshot g[k] = lambda[k] - d[k]: in shared memory, or in L2 kept by the slice
+// owners when the prices do not fit), so the labels
 // and the (label, slot) minima do not depend on the interleaving; the lists built with atomics are
 // sets.  Same assignment for any grid size (tested against the CPU model).
 //
@@ -55,7 +55,7 @@
 //
 // Tuning knobs (environment, read at launch): CYB_LAP_SAP_T (free persons at which the search
 // takes over), CYB_LAP_SAP_K (rows per search round), CYB_LAP_SAP_MULTI (paths per search, <= 32),
-// CYB_LAP_THETA, CYB_LAP_EPS0, CYB_LAP_SMEM_PRICES=0 / CYB_LAP_SMEM_OWNER=0 / CYB_LAP_APPROX=0 (force the L2 paths).
+// CYB_LAP_THETA, CYB_LAP_EPS0, CYB_LAP_SMEM_PRICES=0 / CYB_LAP_SMEM_OWNER=0 (force the L2 paths).
 
 #include <algorithm>
 #include <climits>
@@ -101,6 +101,7 @@ struct SapParams {
     int *gmm;                // [0] cmin, [1] cmax, [2] status
     // search state
     unsigned long long *dkey;        // [O] (label << 18 | entering slot; sources are P + k), ~0 = unreached
+    long long *gsnap;                // [O] lambda - (label at the start of the round), for the variants without shared-memory prices
     unsigned *chgbits[3];            // [(O+31)/32] objects whose label a round lowered, rotating by round
     int32_t *claim;                  // [O + kSapMax] path claims (decreasing base per search)
     int4 *moves;                     // [P] (person, object, slot, -) of the accepted paths
@@ -335,28 +336,15 @@ __device__ __forceinline__ void cheapest_slot(const SapParams &P, int o, int t_n
     }
 }
 
-constexpr int kApxShift = 16;
-// 32-bit prefix of g = lambda - label: floor(g / 2^16), clamped; floor(a) + floor(b) <= floor(a + b), so
-// (v >> 16) + apx <= (thr >> 16) is NECESSARY for v + g < thr -- the filter never drops a relaxation.
-__device__ __forceinline__ int apx_of(long long lam, long long d) {
-    if (lam >= kInf / 2) return INT_MAX;
-    const long long h = (lam - d) >> kApxShift;
-    return (int)max((long long)(INT_MIN + 1), min((long long)(INT_MAX - 1), h));
-}
-
 // SMEMP: prices (auction) / g (search) in shared memory.  SMEMO: slot-owner, tree-predecessor and
 // (capacitated) cheapest-slot replicas in shared memory.
-// APX (only without SMEMP): 32-bit prefixes g >> 16 of the search snapshot in shared memory, a conservative filter in front
-// of the exact test (50k objects: 200 KB instead of 16 bytes of lambda / label per row element through L2).
-template <bool SMEMP, bool SMEMO, bool APX>
+template <bool SMEMP, bool SMEMO>
 __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int np = P.P, no = P.O;
     size_t off = 0;
     long long *sarr = reinterpret_cast<long long *>(smem_raw);
-    int *sh32 = reinterpret_cast<int *>(smem_raw);                     // APX: [O]
     if (SMEMP) off += ((size_t)no * 8 + 15) / 16 * 16;
-    else if (APX) off += ((size_t)no * 4 + 15) / 16 * 16;
     long long *myqd = reinterpret_cast<long long *>(smem_raw + off);   // [qcap] labels of this CTA's frontier objects
     off += ((size_t)P.qcap * 8 + 15) / 16 * 16;
     int *myq = reinterpret_cast<int *>(smem_raw + off);                // [qcap] work queue (persons / frontier objects)
@@ -607,11 +595,13 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
             if (searches >= kMaxSearch) { status = CYB_ERR_NOT_CONVERGED; break; }
             const int cbase = (kMaxSearch - searches) * kMultiMax;
             // S0: labels unreached, lists empty; shared memory switches from prices to g = lambda - d
-            for (int o = b * kThreads + t; o < no; o += G * kThreads) P.dkey[o] = ~0ull;
+            for (int o = b * kThreads + t; o < no; o += G * kThreads) {
+                P.dkey[o] = ~0ull;
+                if (!SMEMP) { const long long lam = __ldcg(P.lambda + o); P.gsnap[o] = lam >= kInf / 2 ? kGInf : lam - kInf; }
+            }
             for (int w = b * kThreads + t; w < 3 * ((no + 31) / 32); w += G * kThreads) P.chgbits[w / ((no + 31) / 32)][w % ((no + 31) / 32)] = 0u;
             if (b == 0 && t < 24) { if ((t & 7) == 4 || (t & 7) == 5) P.rstat[t] = -1; else P.rstat[t] = 0; }      // dmin = all ones
             if (SMEMP) for (int o = t; o < no; o += kThreads) { const long long l = sarr[o]; sarr[o] = l >= kInf / 2 ? kGInf : l - kInf; }
-            if (APX) for (int o = t; o < no; o += kThreads) sh32[o] = capacity(o) > 0 ? INT_MIN : INT_MAX;      // unreached: always a candidate; priced out: never
             GRID_BARRIER();
             // (every CTA has finished applying the previous search's moves: their buffers can be reset)
             if (b == 0 && t == 0) P.nmoves[0] = 0;
@@ -694,7 +684,7 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
                 // the objects the previous round lowered, as a bitmap in shared memory + prefix counts: their
                 // g = lambda - d and tree predecessor replicas are refreshed below
                 int nchg = 0;
-                if (SMEMP || SMEMO || APX) {
+                if (SMEMP || SMEMO) {
                     for (int wb = 0; wb < nwords; wb += kThreads) {
                         const int w = wb + t;
                         unsigned cw = 0;
@@ -718,7 +708,6 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
                         __syncthreads();
                     }
                 } else {
-                    for (int w = t; w < nwords; w += kThreads) sfront[w] = 0u;      // frontier bitmask of the L2-label tie rule
                     __syncthreads();
                 }
                 // D = the want-th smallest label of an object with a free slot
@@ -743,10 +732,10 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
                     return lo * 32 + (int)__fns(sfront[lo], 0, i - swbase[lo] + 1);
                 };
                 int ro = -1; unsigned long long rkey = ~0ull; long long rlam = 0;
-                if ((SMEMP || SMEMO || APX) && t < nchg) {
+                if ((SMEMP || SMEMO) && t < nchg) {
                     ro = lowered_object(t);
                     rkey = __ldcg(P.dkey + ro);
-                    if (SMEMP || APX) rlam = __ldcg(P.lambda + ro);
+                    if (SMEMP) rlam = __ldcg(P.lambda + ro);
                 }
                 // this CTA's slice: eligible = dirty, held and below D; candidates = eligible with label <= Tg
                 for (int ww = warp; ww < nmy; ww += kWarps) {
@@ -762,6 +751,11 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
                         }
                     }
                     sld[ww * 32 + lane] = d;
+                    if (!SMEMP && o < no && key != ~0ull && ((cbw >> lane) & 1u)) {
+                        // without shared-memory prices the round-start snapshot g = lambda - label lives in L2, kept by the slice owners
+                        const long long lam = __ldcg(P.lambda + o);
+                        P.gsnap[o] = lam >= kInf / 2 ? kGInf : lam - d;
+                    }
                     const bool cnd = el && d <= Tg;
                     const unsigned mel = __ballot_sync(0xffffffffu, el), mc = __ballot_sync(0xffffffffu, cnd);
                     int base = 0;
@@ -783,10 +777,9 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
                     }
                 }
                 // (the replicas of the lowered objects: loads requested above, stored here; the rest of a long list follows)
-                if (SMEMP || SMEMO || APX) {
+                if (SMEMP || SMEMO) {
                     if (ro >= 0 && rkey != ~0ull) {
                         if (SMEMP) sarr[ro] = rlam >= kInf / 2 ? kGInf : rlam - (long long)(rkey >> kPB);
-                        if (APX) sh32[ro] = apx_of(rlam, (long long)(rkey >> kPB));
                         if (SMEMO) spred[ro] = (int)(rkey & kPM);
                     }
 #pragma unroll 2
@@ -795,7 +788,6 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
                         const unsigned long long key = __ldcg(P.dkey + o);
                         if (key != ~0ull) {
                             if (SMEMP) { const long long lam = __ldcg(P.lambda + o); sarr[o] = lam >= kInf / 2 ? kGInf : lam - (long long)(key >> kPB); }
-                            if (APX) sh32[o] = apx_of(__ldcg(P.lambda + o), (long long)(key >> kPB));
                             if (SMEMO) spred[o] = (int)(key & kPM);
                         }
                     }
@@ -809,7 +801,6 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
                     sh_i[0] = __ldcg(RS + 0); sh_i[1] = __ldcg(RS + 1); sh_i[2] = __ldcg(RS + 2);
                     sh_ll[1] = (long long)__ldcg(reinterpret_cast<unsigned long long *>(RS + 4));
                 }
-                if (SMEMP || SMEMO || APX) for (int w = t; w < nwords; w += kThreads) sfront[w] = 0u;       // (held the lowered bitmap in phase 1)
                 __syncthreads();
                 const int ncand = sh_i[0], wC = sh_i[1], wE = sh_i[2];
                 const long long dmin_el = sh_ll[1];
@@ -865,7 +856,6 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
                     if (fr) {
                         const int o = (int)(ent & kPM);
                         if (pos % G == b) { myq[pos / G] = o; myqd[pos / G] = d; }
-                        if (!SMEMP) atomicOr(&sfront[o >> 5], 1u << (o & 31));
                     }
                     nfront += tot;
                 }
@@ -937,33 +927,16 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
                         rw_thr[t] = (long long)(cval - cmin) * S + lam_minus_d - eps;
                     }
                     __syncthreads();
-                    auto relax = [&](int k, int c, long long thr, unsigned long long slot, long long gk_or_lam, unsigned long long curkey) {
-                        if (SMEMP) {
-                            // g form: strictly below the label of the round start
-                            const long long v = (long long)(c - cmin) * S;
-                            if (v + gk_or_lam < thr) {
-                                const long long nd = v + __ldcg(P.lambda + k) - thr;
-                                if (nd >= kBidLimit) { atomicExch(P.gmm + 2, CYB_ERR_OVERFLOW); return; }
-                                const unsigned long long key = ((unsigned long long)nd << kPB) | slot;
-                                const unsigned long long prev = atomicMin(P.dkey + k, key);
-                                if (key < prev) atomicOr(NB + (k >> 5), 1u << (k & 31));
-                            }
-                        } else {
-                            if (gk_or_lam >= kInf / 2) return;
-                            const long long nd = (long long)(c - cmin) * S + gk_or_lam - thr;
-                            const long long rd = curkey == ~0ull ? kInf : (long long)(curkey >> kPB);
-                            bool go = nd < rd;
-                            if (!go && nd == rd) {
-                                // equal labels only displace an entry written in THIS round (its writer is in the frontier)
-                                const int ps = (int)(curkey & kPM);
-                                if (ps < np) { const int po = obj_of_slot(ps); go = (sfront[po >> 5] >> (po & 31)) & 1u; }
-                            }
-                            if (go) {
-                                if (nd >= kBidLimit) { atomicExch(P.gmm + 2, CYB_ERR_OVERFLOW); return; }
-                                const unsigned long long key = ((unsigned long long)nd << kPB) | slot;
-                                const unsigned long long prev = atomicMin(P.dkey + k, key);
-                                if (key < prev) atomicOr(NB + (k >> 5), 1u << (k & 31));
-                            }
+                    // one element: g = lambda[k] - (label of k when the round started) from shared memory (SMEMP) or from the
+                    // snapshot array the slice owners keep in L2; the relaxation counts iff it is STRICTLY below that label
+                    auto relax = [&](int k, int c, long long thr, unsigned long long slot, long long g) {
+                        const long long v = (long long)(c - cmin) * S;
+                        if (v + g < thr) {
+                            const long long nd = v + __ldcg(P.lambda + k) - thr;
+                            if (nd >= kBidLimit) { atomicExch(P.gmm + 2, CYB_ERR_OVERFLOW); return; }
+                            const unsigned long long key = ((unsigned long long)nd << kPB) | slot;
+                            const unsigned long long prev = atomicMin(P.dkey + k, key);
+                            if (key < prev) atomicOr(NB + (k >> 5), 1u << (k & 31));
                         }
                     };
                     auto relax4 = [&](int row, int q, const int4 &c) {
@@ -973,23 +946,13 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
                         if (SMEMP) {
                             const longlong2 a = *reinterpret_cast<const longlong2 *>(sarr + j);
                             const longlong2 bb = *reinterpret_cast<const longlong2 *>(sarr + j + 2);
-                            relax(j, c.x, thr, slot, a.x, 0); relax(j + 1, c.y, thr, slot, a.y, 0);
-                            relax(j + 2, c.z, thr, slot, bb.x, 0); relax(j + 3, c.w, thr, slot, bb.y, 0);
-                        } else if (APX) {
-                            // conservative 32-bit filter; the rare survivors take the exact test against lambda / label in L2
-                            const int4 h = *reinterpret_cast<const int4 *>(sh32 + j);
-                            const long long ts = thr >> kApxShift;
-                            if ((((long long)(c.x - cmin) * S) >> kApxShift) + h.x <= ts) relax(j, c.x, thr, slot, __ldcg(P.lambda + j), __ldcg(P.dkey + j));
-                            if ((((long long)(c.y - cmin) * S) >> kApxShift) + h.y <= ts) relax(j + 1, c.y, thr, slot, __ldcg(P.lambda + j + 1), __ldcg(P.dkey + j + 1));
-                            if ((((long long)(c.z - cmin) * S) >> kApxShift) + h.z <= ts) relax(j + 2, c.z, thr, slot, __ldcg(P.lambda + j + 2), __ldcg(P.dkey + j + 2));
-                            if ((((long long)(c.w - cmin) * S) >> kApxShift) + h.w <= ts) relax(j + 3, c.w, thr, slot, __ldcg(P.lambda + j + 3), __ldcg(P.dkey + j + 3));
+                            relax(j, c.x, thr, slot, a.x); relax(j + 1, c.y, thr, slot, a.y);
+                            relax(j + 2, c.z, thr, slot, bb.x); relax(j + 3, c.w, thr, slot, bb.y);
                         } else {
-                            const longlong2 a = __ldcg(reinterpret_cast<const longlong2 *>(P.lambda + j));
-                            const longlong2 bb = __ldcg(reinterpret_cast<const longlong2 *>(P.lambda + j + 2));
-                            const ulonglong2 ka = __ldcg(reinterpret_cast<const ulonglong2 *>(P.dkey + j));
-                            const ulonglong2 kb = __ldcg(reinterpret_cast<const ulonglong2 *>(P.dkey + j + 2));
-                            relax(j, c.x, thr, slot, a.x, ka.x); relax(j + 1, c.y, thr, slot, a.y, ka.y);
-                            relax(j + 2, c.z, thr, slot, bb.x, kb.x); relax(j + 3, c.w, thr, slot, bb.y, kb.y);
+                            const longlong2 a = __ldcg(reinterpret_cast<const longlong2 *>(P.gsnap + j));
+                            const longlong2 bb = __ldcg(reinterpret_cast<const longlong2 *>(P.gsnap + j + 2));
+                            relax(j, c.x, thr, slot, a.x); relax(j + 1, c.y, thr, slot, a.y);
+                            relax(j + 2, c.z, thr, slot, bb.x); relax(j + 3, c.w, thr, slot, bb.y);
                         }
                     };
 #pragma unroll
@@ -1007,9 +970,8 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
                         const int32_t *r = rowptr(rw_person[row]);
                         for (int j = (n4 << 2) + t; j < no; j += kThreads) {
                             const int cj = __ldg(r + j);
-                            if (SMEMP) relax(j, cj, rw_thr[row], (unsigned long long)rw_slot2[row], sarr[j], 0);
-                            else if (!APX || (((long long)(cj - cmin) * S) >> kApxShift) + sh32[j] <= (rw_thr[row] >> kApxShift))
-                                relax(j, cj, rw_thr[row], (unsigned long long)rw_slot2[row], __ldcg(P.lambda + j), __ldcg(P.dkey + j));
+                            if (SMEMP) relax(j, cj, rw_thr[row], (unsigned long long)rw_slot2[row], sarr[j]);
+                            else relax(j, cj, rw_thr[row], (unsigned long long)rw_slot2[row], __ldcg(P.gsnap + j));
                         }
                     }
                 }
@@ -1160,7 +1122,7 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
     if (b == 0 && t == 0) {
         P.stats[0] = status; P.stats[1] = phases; P.stats[2] = rounds; P.stats[3] = st_acc[0];
         P.stats[4] = phases - 1; P.stats[5] = cmin; P.stats[6] = cmax; P.stats[7] = S;
-        P.stats[8] = G; P.stats[9] = SMEMP ? 1 : 0; P.stats[10] = 2 + (SMEMO ? 1 : 0) + (APX ? 2 : 0); P.stats[11] = st_acc[1];
+        P.stats[8] = G; P.stats[9] = SMEMP ? 1 : 0; P.stats[10] = 2 + (SMEMO ? 1 : 0); P.stats[11] = st_acc[1];
         P.stats[12] = (phases - 1) * (long long)np; P.stats[14] = searches; P.stats[15] = srounds;
         P.stats[16] = st_acc[3]; P.stats[17] = st_acc[4]; P.stats[18] = st_acc[5]; P.stats[19] = st_acc[6]; P.stats[20] = st_acc[7];
         P.stats[21] = paths; P.stats[22] = st_acc[9]; P.stats[23] = st_acc[10]; P.stats[24] = st_acc[11];
@@ -1169,7 +1131,7 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
 }
 
 struct SapLayout {
-    size_t list[3], rec[3], bidw[3], flag, slot_price, person_slot, minslot, slot_obj, dkey, chgbits[3], cand[3], claim, moves, small, total;
+    size_t list[3], rec[3], bidw[3], flag, slot_price, person_slot, minslot, slot_obj, dkey, gsnap, chgbits[3], cand[3], claim, moves, small, total;
 };
 
 SapLayout sap_layout(int64_t np, int64_t no) {
@@ -1185,6 +1147,7 @@ SapLayout sap_layout(int64_t np, int64_t no) {
     L.minslot = take((size_t)no * 4);
     L.slot_obj = take((size_t)np * 4);
     L.dkey = take((size_t)no * 8);
+    L.gsnap = take((size_t)no * 8);
     for (int k = 0; k < 3; ++k) L.chgbits[k] = take((size_t)((no + 31) / 32) * 4);
     for (int k = 0; k < 3; ++k) L.cand[k] = take((size_t)no * 8);
     L.claim = take((size_t)(no + kSapMax) * 4);
@@ -1258,6 +1221,7 @@ extern "C" int cyb_lap_solve_i32(const int32_t *cost_dev, int64_t ld, int64_t n_
     P.minslot = reinterpret_cast<int32_t *>(ws + L.minslot);
     P.slot_obj = reinterpret_cast<int32_t *>(ws + L.slot_obj);
     P.dkey = reinterpret_cast<unsigned long long *>(ws + L.dkey);
+    P.gsnap = reinterpret_cast<long long *>(ws + L.gsnap);
     P.claim = reinterpret_cast<int32_t *>(ws + L.claim);
     P.moves = reinterpret_cast<int4 *>(ws + L.moves);
     P.bar = reinterpret_cast<unsigned int *>(ws + L.small);
@@ -1303,16 +1267,8 @@ extern "C" int cyb_lap_solve_i32(const int32_t *cost_dev, int64_t ld, int64_t n_
     if (const char *e = getenv("CYB_LAP_SMEM_OWNER")) smemo = smemo && atoi(e);
     if (smemo) dyn += owner_bytes;
 
-    // without room for the 8-byte prices their 32-bit search prefixes may still fit (50k objects: 200 KB)
-    // (OFF by default, CYB_LAP_APPROX=1 enables it.  Measured at 50k x 50k: the relax drops 217 -> 153 ms, but
-    // refreshing the prefixes costs 40 ms in the classification and the 200 KB carve-out slows the bid scans and the
-    // replay by 11 ms: 565 -> 590 ms in total.)
-    bool apx = false;
-    if (const char *e = getenv("CYB_LAP_APPROX"))
-        apx = atoi(e) && !smemp && dyn + cyb::align_up((size_t)no * 4, 16) + static_smem <= (size_t)max_smem;
-    if (apx) dyn += cyb::align_up((size_t)no * 4, 16);
-    const void *fn = smemp ? (smemo ? (const void *)lap_sap_kernel<true, true, false> : (const void *)lap_sap_kernel<true, false, false>)
-                           : (apx ? (const void *)lap_sap_kernel<false, false, true> : (const void *)lap_sap_kernel<false, false, false>);
+    const void *fn = smemp ? (smemo ? (const void *)lap_sap_kernel<true, true> : (const void *)lap_sap_kernel<true, false>)
+                           : (const void *)lap_sap_kernel<false, false>;
     CYB_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
     int occ = 0;
     CYB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kThreads, dyn));

@@ -101,8 +101,8 @@ def test_matches_cpu_model_of_the_device_algorithm(engine, knobs):
              (rng.integers(-100_000, 100_000, (700, 700), dtype=np.int32), None)]
     # the default schedule on every memory variant, the other schedules on the default variant
     variants = MEMORY_VARIANTS if knobs is SAP_KNOBS[0] else MEMORY_VARIANTS[:1]
-    for (mat, cp), (sp, so_, ap) in [(c, v) for c in cases for v in variants]:
-        env = dict(_sap_env(knobs), CYB_LAP_SMEM_PRICES=sp, CYB_LAP_SMEM_OWNER=so_, CYB_LAP_APPROX=ap)
+    for (mat, cp), (sp, so_) in [(c, v) for c in cases for v in variants]:
+        env = dict(_sap_env(knobs), CYB_LAP_SMEM_PRICES=sp, CYB_LAP_SMEM_OWNER=so_)
         res, po = _with_env(env, lambda: solve_and_check(engine, mat, cp))
         po_model, so_model, tot_model, lam_model, st, _ = oracle.sap_model(mat, cp, **knobs)
         assert res.total == tot_model and np.array_equal(po, po_model)
@@ -245,21 +245,20 @@ def test_certificate_tiled_variant_above_12288_objects(engine):
     assert engine.lap_check(dev, res)["capacity_mismatch"] == 2
 
 
-MEMORY_VARIANTS = [(1, 1, 1), (1, 0, 1), (0, 0, 1), (0, 0, 0)]      # (smem prices, smem owners, 32-bit search prefixes)
+MEMORY_VARIANTS = [(1, 1), (1, 0), (0, 0)]      # (prices / search snapshot in shared memory, slot owners / predecessors in shared memory)
 
 
-@pytest.mark.parametrize("smem_prices,smem_owner,approx", MEMORY_VARIANTS)
-def test_memory_variants_on_small_problems(engine, lap_golden, smem_prices, smem_owner, approx):
+@pytest.mark.parametrize("smem_prices,smem_owner", MEMORY_VARIANTS)
+def test_memory_variants_on_small_problems(engine, lap_golden, smem_prices, smem_owner):
     """The code paths of problems too large for shared memory, forced on small inputs: slot owners / tree
-    predecessors read from global memory (25k and up: CYB_LAP_SMEM_OWNER=0), prices streamed from L2 with the
-    32-bit search prefixes in shared memory (50k: CYB_LAP_SMEM_PRICES=0) and without them (CYB_LAP_APPROX=0).
-    Same totals AND the same assignment as the default path."""
-    env = {"CYB_LAP_SMEM_PRICES": smem_prices, "CYB_LAP_SMEM_OWNER": smem_owner, "CYB_LAP_APPROX": approx}
+    predecessors read from global memory (25k and up: CYB_LAP_SMEM_OWNER=0), prices and the search snapshot
+    streamed from L2 (50k: CYB_LAP_SMEM_PRICES=0).  Same totals AND the same assignment as the default path."""
+    env = {"CYB_LAP_SMEM_PRICES": smem_prices, "CYB_LAP_SMEM_OWNER": smem_owner}
     for name in LAP_NAMES:
         cost = lap_golden[f"{name}_cost"]
         res, po = _with_env(env, lambda: solve_and_check(engine, cost))
         assert res.total == int(lap_golden[f"{name}_opt"]) and res.stats["smem_prices"] == smem_prices
-        assert res.stats["tail_mode"] == 2 + smem_owner + (2 if (approx and not smem_prices) else 0)      # the variant that ran
+        assert res.stats["tail_mode"] == 2 + smem_owner                                                  # the variant that ran
     rng = np.random.default_rng(12)
     cap = rng.integers(0, 5, 300).astype(np.int32)
     m = rng.integers(-200_000, 200_000, (int(cap.sum()), 300), dtype=np.int32)
