@@ -105,6 +105,25 @@ class TorchTransport:
 #: owners fed concurrently by one NCCL group of sends (rank 0 holds the blocks of two groups at most)
 SEND_GROUP = 4
 
+#: send float64 blocks as float32 when every value survives the round trip exactly (raw counts do)
+NARROW_EXACT = True
+
+
+def _exact_in_float32(x, block=4096):
+    for c0 in range(0, x.shape[1], block):
+        blk = x[:, c0:c0 + block]
+        if not bool((blk.to(torch.float32).to(torch.float64) == blk).all()):
+            return False
+    return True
+
+
+def _to_float32(x, block=8192):
+    out = torch.empty(x.shape, dtype=torch.float32, device=x.device)
+    for c0 in range(0, x.shape[1], block):
+        out[:, c0:c0 + block] = x[:, c0:c0 + block]
+    return out
+
+
 #: pass as ``transport=`` to run every chunk on the calling rank although a process group is up
 SOLO = "solo"
 
@@ -204,9 +223,21 @@ def _solve_chunks_distributed(tp, engine, sc_np, st_np, plan, log_tpm, assign_kw
 
     # rank 0: ONE upload of each matrix (pinned staging ring); chunk columns are gathered on the device
     sc_dev = st_dev = None
+    narrow = False
     if rank == 0:
         sc_dev = engine.to_device(sc_np, tdt)
         st_dev = engine.to_device(st_np, tdt)
+        # Lossless narrowing of the wire format: raw count matrices (what apply_linear_assignment hands over,
+        # normalize_data being fused into the device pre-pass) are small integers stored as float64 -- every value
+        # is exactly a float32, so the blocks travel as float32 (half the NVLink bytes) and the owners, whose kernels
+        # widen every element back to double on load, compute bit-identical statistics.  Checked, not assumed.
+        if tdt == torch.float64 and NARROW_EXACT and sc_dev.is_cuda:
+            narrow = _exact_in_float32(sc_dev) and _exact_in_float32(st_dev)
+            if narrow:
+                sc_dev, st_dev = _to_float32(sc_dev), _to_float32(st_dev)
+    narrow = bool(tp.bcast_object(narrow if rank == 0 else None, root=0))
+    if narrow:
+        tdt, esz = torch.float32, 4
 
     st_all = None
     if shared_st:
