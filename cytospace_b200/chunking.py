@@ -109,21 +109,6 @@ SEND_GROUP = 4
 NARROW_EXACT = True
 
 
-def _exact_in_float32(x, block=4096):
-    for c0 in range(0, x.shape[1], block):
-        blk = x[:, c0:c0 + block]
-        if not bool((blk.to(torch.float32).to(torch.float64) == blk).all()):
-            return False
-    return True
-
-
-def _to_float32(x, block=8192):
-    out = torch.empty(x.shape, dtype=torch.float32, device=x.device)
-    for c0 in range(0, x.shape[1], block):
-        out[:, c0:c0 + block] = x[:, c0:c0 + block]
-    return out
-
-
 #: pass as ``transport=`` to run every chunk on the calling rank although a process group is up
 SOLO = "solo"
 
@@ -209,35 +194,31 @@ def _solve_chunks_distributed(tp, engine, sc_np, st_np, plan, log_tpm, assign_kw
     dev = engine.device
     rank, world = tp.rank, tp.world
     traffic = {"bcast_bytes": 0, "p2p_bytes": 0, "gather_bytes": 0}
-    # plan and shapes travel as one small object broadcast (host metadata, not the data path)
+    # rank 0: ONE upload of each matrix (pinned staging ring); chunk columns are gathered on the device
+    sc_dev = st_dev = None
     meta = None
     if rank == 0:
         # float32 stays float32; anything else (float64, integer counts) is float64 as in the reference
         dt = "float32" if str(sc_np.dtype).endswith("float32") and str(st_np.dtype).endswith("float32") else "float64"
-        meta = (plan, int(sc_np.shape[0]), int(st_np.shape[1]), dt, dict(assign_kw))
-    plan, n_genes, n_spots, dt, assign_kw = tp.bcast_object(meta, root=0)
-    tdt = torch.float64 if dt == "float64" else torch.float32
-    esz = 8 if dt == "float64" else 4
-    owner = assign_ranks([c.n for c in plan], world)
-    shared_st = any(c.st_index is None for c in plan)
-
-    # rank 0: ONE upload of each matrix (pinned staging ring); chunk columns are gathered on the device
-    sc_dev = st_dev = None
-    narrow = False
-    if rank == 0:
+        tdt = torch.float64 if dt == "float64" else torch.float32
         sc_dev = engine.to_device(sc_np, tdt)
         st_dev = engine.to_device(st_np, tdt)
         # Lossless narrowing of the wire format: raw count matrices (what apply_linear_assignment hands over,
         # normalize_data being fused into the device pre-pass) are small integers stored as float64 -- every value
         # is exactly a float32, so the blocks travel as float32 (half the NVLink bytes) and the owners, whose kernels
         # widen every element back to double on load, compute bit-identical statistics.  Checked, not assumed.
-        if tdt == torch.float64 and NARROW_EXACT and sc_dev.is_cuda:
-            narrow = _exact_in_float32(sc_dev) and _exact_in_float32(st_dev)
-            if narrow:
-                sc_dev, st_dev = _to_float32(sc_dev), _to_float32(st_dev)
-    narrow = bool(tp.bcast_object(narrow if rank == 0 else None, root=0))
-    if narrow:
-        tdt, esz = torch.float32, 4
+        if tdt == torch.float64 and NARROW_EXACT and sc_dev.is_cuda and hasattr(engine, "narrow_exact"):
+            sc32, st32 = engine.narrow_exact(sc_dev), engine.narrow_exact(st_dev)       # one fused pass each
+            if sc32 is not None and st32 is not None:
+                dt, sc_dev, st_dev = "float32", sc32, st32
+            del sc32, st32
+        # plan, shapes and wire dtype travel as one small object broadcast (host metadata, not the data path)
+        meta = (plan, int(sc_np.shape[0]), int(st_np.shape[1]), dt, dict(assign_kw))
+    plan, n_genes, n_spots, dt, assign_kw = tp.bcast_object(meta, root=0)
+    tdt = torch.float64 if dt == "float64" else torch.float32
+    esz = 8 if dt == "float64" else 4
+    owner = assign_ranks([c.n for c in plan], world)
+    shared_st = any(c.st_index is None for c in plan)
 
     st_all = None
     if shared_st:

@@ -206,7 +206,19 @@ class AssignmentEngine:
         main.wait_stream(st["stream"])
         return out
 
-    # --------------------------------------------------------------- cost build
+    @_on_engine_device
+    def narrow_exact(self, x: torch.Tensor):
+        """float32 copy of a contiguous float64 device matrix if EVERY value is exactly representable (raw counts are),
+        else None -- ``cyb_narrow_f64_to_f32``, one pass.  Used for the wire format of chunk blocks."""
+        if x.dtype != torch.float64 or not x.is_contiguous():
+            return None
+        out = torch.empty(x.shape, dtype=torch.float32, device=x.device)
+        flag = torch.zeros(1, dtype=torch.int32, device=x.device)
+        _native.check(self.lib.cyb_narrow_f64_to_f32(_native.ptr("double *", x), x.numel(), _native.ptr("float *", out),
+                                                     _native.ptr("int32_t *", flag), self._stream()))
+        self.launches += 1
+        return None if int(flag.item()) else out
+
     @_on_engine_device
     def cost_build(self, sc: torch.Tensor, st: torch.Tensor, log_tpm: bool = False, out: torch.Tensor | None = None,
                    return_colstats: bool = False, check_variance: bool = True, layout: str = "cells_x_spots",

@@ -291,6 +291,12 @@ int cyb_gather_columns(const void *x_dev, int x_dtype, int64_t n_rows, int64_t l
                        const int32_t *cols_dev, int64_t n_cols_out, void *out_dev, int64_t ld_out,
                        void *stream);
 
+/* out[i] = (float) x[i] for a contiguous float64 buffer of n elements; *inexact_dev (int32, zeroed by the caller) is
+ * OR-ed with 1 when some value does not survive the round trip exactly (NaN counts as inexact).  The wire format of the
+ * chunk blocks: raw count matrices (cytospace.py:398: the input of normalize_data) are exact in float32, which halves
+ * the NVLink bytes of cyb_dist_send without changing a single bit of the result (the kernels widen on load). */
+int cyb_narrow_f64_to_f32(const double *x_dev, int64_t n, float *out_dev, int32_t *inexact_dev, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
