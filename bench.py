@@ -156,8 +156,9 @@ def run_reference(args, wl):
     threads = max(1, cores // workers)
     # CPU code needs no warm-up: at most one untimed step, so that the timed ones can be as large as possible
     warmup = min(args.warmup, 1)
-    budget_s = 240.0 / max(1, args.steps + warmup) / -(-n_units // workers)
-    est_full = 45.0 * (wl["n_cells"] / 10000.0) ** 2.6 * (wl["n_genes"] / 20000.0) ** 0.5 * (8.0 / min(8, threads)) ** 0.5
+    # one full-size cfg2 step measured here: 42 s on 8 cores (float64 cost build ~25 s, tie noise, float64 JV ~12 s)
+    budget_s = 330.0 / max(1, args.steps + warmup) / -(-n_units // workers)
+    est_full = 42.0 * (wl["n_cells"] / 10000.0) ** 2.6 * (wl["n_genes"] / 20000.0) ** 0.5 * (8.0 / min(16, max(threads, 1))) ** 0.5
     n = min(500, wl["n_cells"])
     for cand in (wl["n_cells"], 8000, 7000, 6000, 5000, 4000, 3000, 2000, 1000, 500):
         if cand <= wl["n_cells"] and est_full * (cand / wl["n_cells"]) ** 2.6 <= budget_s:

@@ -934,9 +934,11 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
                         if (v + g < thr) {
                             const long long nd = v + __ldcg(P.lambda + k) - thr;
                             if (nd >= kBidLimit) { atomicExch(P.gmm + 2, CYB_ERR_OVERFLOW); return; }
-                            const unsigned long long key = ((unsigned long long)nd << kPB) | slot;
-                            const unsigned long long prev = atomicMin(P.dkey + k, key);
-                            if (key < prev) atomicOr(NB + (k >> 5), 1u << (k & 31));
+                            // strictly below the round-start label: whoever wins the minimum, the label IS lowered in this
+                            // round, so the bit can be set without waiting for the atomic's return value (both are
+                            // fire-and-forget reductions: no round trip on the relax path)
+                            atomicMin(P.dkey + k, ((unsigned long long)nd << kPB) | slot);
+                            atomicOr(NB + (k >> 5), 1u << (k & 31));
                         }
                     };
                     auto relax4 = [&](int row, int q, const int4 &c) {
