@@ -30,3 +30,18 @@ def test_reference_arm_is_silent_on_other_ranks():
                           "--steps", "1", "--warmup", "0", "--gpus", "2"], capture_output=True, text=True, timeout=600,
                          cwd=ROOT, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_reference_arm_mirrors_nop_for_several_gpus():
+    """`--gpus 2`: two independent units on two worker processes sharing the cores (the reference's `-nop 2`,
+    cytospace.py:430); the value is the aggregate over both units, BLAS threads are split between the workers even when
+    the launcher exported OMP_NUM_THREADS=1 (torchrun does)."""
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "cfg1",
+                          "--steps", "1", "--warmup", "1", "--gpus", "2"], capture_output=True, text=True, timeout=900,
+                         cwd=ROOT, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    d = json.loads([l for l in out.stdout.splitlines() if l.strip()][0])
+    assert d["n_gpus"] == 2 and d["config"]["units"] == 2 and d["config"]["worker_processes"] == min(2, os.cpu_count() or 1)
+    assert d["config"]["same_config"] is True and d["config"]["sample_n"] == 1000
+    assert d["config"]["blas_threads_per_worker"] >= 1 and d["value"] > 0
