@@ -658,7 +658,7 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
             const int nwords = (no + 31) / 32;
             const int w0 = b * P.wpc, nmy = max(0, min(nwords, w0 + P.wpc) - w0);
             for (int ww = t; ww < P.wpc; ww += kThreads) sdirty_loc[ww] = 0u;
-            long long Tg = -1;                   // this round's guess: candidates are the eligible labels <= Tg
+            long long Tg = step;                 // this round's guess: candidates are the eligible labels <= Tg (round 0 leaves labels 0)
             for (;;) {
                 ++rid;
                 if (b == 0 && t == 0) st_tm[1] = global_ns();

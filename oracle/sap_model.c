@@ -176,7 +176,7 @@ int sap_model_i32(int P, int O, const int32_t *m, int64_t ld, const int32_t *cap
                 for (int o = 0; o < O; ++o) if (d[o] < SAP_INF / 2) { dirty[ndirty++] = o; indirty[o] = 1; }
                 int want = nfree < nfo ? nfree : nfo;
                 if (multi <= 0) want = 1; else if (want > multi) want = (int)multi;
-                int64_t D = SAP_INF, T = -1, Tg = -1, Tnext = -1;
+                int64_t D = SAP_INF, T = -1, Tg = step, Tnext = -1;         /* round 0 leaves labels 0: the first guess is one window */
                 for (;;) {
                     /* D = the want-th smallest label of an object with a free slot */
                     int nc = 0;
