@@ -55,7 +55,7 @@
 //
 // Tuning knobs (environment, read at launch): CYB_LAP_SAP_T (free persons at which the search
 // takes over), CYB_LAP_SAP_K (rows per search round), CYB_LAP_SAP_MULTI (paths per search, <= 32),
-// CYB_LAP_THETA, CYB_LAP_EPS0, CYB_LAP_SMEM_PRICES=0 / CYB_LAP_SMEM_OWNER=0 (force the L2 paths).
+// CYB_LAP_WARM (0: every search starts from scratch), CYB_LAP_THETA, CYB_LAP_EPS0, CYB_LAP_SMEM_PRICES=0 / CYB_LAP_SMEM_OWNER=0 (force the L2 paths).
 
 #include <algorithm>
 #include <climits>
@@ -113,6 +113,7 @@ struct SapParams {
     int qcap;
     long long max_rounds;
     int sap_t, sap_k, multi;
+    int warm;                        // 1: a search that follows another one in the phase starts from the surviving forest
     int theta, eps0_div;
     int packed_reduce, prefetch;
 };
@@ -359,6 +360,12 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
     off += ((size_t)P.wpc * 4 + 15) / 16 * 16;
     int *swbase = reinterpret_cast<int *>(smem_raw + off);             // [(O+31)/32] frontier rank of a word's first bit
     off += ((size_t)((no + 31) / 32) * 4 + 15) / 16 * 16;
+    unsigned *sreach = reinterpret_cast<unsigned *>(smem_raw + off);   // [(O+31)/32] SMEMO: objects the finished search reached
+    off += ((size_t)((no + 31) / 32) * 4 + 15) / 16 * 16;
+    unsigned *skept = reinterpret_cast<unsigned *>(smem_raw + off);    // [(O+31)/32] SMEMO: forest nodes the next search keeps
+    off += ((size_t)((no + 31) / 32) * 4 + 15) / 16 * 16;
+    unsigned *sdrop = reinterpret_cast<unsigned *>(smem_raw + off);    // [(O+31)/32] SMEMO: forest nodes it forgets
+    off += ((size_t)((no + 31) / 32) * 4 + 15) / 16 * 16;
     int *sowner = reinterpret_cast<int *>(smem_raw + off);             // SMEMO: [P]
     int *spred = sowner + ((np + 3) & ~3);                             // SMEMO: [O]
     int *sminslot = spred + ((no + 3) & ~3);                           // SMEMO && soff: [O]
@@ -367,7 +374,7 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
     __shared__ int red_j[32], wcnt[32];
     __shared__ long long st_tm[8];
     __shared__ long long st_acc[12];   // bids, max bidders, -, small rounds, ns bid / barrier / replay / sap, relax hits, sap ns select, sap ns trace
-    __shared__ int ssrc[kSapMax], sfo[kSapMax];
+    __shared__ int ssrc[kSapMax], sfo[kSapMax], ssmap[kSapMax];
     __shared__ long long sfo_d[kSapMax];
     __shared__ int hist[256];
     __shared__ long long sh_ll[4];      // broadcast slots: [0] D, [1] dmin, [2] dmax, [3] T
@@ -590,13 +597,14 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
             if (t < F) ssrc[t] = __ldcg(P.list[cur] + t);
             __syncthreads();
         }
+        bool warm = false;                       // the forest of the previous search of this phase is available
         while (F > 0) {
             ++searches;
             if (searches >= kMaxSearch) { status = CYB_ERR_NOT_CONVERGED; break; }
             const int cbase = (kMaxSearch - searches) * kMultiMax;
             // S0: labels unreached, lists empty; shared memory switches from prices to g = lambda - d
             for (int o = b * kThreads + t; o < no; o += G * kThreads) {
-                P.dkey[o] = ~0ull;
+                if (!warm) P.dkey[o] = ~0ull;                         // (a warm search keeps the labels written at the end of the previous one)
                 if (!SMEMP) { const long long lam = __ldcg(P.lambda + o); P.gsnap[o] = lam >= kInf / 2 ? kGInf : lam - kInf; }
             }
             for (int w = b * kThreads + t; w < 3 * ((no + 31) / 32); w += G * kThreads) P.chgbits[w / ((no + 31) / 32)][w % ((no + 31) / 32)] = 0u;
@@ -659,6 +667,7 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
             const int w0 = b * P.wpc, nmy = max(0, min(nwords, w0 + P.wpc) - w0);
             for (int ww = t; ww < P.wpc; ww += kThreads) sdirty_loc[ww] = 0u;
             long long Tg = step;                 // this round's guess: candidates are the eligible labels <= Tg (round 0 leaves labels 0)
+            bool repair = warm;                  // first round of a warm search: every surviving tree node relaxes again
             for (;;) {
                 ++rid;
                 if (b == 0 && t == 0) st_tm[1] = global_ns();
@@ -722,7 +731,7 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
                 if (D >= kInf / 2) { status = CYB_ERR_NOT_CONVERGED; break; }     // cannot happen: round 0 reaches every object
                 if (step > D) step = D;
                 if (step < 1) step = 1;
-                if (Tg > D - 1) Tg = D - 1;                                  // every eligible label is below D
+                if (Tg > D - 1 || repair) Tg = D - 1;                        // every eligible label is below D
                 // replicas of the lowered objects: position i of the bitmap -> word by binary search over the prefix counts.
                 // The first object of every thread is requested NOW, so that its round trip overlaps the atomicAdd
                 // round trip of the classification below.
@@ -819,7 +828,7 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
                 // T = about K rows' worth of the smallest candidates: 256 power-of-two bins over [dmin_el, Tg], upper
                 // edge of the first bin where the cumulative slot count reaches K (Tg when the candidates hold fewer)
                 long long T = Tg;
-                if (wC > P.sap_k) {
+                if (wC > P.sap_k && !repair) {
                     int sh = 0;
                     while (((Tg - dmin_el) >> sh) >= 256) ++sh;
                     for (int e = t; e < ncand; e += kThreads) {
@@ -865,7 +874,8 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
                     if (lane == 0) sdirty_loc[ww] = sel_loc[ww] & ~mf;
                 }
                 // the window doubles when it held fewer than K although more was eligible, halves above 4K
-                if (wC < P.sap_k && wC < wE) step *= 2;
+                if (repair) repair = false;
+                else if (wC < P.sap_k && wC < wE) step *= 2;
                 else if (wC > 4 * P.sap_k && step > 1) step /= 2;
                 Tg = T + step;
                 const int myn = nfront > b ? (nfront - b - 1) / G + 1 : 0;
@@ -988,24 +998,31 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
             if (D >= kInf / 2) { status = CYB_ERR_NOT_CONVERGED; break; }
             if (b == 0 && t == 0) st_tm[4] = global_ns();
             // S3a: price update -- lambda[o] += D - d[o] below D; shared memory goes back to prices
-            for (int o = t; o < no; o += kThreads) {
+            for (int o0 = 0; o0 < no; o0 += kThreads) {
+                const int o = o0 + t;
                 const bool mine = (o % G == b);
-                if (!SMEMP && !mine) continue;
-                const unsigned long long key = __ldcg(P.dkey + o);
-                const long long d = key == ~0ull ? kInf : (long long)(key >> kPB);
-                long long lam;
-                if (SMEMP) { const long long g = sarr[o]; lam = g >= kGInf / 2 ? kInf : g + d; }
-                else lam = __ldcg(P.lambda + o);
-                if (d < D) {
-                    lam += D - d;
-                    if (mine) {
-                        if (lam >= kBidLimit) atomicExch(P.gmm + 2, CYB_ERR_OVERFLOW);
-                        P.lambda[o] = lam;
-                        const int s0 = capd ? __ldg(P.soff + o) : o, s1 = capd ? __ldg(P.soff + o + 1) : o + 1;
-                        for (int s = s0; s < s1; ++s) if (__ldcg(P.slot_price + s) < lam) P.slot_price[s] = lam;
+                unsigned long long key = ~0ull;
+                if (o < no && (SMEMP || mine)) {
+                    key = __ldcg(P.dkey + o);
+                    const long long d = key == ~0ull ? kInf : (long long)(key >> kPB);
+                    long long lam;
+                    if (SMEMP) { const long long g = sarr[o]; lam = g >= kGInf / 2 ? kInf : g + d; }
+                    else lam = __ldcg(P.lambda + o);
+                    if (d < D) {
+                        lam += D - d;
+                        if (mine) {
+                            if (lam >= kBidLimit) atomicExch(P.gmm + 2, CYB_ERR_OVERFLOW);
+                            P.lambda[o] = lam;
+                            const int s0 = capd ? __ldg(P.soff + o) : o, s1 = capd ? __ldg(P.soff + o + 1) : o + 1;
+                            for (int s = s0; s < s1; ++s) if (__ldcg(P.slot_price + s) < lam) P.slot_price[s] = lam;
+                        }
                     }
+                    if (SMEMP) sarr[o] = lam;
                 }
-                if (SMEMP) sarr[o] = lam;
+                if (SMEMO) {                                           // (SMEMO implies SMEMP: every thread read its key)
+                    const unsigned mr = __ballot_sync(0xffffffffu, key != ~0ull);
+                    if (lane == 0 && (o >> 5) < (no + 31) / 32) sreach[o >> 5] = mr;
+                }
             }
             // S3b: CTA 0 traces the candidate paths (one lane of warp 0 each) and publishes the accepted moves
             if (b == 0) {
@@ -1089,10 +1106,66 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
                 int tot;
                 const int pos = block_excl_count(still, wcnt, tot);
                 if (still) ssrc[pos] = me;
+                if (t < F) ssmap[t] = still ? pos : -1;
                 paths += F - tot;
                 if (tot == F) { status = CYB_ERR_NOT_CONVERGED; }        // no path applied: cannot happen
+                const int Fold = F;
                 F = tot;
                 __syncthreads();
+                warm = false;
+                if (SMEMO && P.warm && F > 0 && !status) {
+                    // ---- the next search starts from the surviving part of this one's shortest-path forest: a node is
+                    // kept iff its root is still free and its chain avoids every object of an applied path.  Its label
+                    // shifts by D (tree arcs stay consistent under the price update above); the rest is forgotten.
+                    // Every CTA derives the same bitmasks from its replicas (predecessors, reached bits, moves).
+                    const int nwd = (no + 31) / 32;
+                    for (int w = t; w < nwd; w += kThreads) { skept[w] = 0u; sdrop[w] = 0u; }
+                    __syncthreads();
+                    for (int k = t; k < nm; k += kThreads) { const int o = __ldcg(P.moves + k).y; atomicOr(&sdrop[o >> 5], 1u << (o & 31)); }
+                    __syncthreads();
+                    for (int o0 = 0; o0 < no; o0 += kThreads) {
+                        const int o = o0 + t;
+                        bool kp = false, dp = false;
+                        if (o < no) {
+                            const bool reached = (sreach[o >> 5] >> (o & 31)) & 1u, onp = (sdrop[o >> 5] >> (o & 31)) & 1u;
+                            if (!reached || onp) dp = true;
+                            else { const int sl = spred[o]; if (sl >= np) { if (sl - np < Fold && ssmap[sl - np] >= 0) kp = true; else dp = true; } }
+                        }
+                        const unsigned mk = __ballot_sync(0xffffffffu, kp), md = __ballot_sync(0xffffffffu, dp);
+                        __syncwarp();
+                        if (lane == 0 && (o >> 5) < nwd) { skept[o >> 5] = mk; sdrop[o >> 5] |= md; }
+                    }
+                    for (int it = 0; it <= no; ++it) {
+                        __syncthreads();
+                        bool undecided = false;
+                        for (int o0 = 0; o0 < no; o0 += kThreads) {
+                            const int o = o0 + t;
+                            bool kp = false, dp = false;
+                            if (o < no && !(((skept[o >> 5] | sdrop[o >> 5]) >> (o & 31)) & 1u)) {
+                                const int po = obj_of_slot(spred[o]);
+                                kp = (skept[po >> 5] >> (po & 31)) & 1u;
+                                dp = (sdrop[po >> 5] >> (po & 31)) & 1u;
+                                undecided = undecided || !(kp || dp);
+                            }
+                            const unsigned mk = __ballot_sync(0xffffffffu, kp), md = __ballot_sync(0xffffffffu, dp);
+                            if (lane == 0 && (mk | md)) { atomicOr(&skept[o >> 5], mk); atomicOr(&sdrop[o >> 5], md); }
+                        }
+                        if (!__syncthreads_or(undecided)) break;
+                    }
+                    // the owners rewrite the labels (nobody reads them before the barrier of the next search)
+                    for (int o = b * kThreads + t; o < no; o += G * kThreads) {
+                        unsigned long long key = ~0ull;
+                        if ((skept[o >> 5] >> (o & 31)) & 1u) {
+                            const unsigned long long old = __ldcg(P.dkey + o);
+                            const long long d = (long long)(old >> kPB);
+                            int sl = (int)(old & kPM);
+                            if (sl >= np) sl = np + ssmap[sl - np];
+                            key = ((unsigned long long)(d > D ? d - D : 0) << kPB) | (unsigned)sl;
+                        }
+                        P.dkey[o] = key;
+                    }
+                    warm = true;
+                }
             }
             if (b == 0 && t == 0) st_acc[11] += global_ns() - st_tm[4];
             if (status) break;
@@ -1127,7 +1200,7 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
         P.stats[8] = G; P.stats[9] = SMEMP ? 1 : 0; P.stats[10] = 2 + (SMEMO ? 1 : 0); P.stats[11] = st_acc[1];
         P.stats[12] = (phases - 1) * (long long)np; P.stats[14] = searches; P.stats[15] = srounds;
         P.stats[16] = st_acc[3]; P.stats[17] = st_acc[4]; P.stats[18] = st_acc[5]; P.stats[19] = st_acc[6]; P.stats[20] = st_acc[7];
-        P.stats[21] = paths; P.stats[22] = st_acc[9]; P.stats[23] = st_acc[10]; P.stats[24] = st_acc[11];
+        P.stats[21] = paths; P.stats[27] = P.warm; P.stats[22] = st_acc[9]; P.stats[23] = st_acc[10]; P.stats[24] = st_acc[11];
         P.stats[25] = st_acc[2]; P.stats[26] = st_acc[8];
     }
 }
@@ -1247,6 +1320,11 @@ extern "C" int cyb_lap_solve_i32(const int32_t *cost_dev, int64_t ld, int64_t n_
     if (const char *e = getenv("CYB_LAP_SAP_T")) P.sap_t = std::max(1, std::min(kSapMax, atoi(e)));
     if (const char *e = getenv("CYB_LAP_SAP_K")) P.sap_k = std::max(1, atoi(e));
     if (const char *e = getenv("CYB_LAP_SAP_MULTI")) P.multi = std::max(1, std::min(kMultiMax, atoi(e)));
+    // Warm-started searches cut the search rounds by a quarter (cfg2: 1 984 -> 1 498) but the repair round relaxes every
+    // surviving row again and the kept / dropped propagation costs ~55 us per search: measured 4k x 4k 19.1 -> 17.4 ms,
+    // cfg2 47.4 -> 49.4 ms, 30k x 5k 100 -> 112 ms.  On by default only where the whole matrix is small (<= 128 MB).
+    P.warm = (np * no <= (1ll << 25)) ? 1 : 0;
+    if (const char *e = getenv("CYB_LAP_WARM")) P.warm = atoi(e) ? 1 : 0;
 
     // barrier counters [0..1], gmm = {cmin, cmax, status, -, -, abort flag}
     const int init[16] = {0, 0, 0, 0, INT_MAX, INT_MIN, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -1256,7 +1334,7 @@ extern "C" int cyb_lap_solve_i32(const int32_t *cost_dev, int64_t ld, int64_t n_
 
     P.wpc = (int)(((no + 31) / 32 + G - 1) / G);
     const size_t base_bytes = cyb::align_up((size_t)P.qcap * 8, 16) + cyb::align_up((size_t)P.qcap * 4, 16) +
-                              2 * cyb::align_up((size_t)((no + 31) / 32) * 4, 16) + (size_t)P.wpc * 32 * 8 +
+                              5 * cyb::align_up((size_t)((no + 31) / 32) * 4, 16) + (size_t)P.wpc * 32 * 8 +
                               2 * cyb::align_up((size_t)P.wpc * 4, 16);
     const size_t price_bytes = cyb::align_up((size_t)no * 8, 16);
     const size_t owner_bytes = (size_t)((np + 3) & ~3) * 4 + (size_t)((no + 3) & ~3) * 4 +

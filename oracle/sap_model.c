@@ -35,6 +35,9 @@
  * [4] search rounds (dependent grid rounds), [5] rows scanned in searches, [6] paths applied,
  * [7] free persons when the SAP finish took over */
 int64_t sap_phase_log[64][8];
+/* 1: a search that follows another one in the same phase starts from the surviving part of its shortest-path forest
+ * (labels shifted by D, trees of the persons that got assigned dropped) instead of from scratch */
+int sap_warm = 0;
 
 typedef struct { int64_t d; int32_t o; } lab_t;
 static int lab_cmp(const void *a, const void *b) {
@@ -86,6 +89,11 @@ int sap_model_i32(int P, int O, const int32_t *m, int64_t ld, const int32_t *cap
     int32_t *slot_obj = (int32_t *)malloc(sizeof(int32_t) * (size_t)P);
     char *indirty = (char *)malloc((size_t)O);
     char *touched = (char *)malloc((size_t)O);
+    char *onpath = (char *)malloc((size_t)O);
+    char *vstate = (char *)malloc((size_t)O);
+    int32_t *chain = (int32_t *)malloc(sizeof(int32_t) * (size_t)O);
+    int32_t *srcmap = (int32_t *)malloc(sizeof(int32_t) * (size_t)P);
+    int have_forest = 0;
     for (int o = 0; o < O; ++o) for (int t = soff[o]; t < soff[o + 1]; ++t) slot_obj[t] = o;
     for (int o = 0; o < O; ++o) { lambda[o] = (soff[o + 1] > soff[o]) ? 0 : SAP_INF; minslot[o] = soff[o]; bidr[o] = -1; }
     for (int t = 0; t < P; ++t) slot_owner[t] = -1;
@@ -142,6 +150,7 @@ int sap_model_i32(int P, int O, const int32_t *m, int64_t ld, const int32_t *cap
             for (int o = 0; o < O; ++o) if (soff[o + 1] > soff[o]) REFRESH(o);
         }
         const int ph = (int)st[0] - 1;
+        have_forest = 0;
         int64_t step = eps;                     /* frontier window of the searches, adapted round by round */
         int64_t ph0[8]; memcpy(ph0, st, sizeof(st));
         if (ph < 64) { memset(sap_phase_log[ph], 0, sizeof(sap_phase_log[ph])); sap_phase_log[ph][0] = nfree; }
@@ -151,8 +160,10 @@ int sap_model_i32(int P, int O, const int32_t *m, int64_t ld, const int32_t *cap
                 /* ================= SAP finish: one search, one price update, >= 1 augmentation ============ */
                 ++st[3];
                 int nfo = 0;
+                const int warm_now = sap_warm && have_forest;
                 for (int o = 0; o < O; ++o) {
-                    d[o] = SAP_INF; pred[o] = -1; nfreeslot[o] = 0; indirty[o] = 0;
+                    if (!warm_now) { d[o] = SAP_INF; pred[o] = -1; }
+                    nfreeslot[o] = 0; indirty[o] = 0;
                     for (int t = soff[o]; t < soff[o + 1]; ++t) if (slot_owner[t] < 0) ++nfreeslot[o];
                     if (nfreeslot[o] > 0) fo[nfo++] = o;
                 }
@@ -177,6 +188,7 @@ int sap_model_i32(int P, int O, const int32_t *m, int64_t ld, const int32_t *cap
                 int want = nfree < nfo ? nfree : nfo;
                 if (multi <= 0) want = 1; else if (want > multi) want = (int)multi;
                 int64_t D = SAP_INF, T = -1, Tg = step, Tnext = -1;         /* round 0 leaves labels 0: the first guess is one window */
+                int repair = warm_now;                                      /* first round of a warm search: every surviving tree node relaxes again */
                 for (;;) {
                     /* D = the want-th smallest label of an object with a free slot */
                     int nc = 0;
@@ -203,6 +215,7 @@ int sap_model_i32(int P, int O, const int32_t *m, int64_t ld, const int32_t *cap
                      * above 4K (state kept across the searches of a phase).  When the guess selects nothing (first
                      * round of a search, D moved below it) it restarts from the smallest eligible label. */
                     int64_t wC = 0, wE = 0, dmin_el = SAP_INF;
+                    if (repair) Tg = D - 1;
                     for (int attempt = 0; attempt < 2; ++attempt) {
                         dmin_el = SAP_INF; wC = 0; wE = 0;
                         if (Tg > D - 1) Tg = D - 1;                        /* every eligible label is below D */
@@ -225,7 +238,7 @@ int sap_model_i32(int P, int O, const int32_t *m, int64_t ld, const int32_t *cap
                             if (d[o] <= Tg) hist[(d[o] - base) >> sh] += soff[o + 1] - soff[o];
                         }
                         int64_t Tq = Tg;
-                        if (wC > K) {
+                        if (wC > K && !repair) {
                             int64_t cum = 0; int bsel = 255;
                             for (int bb = 0; bb < 256; ++bb) { cum += hist[bb]; if (cum >= K) { bsel = bb; break; } }
                             Tq = base + (((int64_t)bsel + 1) << sh) - 1;
@@ -233,7 +246,8 @@ int sap_model_i32(int P, int O, const int32_t *m, int64_t ld, const int32_t *cap
                         }
                         T = Tq;
                     }
-                    if (wC < K && wC < wE) step *= 2;                      /* the window was too small (not: too little left) */
+                    if (repair) repair = 0;
+                    else if (wC < K && wC < wE) step *= 2;                 /* the window was too small (not: too little left) */
                     else if (wC > 4 * K && step > 1) step /= 2;
                     Tnext = T + step;
                     ++st[4];
@@ -292,6 +306,7 @@ int sap_model_i32(int P, int O, const int32_t *m, int64_t ld, const int32_t *cap
                     } else touched[o] = 0;
                 }
                 int applied = 0;
+                memset(onpath, 0, (size_t)O);
                 for (int c = 0; c < nc; ++c) {
                     int o = cand[c].o, ok = 1;
                     for (;;) {
@@ -308,7 +323,7 @@ int sap_model_i32(int P, int O, const int32_t *m, int64_t ld, const int32_t *cap
                         const int s = pred[o];
                         const int p = s >= P ? freel[s - P] : slot_owner[s];
                         slot_owner[slot] = p; slot_price[slot] = lambda[o]; person_obj[p] = o; person_slot[p] = slot;
-                        touched[o] = 1;
+                        touched[o] = 1; onpath[o] = 1;
                         if (s >= P) break;
                         o = slot_obj[s]; slot = s;
                     }
@@ -319,11 +334,37 @@ int sap_model_i32(int P, int O, const int32_t *m, int64_t ld, const int32_t *cap
                 for (int o = 0; o < O; ++o) if (touched[o]) REFRESH(o);
                 {
                     int nn = 0;
-                    for (int k = 0; k < nfree; ++k) { const int i = freel[k]; if (person_obj[i] < 0) nextl[nn++] = i; }
+                    for (int k = 0; k < nfree; ++k) { const int i = freel[k]; srcmap[k] = -1; if (person_obj[i] < 0) { srcmap[k] = nn; nextl[nn++] = i; } }
                     int32_t *tmp = freel; freel = nextl; nextl = tmp; nfree = nn;
                 }
+                if (sap_warm && nfree > 0) {
+                    /* keep the part of the forest whose root is still free and whose chain avoids every object of an
+                     * applied path: labels shift by D (tree arcs stay consistent under the price update), the rest is
+                     * forgotten.  vstate: 0 unknown, 1 kept, 2 dropped. */
+                    for (int o = 0; o < O; ++o) vstate[o] = (d[o] >= SAP_INF / 2 || onpath[o]) ? 2 : 0;
+                    for (int o = 0; o < O; ++o) {
+                        if (vstate[o]) continue;
+                        int x = o, depth = 0, res;
+                        for (;;) {                                            /* walk up to the first decided node */
+                            chain[depth++] = x;
+                            const int sl = pred[x];
+                            if (sl >= P) { res = srcmap[sl - P] >= 0 ? 1 : 2; break; }
+                            x = slot_obj[sl];
+                            if (vstate[x]) { res = vstate[x]; break; }
+                        }
+                        for (int q = 0; q < depth; ++q) vstate[chain[q]] = (char)res;
+                    }
+                    for (int o = 0; o < O; ++o) {
+                        if (vstate[o] == 1) {
+                            d[o] = d[o] > D ? d[o] - D : 0;
+                            if (pred[o] >= P) pred[o] = P + srcmap[pred[o] - P];
+                        } else { d[o] = SAP_INF; pred[o] = -1; }
+                    }
+                    have_forest = 1;
+                } else have_forest = 0;
                 continue;
             }
+            have_forest = 0;
             ++st[1]; st[2] += nfree;
             for (int k = 0; k < nfree; ++k) {
                 const int i = freel[k];
@@ -361,6 +402,6 @@ done:;
     if (stats) memcpy(stats, st, sizeof(st));
     free(soff); free(slot_price); free(minslot); free(person_slot); free(freel); free(nextl);
     free(bidp); free(bidr); free(kobj); free(d); free(snap); free(pred); free(nfreeslot);
-    free(cand); free(fo); free(dirty); free(front); free(claim); free(claim_src); free(slot_obj); free(indirty); free(touched);
+    free(cand); free(fo); free(dirty); free(front); free(claim); free(claim_src); free(slot_obj); free(indirty); free(touched); free(onpath); free(vstate); free(chain); free(srcmap);
     return rc;
 }

@@ -102,9 +102,10 @@ def test_matches_cpu_model_of_the_device_algorithm(engine, knobs):
     # the default schedule on every memory variant, the other schedules on the default variant
     variants = MEMORY_VARIANTS if knobs is SAP_KNOBS[0] else MEMORY_VARIANTS[:1]
     for (mat, cp), (sp, so_) in [(c, v) for c in cases for v in variants]:
-        env = dict(_sap_env(knobs), CYB_LAP_SMEM_PRICES=sp, CYB_LAP_SMEM_OWNER=so_)
+        env = dict(_sap_env(knobs), CYB_LAP_SMEM_PRICES=sp, CYB_LAP_SMEM_OWNER=so_, CYB_LAP_WARM=1)
         res, po = _with_env(env, lambda: solve_and_check(engine, mat, cp))
-        po_model, so_model, tot_model, lam_model, st, _ = oracle.sap_model(mat, cp, **knobs)
+        # searches are warm-started from the previous one's forest where the predecessors live in shared memory
+        po_model, so_model, tot_model, lam_model, st, _ = oracle.sap_model(mat, cp, warm=int(sp and so_), **knobs)
         assert res.total == tot_model and np.array_equal(po, po_model)
         assert np.array_equal(res.slot_owner.cpu().numpy(), so_model)
         assert np.array_equal(res.price.cpu().numpy(), lam_model)
@@ -262,15 +263,18 @@ def test_memory_variants_on_small_problems(engine, lap_golden, smem_prices, smem
     rng = np.random.default_rng(12)
     cap = rng.integers(0, 5, 300).astype(np.int32)
     m = rng.integers(-200_000, 200_000, (int(cap.sum()), 300), dtype=np.int32)
-    ref, po_ref = solve_and_check(engine, m, cap)
-    res, po = _with_env(env, lambda: solve_and_check(engine, m, cap))
+    cold = {"CYB_LAP_WARM": 0}            # (warm-started searches exist only with shared-memory predecessors: compare like with like)
+    ref, po_ref = _with_env(cold, lambda: solve_and_check(engine, m, cap))
+    res, po = _with_env(dict(env, **cold), lambda: solve_and_check(engine, m, cap))
     assert res.total == ref.total and np.array_equal(po, po_ref)
+    assert solve_and_check(engine, m, cap)[0].total == ref.total
     row_map = np.repeat(np.arange(300, dtype=np.int32), cap)
     assert res.total == oracle.lapjv_i32(np.ascontiguousarray(m.T), row_map)[2][0]
     sq = syn.uniform_cost_i32(1500, seed=9, high=3000)                    # many near-ties
-    ref, po_ref = solve_and_check(engine, sq)
-    res, po = _with_env(env, lambda: solve_and_check(engine, sq))
+    ref, po_ref = _with_env(cold, lambda: solve_and_check(engine, sq))
+    res, po = _with_env(dict(env, **cold), lambda: solve_and_check(engine, sq))
     assert res.total == ref.total == oracle.lapjv_i32(sq)[2][0] and np.array_equal(po, po_ref)
+    assert solve_and_check(engine, sq)[0].total == ref.total
     tie = np.zeros((200, 200), np.int32)                                   # every column ties
     res, _ = _with_env(env, lambda: solve_and_check(engine, tie))
     assert res.total == 0

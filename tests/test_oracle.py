@@ -95,7 +95,8 @@ def test_sap_finish_model_equals_expanded_jv(n_obj, seed, high, knobs, theta):
     compact = rng.integers(-high, high, (n_obj, n), dtype=np.int32)           # spots x cells (reference orientation)
     row_map = np.repeat(np.arange(n_obj, dtype=np.int32), cap)
     want = oracle.lapjv_i32(compact, row_map)[2][0]
-    po, so, tot, lam, stats, _ = oracle.sap_model(np.ascontiguousarray(compact.T), cap, theta=theta, sap_t=sap_t, K=K, multi=multi)
+    po, so, tot, lam, stats, _ = oracle.sap_model(np.ascontiguousarray(compact.T), cap, theta=theta, sap_t=sap_t, K=K, multi=multi,
+                                                  warm=seed & 1)
     assert tot == want
     assert np.array_equal(np.bincount(po, minlength=n_obj), cap)
     soff = np.concatenate([[0], np.cumsum(cap)])
