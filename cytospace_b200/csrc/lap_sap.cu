@@ -83,6 +83,7 @@ constexpr int kSapMax = 256;                                   // free persons a
 constexpr int kMultiMax = 32;                                  // augmenting paths per search (one warp each)
 constexpr int kRowsMax = 32;                                   // rows a CTA relaxes per chunk
 constexpr int kMaxSearch = 1 << 24;
+constexpr int kMaxGrid = 160;                                  // CTAs (one per SM; B200: 148)
 
 struct SapParams {
     const int32_t *cost;
@@ -105,6 +106,7 @@ struct SapParams {
     unsigned *chgbits[3];            // [(O+31)/32] objects whose label a round lowered, rotating by round
     int32_t *claim;                  // [O + kSapMax] path claims (decreasing base per search)
     int4 *moves;                     // [P] (person, object, slot, -) of the accepted paths
+    int32_t *anc;                    // [G][O] per-CTA scratch of the kept / dropped pointer jumping (warm searches)
     int *nmoves;                     // [1]
     int32_t *srcdone;                // [kSapMax]
     unsigned long long *cand[3];     // [O] candidate lists (label << 18 | object), rotating by round
@@ -874,6 +876,7 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
                     if (lane == 0) sdirty_loc[ww] = sel_loc[ww] & ~mf;
                 }
                 // the window doubles when it held fewer than K although more was eligible, halves above 4K
+                const bool flood = repair;
                 if (repair) repair = false;
                 else if (wC < P.sap_k && wC < wE) step *= 2;
                 else if (wC > 4 * P.sap_k && step > 1) step /= 2;
@@ -947,8 +950,18 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
                             // strictly below the round-start label: whoever wins the minimum, the label IS lowered in this
                             // round, so the bit can be set without waiting for the atomic's return value (both are
                             // fire-and-forget reductions: no round trip on the relax path)
-                            atomicMin(P.dkey + k, ((unsigned long long)nd << kPB) | slot);
-                            atomicOr(NB + (k >> 5), 1u << (k & 31));
+                            // (in the repair round of a warm search thousands of rows lower the same objects: a racy look at the
+                            // current label first -- most of them lose to the running minimum, and a read is far cheaper than an
+                            // atomic serialised at one L2 slice; same minimum.  Elsewhere hits are rare and the extra read only stalls.)
+                            const unsigned long long key = ((unsigned long long)nd << kPB) | slot;
+                            const unsigned bit = 1u << (k & 31);
+                            if (flood) {
+                                if (key < __ldcg(P.dkey + k)) atomicMin(P.dkey + k, key);
+                                if (!(__ldcg(NB + (k >> 5)) & bit)) atomicOr(NB + (k >> 5), bit);
+                            } else {
+                                atomicMin(P.dkey + k, key);
+                                atomicOr(NB + (k >> 5), bit);
+                            }
                         }
                     };
                     auto relax4 = [&](int row, int q, const int4 &c) {
@@ -1119,6 +1132,7 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
                     // shifts by D (tree arcs stay consistent under the price update above); the rest is forgotten.
                     // Every CTA derives the same bitmasks from its replicas (predecessors, reached bits, moves).
                     const int nwd = (no + 31) / 32;
+                    int *anc = P.anc + (size_t)b * no;
                     for (int w = t; w < nwd; w += kThreads) { skept[w] = 0u; sdrop[w] = 0u; }
                     __syncthreads();
                     for (int k = t; k < nm; k += kThreads) { const int o = __ldcg(P.moves + k).y; atomicOr(&sdrop[o >> 5], 1u << (o & 31)); }
@@ -1131,21 +1145,25 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
                             if (!reached || onp) dp = true;
                             else { const int sl = spred[o]; if (sl >= np) { if (sl - np < Fold && ssmap[sl - np] >= 0) kp = true; else dp = true; } }
                         }
+                        // an undecided node starts with its tree parent as ancestor (this CTA's scratch row in L2)
+                        if (o < no && !kp && !dp) __stcg(anc + o, obj_of_slot(spred[o]));
                         const unsigned mk = __ballot_sync(0xffffffffu, kp), md = __ballot_sync(0xffffffffu, dp);
                         __syncwarp();
                         if (lane == 0 && (o >> 5) < nwd) { skept[o >> 5] = mk; sdrop[o >> 5] |= md; }
                     }
-                    for (int it = 0; it <= no; ++it) {
+                    // pointer jumping: an undecided node takes the state of its ancestor, or jumps to the ancestor's ancestor
+                    // (chains are tens of nodes deep: a handful of iterations instead of one per level)
+                    for (int it = 0; it <= 40; ++it) {
                         __syncthreads();
                         bool undecided = false;
                         for (int o0 = 0; o0 < no; o0 += kThreads) {
                             const int o = o0 + t;
                             bool kp = false, dp = false;
                             if (o < no && !(((skept[o >> 5] | sdrop[o >> 5]) >> (o & 31)) & 1u)) {
-                                const int po = obj_of_slot(spred[o]);
-                                kp = (skept[po >> 5] >> (po & 31)) & 1u;
-                                dp = (sdrop[po >> 5] >> (po & 31)) & 1u;
-                                undecided = undecided || !(kp || dp);
+                                const int a = __ldcg(anc + o);
+                                kp = (skept[a >> 5] >> (a & 31)) & 1u;
+                                dp = (sdrop[a >> 5] >> (a & 31)) & 1u;
+                                if (!(kp || dp)) { __stcg(anc + o, __ldcg(anc + a)); undecided = true; }
                             }
                             const unsigned mk = __ballot_sync(0xffffffffu, kp), md = __ballot_sync(0xffffffffu, dp);
                             if (lane == 0 && (mk | md)) { atomicOr(&skept[o >> 5], mk); atomicOr(&sdrop[o >> 5], md); }
@@ -1206,7 +1224,7 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
 }
 
 struct SapLayout {
-    size_t list[3], rec[3], bidw[3], flag, slot_price, person_slot, minslot, slot_obj, dkey, gsnap, chgbits[3], cand[3], claim, moves, small, total;
+    size_t list[3], rec[3], bidw[3], flag, slot_price, person_slot, minslot, slot_obj, dkey, gsnap, chgbits[3], cand[3], claim, moves, anc, small, total;
 };
 
 SapLayout sap_layout(int64_t np, int64_t no) {
@@ -1227,6 +1245,7 @@ SapLayout sap_layout(int64_t np, int64_t no) {
     for (int k = 0; k < 3; ++k) L.cand[k] = take((size_t)no * 8);
     L.claim = take((size_t)(no + kSapMax) * 4);
     L.moves = take((size_t)np * 16);
+    L.anc = take((size_t)kMaxGrid * no * 4);
     L.small = take(2048);
     L.total = o;
     return L;
@@ -1273,6 +1292,7 @@ extern "C" int cyb_lap_solve_i32(const int32_t *cost_dev, int64_t ld, int64_t n_
 
     int G = grid_hint > 0 ? grid_hint : sms;
     if (G > sms) G = sms;
+    if (G > kMaxGrid) G = kMaxGrid;
     if (G > np) G = (int)np;
     if (G < 1) G = 1;
 
@@ -1299,6 +1319,7 @@ extern "C" int cyb_lap_solve_i32(const int32_t *cost_dev, int64_t ld, int64_t n_
     P.gsnap = reinterpret_cast<long long *>(ws + L.gsnap);
     P.claim = reinterpret_cast<int32_t *>(ws + L.claim);
     P.moves = reinterpret_cast<int4 *>(ws + L.moves);
+    P.anc = reinterpret_cast<int32_t *>(ws + L.anc);
     P.bar = reinterpret_cast<unsigned int *>(ws + L.small);
     P.gmm = reinterpret_cast<int *>(ws + L.small + 16);
     P.nmoves = reinterpret_cast<int *>(ws + L.small + 96);
@@ -1320,10 +1341,10 @@ extern "C" int cyb_lap_solve_i32(const int32_t *cost_dev, int64_t ld, int64_t n_
     if (const char *e = getenv("CYB_LAP_SAP_T")) P.sap_t = std::max(1, std::min(kSapMax, atoi(e)));
     if (const char *e = getenv("CYB_LAP_SAP_K")) P.sap_k = std::max(1, atoi(e));
     if (const char *e = getenv("CYB_LAP_SAP_MULTI")) P.multi = std::max(1, std::min(kMultiMax, atoi(e)));
-    // Warm-started searches cut the search rounds by a quarter (cfg2: 1 984 -> 1 498) but the repair round relaxes every
-    // surviving row again and the kept / dropped propagation costs ~55 us per search: measured 4k x 4k 19.1 -> 17.4 ms,
-    // cfg2 47.4 -> 49.4 ms, 30k x 5k 100 -> 112 ms.  On by default only where the whole matrix is small (<= 128 MB).
-    P.warm = (np * no <= (1ll << 25)) ? 1 : 0;
+    // Warm-started searches (kept forest + repair round, only where the predecessors live in shared memory) cut the search
+    // rounds by a quarter (cfg2: 1 984 -> 1 498).  Measured with the pointer-jumping kept / dropped pass: 4k x 4k
+    // 19.3 -> 16.8 ms, cfg2 48.4 -> 45.9 ms, 30k x 5k 103 -> 102 ms.
+    P.warm = 1;
     if (const char *e = getenv("CYB_LAP_WARM")) P.warm = atoi(e) ? 1 : 0;
 
     // barrier counters [0..1], gmm = {cmin, cmax, status, -, -, abort flag}
@@ -1346,6 +1367,7 @@ extern "C" int cyb_lap_solve_i32(const int32_t *cost_dev, int64_t ld, int64_t n_
     bool smemo = smemp && dyn + owner_bytes + static_smem <= (size_t)max_smem;
     if (const char *e = getenv("CYB_LAP_SMEM_OWNER")) smemo = smemo && atoi(e);
     if (smemo) dyn += owner_bytes;
+    if (!smemo) P.warm = 0;
 
     const void *fn = smemp ? (smemo ? (const void *)lap_sap_kernel<true, true> : (const void *)lap_sap_kernel<true, false>)
                            : (const void *)lap_sap_kernel<false, false>;
