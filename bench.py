@@ -343,8 +343,8 @@ def run_b200(args, wl):
         dist.init_process_group("nccl", device_id=dev)
     eng = AssignmentEngine(device=dev, precision=args.precision)
     las._engine = eng                      # the engine behind the plugin entry points of this process
-    if world > 1:                          # the host cores are shared by the ranks' staging threads
-        eng._stage_threads = max(1, (os.cpu_count() or 1) // world)
+    if world > 1:                          # the host cores are shared by the ranks' staging threads (read at first use)
+        os.environ.setdefault("CYB_STAGE_THREADS", str(max(1, min(16, (os.cpu_count() or 1) // world))))
     eng.profile = True
     n_cells, n_spots, n_genes, cps = wl["n_cells"], wl["n_spots"], wl["n_genes"], wl["cps"]
     n_chunks = wl.get("chunks", 0)          # --workload cfg5: sub-LAPs dealt round-robin, inputs resident per rank

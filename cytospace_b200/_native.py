@@ -19,7 +19,7 @@ _ROOT = os.path.dirname(_PKG)
 HEADER = os.path.join(_ROOT, "include", "cytospace_b200.h")
 LIB_PATH = os.path.join(_PKG, "libcytospace_b200.so")
 CSRC = os.path.join(_PKG, "csrc")
-SOURCES = ("common.cu", "cost_build.cu", "metrics.cu", "lap_sap.cu", "lap_check.cu", "dist.cu")
+SOURCES = ("common.cu", "cost_build.cu", "metrics.cu", "lap_sap.cu", "lap_check.cu", "dist.cu", "stage.cu")
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared", "-ldl"]

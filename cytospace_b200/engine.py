@@ -14,7 +14,6 @@ Reference path replaced (paths relative to the CytoSPACE repo):
 from __future__ import annotations
 
 import os
-from concurrent.futures import ThreadPoolExecutor
 from dataclasses import dataclass
 
 import numpy as np
@@ -97,7 +96,6 @@ class AssignmentEngine:
         self.precision = precision
         self.cost_scale = float(cost_scale)
         self._ws = {}
-        self._stage = None
         #: kernels of this library launched so far (every C-ABI call launches a fixed number: see KERNELS_PER_CALL)
         self.launches = 0
         self.profile = False          # True: bracket the cost-build and LAP launches with CUDA events
@@ -135,8 +133,6 @@ class AssignmentEngine:
 
     #: host arrays at least this large go through the pinned staging ring
     STAGE_MIN_BYTES = 32 << 20
-    STAGE_SLAB_BYTES = 64 << 20
-    STAGE_SLABS = 3
 
     @_on_engine_device
     def to_device(self, x, dtype=None) -> torch.Tensor:
@@ -145,9 +141,9 @@ class AssignmentEngine:
         Expression matrices reach ``solve_linear_assignment_problem`` as pageable numpy arrays
         (cytospace.py:398-409).  Anything that is not float32 / float64 (``read_csv`` count matrices are
         int64) is cast to float64 on the host as the reference's ``normalize_data`` does
-        (common.py:143: ``np.nan_to_num(data).astype(float)``).  Large arrays are uploaded through a ring of
-        pinned slabs: worker threads copy pageable -> pinned while the previous slab's DMA is in flight
-        (a plain ``cudaMemcpy`` from pageable memory runs at a fraction of the PCIe rate)."""
+        (common.py:143: ``np.nan_to_num(data).astype(float)``).  Large arrays are uploaded through the native library's ring
+        of pinned pieces (``cyb_stage_upload``; a plain ``cudaMemcpy`` from pageable memory runs at a fraction of the
+        PCIe rate)."""
         if torch.is_tensor(x):
             if x.is_cuda:
                 return x if dtype is None or x.dtype == dtype else x.to(dtype)
@@ -167,43 +163,11 @@ class AssignmentEngine:
         return self._staged_upload(x)
 
     def _staged_upload(self, x: np.ndarray) -> torch.Tensor:
+        """``cyb_stage_upload``: worker threads of the native library copy pageable -> pinned pieces with
+        non-temporal stores and enqueue one DMA per piece; returns when the last piece is enqueued."""
         out = torch.empty(x.shape, dtype=torch.from_numpy(x[:0]).dtype, device=self.device)
-        src = x.reshape(-1).view(np.uint8)
-        dst = out.view(-1).view(torch.uint8)
-        st = self._stage
-        if st is None:
-            n_thr = getattr(self, "_stage_threads", None) or max(1, min(8, (os.cpu_count() or 2)))
-            st = self._stage = {
-                "slabs": [torch.empty(self.STAGE_SLAB_BYTES, dtype=torch.uint8).pin_memory() for _ in range(self.STAGE_SLABS)],
-                "events": [None] * self.STAGE_SLABS,
-                "stream": torch.cuda.Stream(device=self.device),
-                "pool": ThreadPoolExecutor(n_thr), "threads": n_thr}
-        slab, k, thr = self.STAGE_SLAB_BYTES, self.STAGE_SLABS, st["threads"]
-        main = torch.cuda.current_stream(self.device)
-
-        def fill(buf, lo, hi):
-            # pageable -> pinned, split over the worker threads (numpy releases the GIL for plain copies)
-            n = hi - lo
-            part = -(-n // thr)
-            futs = [st["pool"].submit(np.copyto, buf[a:min(a + part, n)], src[lo + a:lo + min(a + part, n)])
-                    for a in range(0, n, part)]
-            for f in futs:
-                f.result()
-
-        with torch.cuda.stream(st["stream"]):
-            st["stream"].wait_stream(main)
-            for i, lo in enumerate(range(0, src.size, slab)):
-                hi = min(lo + slab, src.size)
-                j = i % k
-                if st["events"][j] is not None:
-                    st["events"][j].synchronize()                 # the slab's previous DMA has drained
-                buf = st["slabs"][j].numpy()
-                fill(buf, lo, hi)
-                dst[lo:hi].copy_(st["slabs"][j][:hi - lo], non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(st["stream"])
-                st["events"][j] = ev
-        main.wait_stream(st["stream"])
+        _native.check(self.lib.cyb_stage_upload(_native.ffi().cast("const void *", x.ctypes.data),
+                                                _native.ptr("void *", out), x.nbytes, self._stream()))
         return out
 
     @_on_engine_device

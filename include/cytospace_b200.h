@@ -47,7 +47,7 @@
 extern "C" {
 #endif
 
-#define CYB_ABI_VERSION 6
+#define CYB_ABI_VERSION 7
 
 /* status codes */
 #define CYB_OK                 0
@@ -296,6 +296,16 @@ int cyb_gather_columns(const void *x_dev, int x_dtype, int64_t n_rows, int64_t l
  * chunk blocks: raw count matrices (cytospace.py:398: the input of normalize_data) are exact in float32, which halves
  * the NVLink bytes of cyb_dist_send without changing a single bit of the result (the kernels widen on load). */
 int cyb_narrow_f64_to_f32(const double *x_dev, int64_t n, float *out_dev, int32_t *inexact_dev, void *stream);
+
+/* ------------------------------------------------------------ host staging */
+
+/* dst_dev[0..bytes) = src_host[0..bytes) for PAGEABLE host memory -- the numpy arrays the reference passes to the
+ * solver (cytospace/cytospace.py:398-443; `.to_numpy()` of the input DataFrames) -- through a process-wide ring of
+ * pinned pieces filled by worker threads with non-temporal stores, one DMA per piece on an internal copy stream.
+ * Returns when every piece is enqueued (src_host may be reused); `stream` waits for the last DMA.  Ordered after the
+ * work already queued on `stream`.  Environment: CYB_STAGE_THREADS (default min(8, cores)), CYB_STAGE_PIECE_MB (8),
+ * CYB_STAGE_PIECES (3 x threads). */
+int cyb_stage_upload(const void *src_host, void *dst_dev, size_t bytes, void *stream);
 
 #ifdef __cplusplus
 }
