@@ -114,7 +114,7 @@ struct SapParams {
     int wpc;                         // label words (32 objects) a CTA classifies per round
     int qcap;
     long long max_rounds;
-    int sap_t, sap_k, multi;
+    int sap_t, sap_k, multi, partial;
     int warm;                        // 1: a search that follows another one in the phase starts from the surviving forest
     int theta, eps0_div;
     int packed_reduce, prefetch;
@@ -508,8 +508,11 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
         }
         __syncthreads();
 
+        // A phase with eps > 1 ends as soon as <= partial persons are free: they stay free into the next phase (its
+        // start re-derives the free list anyway), only the last phase has to place everybody.
+        const int partial = eps > 1 ? P.partial : 0;
         // ---- bidding rounds (more than sap_t persons free) -------------------
-        while (F > sap_t) {
+        while (F > sap_t && F > partial) {
             if (++rounds > P.max_rounds) { status = CYB_ERR_NOT_CONVERGED; break; }
             if (t == 0) { st_acc[0] += F; if (F > st_acc[1]) st_acc[1] = F; }
             const bool timed = (b == 0 && t == 0 && F <= G);
@@ -595,12 +598,12 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
         // ---- shortest-augmenting-path finish -------------------------------------
         long long step = eps;                    // frontier window of the searches, adapted round by round
         if (b == 0 && t == 0) st_tm[0] = global_ns();
-        if (F > 0) {
+        if (F > partial) {
             if (t < F) ssrc[t] = __ldcg(P.list[cur] + t);
             __syncthreads();
         }
         bool warm = false;                       // the forest of the previous search of this phase is available
-        while (F > 0) {
+        while (F > partial) {
             ++searches;
             if (searches >= kMaxSearch) { status = CYB_ERR_NOT_CONVERGED; break; }
             const int cbase = (kMaxSearch - searches) * kMultiMax;
@@ -1126,7 +1129,7 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
                 F = tot;
                 __syncthreads();
                 warm = false;
-                if (SMEMO && P.warm && F > 0 && !status) {
+                if (SMEMO && P.warm && F > partial && !status) {
                     // ---- the next search starts from the surviving part of this one's shortest-path forest: a node is
                     // kept iff its root is still free and its chain avoids every object of an applied path.  Its label
                     // shifts by D (tree arcs stay consistent under the price update above); the rest is forgotten.
@@ -1187,7 +1190,7 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
             }
             if (b == 0 && t == 0) st_acc[11] += global_ns() - st_tm[4];
             if (status) break;
-            if (F > 0 && !SMEMO) GRID_BARRIER();     // the next search reads slot owners from global memory
+            if (F > partial && !SMEMO) GRID_BARRIER();     // the next search reads slot owners from global memory
         }
         if (b == 0 && t == 0) st_acc[7] += global_ns() - st_tm[0];
         if (status) break;
@@ -1341,6 +1344,8 @@ extern "C" int cyb_lap_solve_i32(const int32_t *cost_dev, int64_t ld, int64_t n_
     if (const char *e = getenv("CYB_LAP_SAP_T")) P.sap_t = std::max(1, std::min(kSapMax, atoi(e)));
     if (const char *e = getenv("CYB_LAP_SAP_K")) P.sap_k = std::max(1, atoi(e));
     if (const char *e = getenv("CYB_LAP_SAP_MULTI")) P.multi = std::max(1, std::min(kMultiMax, atoi(e)));
+    P.partial = 0;
+    if (const char *e = getenv("CYB_LAP_PARTIAL")) P.partial = std::max(0, atoi(e));
     // Warm-started searches (kept forest + repair round, only where the predecessors live in shared memory) cut the search
     // rounds by a quarter (cfg2: 1 984 -> 1 498).  Measured with the pointer-jumping kept / dropped pass: 4k x 4k
     // 19.3 -> 16.8 ms, cfg2 48.4 -> 45.9 ms, 30k x 5k 103 -> 102 ms.

@@ -38,6 +38,7 @@ int64_t sap_phase_log[64][8];
 /* 1: a search that follows another one in the same phase starts from the surviving part of its shortest-path forest
  * (labels shifted by D, trees of the persons that got assigned dropped) instead of from scratch */
 int sap_warm = 0;
+int sap_partial = 0;      /* > 0: a phase with eps > 1 ends as soon as <= sap_partial persons are free (they stay free into the next phase) */
 
 typedef struct { int64_t d; int32_t o; } lab_t;
 static int lab_cmp(const void *a, const void *b) {
@@ -155,6 +156,7 @@ int sap_model_i32(int P, int O, const int32_t *m, int64_t ld, const int32_t *cap
         int64_t ph0[8]; memcpy(ph0, st, sizeof(st));
         if (ph < 64) { memset(sap_phase_log[ph], 0, sizeof(sap_phase_log[ph])); sap_phase_log[ph][0] = nfree; }
         while (nfree > 0) {
+            if (eps > 1 && nfree <= sap_partial) break;
             if (nfree <= sap_t) {
                 if (ph < 64 && sap_phase_log[ph][7] == 0) sap_phase_log[ph][7] = nfree;
                 /* ================= SAP finish: one search, one price update, >= 1 augmentation ============ */

@@ -78,18 +78,21 @@ def _with_env(env, fn):
                 os.environ[k] = v
 
 
-SAP_KNOBS = [dict(theta=64, sap_t=64, K=296, multi=16),       # the defaults
-             dict(theta=64, sap_t=148, K=296, multi=32),
-             dict(theta=4, sap_t=8, K=16, multi=1),            # one path per search, tiny rounds (threshold histogram in use)
-             dict(theta=256, sap_t=40, K=64, multi=8),
-             dict(theta=16, sap_t=256, K=100000, multi=32)]    # every dirty object each round (Bellman-Ford rounds)
+SAP_KNOBS = [dict(theta=64, sap_t=64, K=296, multi=16, partial=0),       # the defaults
+             dict(theta=64, sap_t=148, K=296, multi=32, partial=0),
+             dict(theta=4, sap_t=8, K=16, multi=1, partial=0),            # one path per search, tiny rounds (threshold histogram in use)
+             dict(theta=256, sap_t=40, K=64, multi=8, partial=0),
+             dict(theta=16, sap_t=256, K=100000, multi=32, partial=0),    # every dirty object each round (Bellman-Ford rounds)
+             dict(theta=4, sap_t=64, K=296, multi=16, partial=64),        # incomplete phases: searches only at eps = 1
+             dict(theta=8, sap_t=32, K=296, multi=16, partial=12)]        # ... and phases that stop in the middle of their searches
 
 
 def _sap_env(k):
-    return {"CYB_LAP_THETA": k["theta"], "CYB_LAP_SAP_T": k["sap_t"], "CYB_LAP_SAP_K": k["K"], "CYB_LAP_SAP_MULTI": k["multi"]}
+    return {"CYB_LAP_THETA": k["theta"], "CYB_LAP_SAP_T": k["sap_t"], "CYB_LAP_SAP_K": k["K"], "CYB_LAP_SAP_MULTI": k["multi"],
+            "CYB_LAP_PARTIAL": k["partial"]}
 
 
-@pytest.mark.parametrize("knobs", SAP_KNOBS, ids=lambda k: "t{sap_t}_k{K}_m{multi}_th{theta}".format(**k))
+@pytest.mark.parametrize("knobs", SAP_KNOBS, ids=lambda k: "t{sap_t}_k{K}_m{multi}_th{theta}_p{partial}".format(**k))
 def test_matches_cpu_model_of_the_device_algorithm(engine, knobs):
     """Same rules as oracle/sap_model.c (auction rounds + shortest-augmenting-path finish: frontier threshold,
     strict relaxations, (label, slot) tie-breaks, path claims): identical assignment, identical counters --
@@ -113,7 +116,7 @@ def test_matches_cpu_model_of_the_device_algorithm(engine, knobs):
             (st[3], st[4], st[5], st[6]), "searches / search rounds / rows relaxed / paths differ from the model"
 
 
-@pytest.mark.parametrize("knobs", SAP_KNOBS[1:], ids=lambda k: "t{sap_t}_k{K}_m{multi}_th{theta}".format(**k))
+@pytest.mark.parametrize("knobs", SAP_KNOBS[1:], ids=lambda k: "t{sap_t}_k{K}_m{multi}_th{theta}_p{partial}".format(**k))
 def test_search_knobs_reach_the_same_optimum(engine, knobs):
     sc, st, cn = syn.structured_counts(1200, 200, 800, 6, seed=1004)
     from oracle import cost_oracle as co
