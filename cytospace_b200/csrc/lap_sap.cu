@@ -1334,7 +1334,7 @@ extern "C" int cyb_lap_solve_i32(const int32_t *cost_dev, int64_t ld, int64_t n_
     if (const char *e = getenv("CYB_LAP_PREFETCH")) P.prefetch = atoi(e) ? 1 : 0;
     P.packed_reduce = 1;
     if (const char *e = getenv("CYB_LAP_PACKED")) P.packed_reduce = atoi(e) ? 1 : 0;
-    P.theta = 64; P.eps0_div = 4;
+    P.theta = 8; P.eps0_div = 4;
     if (const char *e = getenv("CYB_LAP_THETA")) P.theta = std::max(2, atoi(e));
     if (const char *e = getenv("CYB_LAP_EPS0")) P.eps0_div = std::max(1, atoi(e));
     // (constants, not functions of the grid: the assignment must not depend on the grid size)
@@ -1344,7 +1344,11 @@ extern "C" int cyb_lap_solve_i32(const int32_t *cost_dev, int64_t ld, int64_t n_
     if (const char *e = getenv("CYB_LAP_SAP_T")) P.sap_t = std::max(1, std::min(kSapMax, atoi(e)));
     if (const char *e = getenv("CYB_LAP_SAP_K")) P.sap_k = std::max(1, atoi(e));
     if (const char *e = getenv("CYB_LAP_SAP_MULTI")) P.multi = std::max(1, std::min(kMultiMax, atoi(e)));
-    P.partial = 0;
+    // Incomplete phases (oracle/sap_model.c `sap_partial`): a phase with eps > 1 stops when <= 64 persons are
+    // free instead of placing them with searches whose result the next phase start throws away again; with that, a gentler
+    // eps schedule (theta 8 instead of 64) pays.  Measured: cfg2 45.9 -> 23.5 ms, 30k x 5k 100 -> 54, 25k 172 -> 102,
+    // 50k 498 -> 283 (search rounds at cfg2: 1 498 -> 721, searches 46 -> 8).
+    P.partial = 64;
     if (const char *e = getenv("CYB_LAP_PARTIAL")) P.partial = std::max(0, atoi(e));
     // Warm-started searches (kept forest + repair round, only where the predecessors live in shared memory) cut the search
     // rounds by a quarter (cfg2: 1 984 -> 1 498).  Measured with the pointer-jumping kept / dropped pass: 4k x 4k

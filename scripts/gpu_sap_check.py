@@ -25,7 +25,7 @@ def run(m, cap=None, label="", model=True, jv=True):
         tot = oracle.lapjv_i32(np.ascontiguousarray(m.T) if cap is not None else m, rm)[2][0]
         msg += f" jv_ok={tot == res.total}"
     if model:
-        pm, sm, tm, _, st, _ = oracle.sap_model(m, cap, theta=64, sap_t=64, K=296, multi=16, warm=0 if (os.environ.get('CYB_LAP_SMEM_OWNER') == '0' or os.environ.get('CYB_LAP_SMEM_PRICES') == '0' or m.shape[0] * m.shape[1] > 2 ** 25) else 1)      # the device defaults
+        pm, sm, tm, _, st, _ = oracle.sap_model(m, cap, theta=8, sap_t=64, K=296, multi=16, partial=64, warm=0 if (os.environ.get('CYB_LAP_SMEM_OWNER') == '0' or os.environ.get('CYB_LAP_SMEM_PRICES') == '0') else 1)      # the device defaults
         msg += f" model_total_ok={tm == res.total} model_assign_ok={np.array_equal(pm, po)} model(srounds={st[4]},srows={st[5]},searches={st[3]},paths={st[6]})"
     s = res.stats
     msg += f" dev(phases={s['phases']},rounds={s['rounds']},bids={s['bids']},searches={s['tails']},srounds={s['list_hits']},srows={s['tail_bids']},paths={s['paths']})"

@@ -78,12 +78,13 @@ def _with_env(env, fn):
                 os.environ[k] = v
 
 
-SAP_KNOBS = [dict(theta=64, sap_t=64, K=296, multi=16, partial=0),       # the defaults
+SAP_KNOBS = [dict(theta=8, sap_t=64, K=296, multi=16, partial=64),       # the defaults (lap_sap.cu): incomplete phases, searches only at eps = 1
+             dict(theta=64, sap_t=64, K=296, multi=16, partial=0),       # every phase finished by searches (the schedule before incomplete phases)
              dict(theta=64, sap_t=148, K=296, multi=32, partial=0),
              dict(theta=4, sap_t=8, K=16, multi=1, partial=0),            # one path per search, tiny rounds (threshold histogram in use)
              dict(theta=256, sap_t=40, K=64, multi=8, partial=0),
              dict(theta=16, sap_t=256, K=100000, multi=32, partial=0),    # every dirty object each round (Bellman-Ford rounds)
-             dict(theta=4, sap_t=64, K=296, multi=16, partial=64),        # incomplete phases: searches only at eps = 1
+             dict(theta=4, sap_t=16, K=296, multi=16, partial=16),        # incomplete phases with a smaller hand-over
              dict(theta=8, sap_t=32, K=296, multi=16, partial=12)]        # ... and phases that stop in the middle of their searches
 
 
@@ -102,8 +103,8 @@ def test_matches_cpu_model_of_the_device_algorithm(engine, knobs):
     m = rng.integers(-1000, 1000, (int(cap.sum()), 70), dtype=np.int32)
     cases = [(m, cap), (rng.integers(0, 50, (90, 90), dtype=np.int32), None),          # unit capacities, many ties
              (rng.integers(-100_000, 100_000, (700, 700), dtype=np.int32), None)]
-    # the default schedule on every memory variant, the other schedules on the default variant
-    variants = MEMORY_VARIANTS if knobs is SAP_KNOBS[0] else MEMORY_VARIANTS[:1]
+    # the default schedule and the complete-phases schedule on every memory variant, the others on the default variant
+    variants = MEMORY_VARIANTS if knobs in SAP_KNOBS[:2] else MEMORY_VARIANTS[:1]
     for (mat, cp), (sp, so_) in [(c, v) for c in cases for v in variants]:
         env = dict(_sap_env(knobs), CYB_LAP_SMEM_PRICES=sp, CYB_LAP_SMEM_OWNER=so_, CYB_LAP_WARM=1)
         res, po = _with_env(env, lambda: solve_and_check(engine, mat, cp))
