@@ -175,3 +175,32 @@ def test_staged_upload_equals_plain_copy(engine):
     assert torch.equal(d.cpu(), torch.from_numpy(x))
     xi = rng.integers(0, 50, (2000, 3000))                     # int64 -> float64 on the host
     assert torch.equal(engine.to_device(xi).cpu(), torch.from_numpy(xi.astype(np.float64)))
+
+
+@pytest.mark.gpu
+def test_stage_upload_ring_wraps_and_odd_sizes():
+    """cyb_stage_upload with a ring much smaller than the array (3 pieces of 1 MB, 4 workers): every slot is reused
+    many times, the last piece is ragged, sizes that are not a multiple of the 64-byte copy unit, back-to-back calls
+    on the same stream.  (The ring is sized once per process, hence the child process.)"""
+    import subprocess, sys, os
+    child = r"""
+import numpy as np, torch
+from cytospace_b200 import _native
+lib = _native.load(); ffi = _native.ffi()
+rng = np.random.default_rng(5)
+s = torch.cuda.current_stream().cuda_stream
+for nbytes in (1, 63, 64, 65, (1 << 20) - 1, (1 << 20) + 1, 37 * (1 << 20) + 5):
+    x = rng.integers(0, 256, nbytes + 3, dtype=np.uint8)[3:]                 # deliberately misaligned source
+    outs = [torch.zeros(nbytes, dtype=torch.uint8, device="cuda") for _ in range(2)]
+    for o in outs:                                                           # two calls in flight behind each other
+        _native.check(lib.cyb_stage_upload(ffi.cast("const void *", x.ctypes.data), ffi.cast("void *", o.data_ptr()), nbytes, ffi.cast("void *", s)))
+    torch.cuda.synchronize()
+    for o in outs:
+        assert np.array_equal(o.cpu().numpy(), x), nbytes
+assert lib.cyb_stage_upload(ffi.NULL, ffi.NULL, 8, ffi.cast("void *", s)) != 0
+print("ok")
+"""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, CYB_STAGE_THREADS="4", CYB_STAGE_PIECE_MB="1", CYB_STAGE_PIECES="3", PYTHONPATH=root)
+    r = subprocess.run([sys.executable, "-c", child], env=env, capture_output=True, text=True, timeout=300, cwd=root)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stderr[-2000:]

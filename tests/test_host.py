@@ -50,6 +50,9 @@ def test_native_argument_errors_without_gpu():
     rc = lib.cyb_cost_gemm_i32(ffi.cast("void *", 16), ffi.cast("void *", 16), 8, 8, 70, 1.0,
                                ffi.cast("int32_t *", 16), 8, ffi.NULL)
     assert rc == lib.CYB_ERR_INVALID           # k not a multiple of 64
+    assert lib.cyb_stage_upload(ffi.NULL, ffi.NULL, 0, ffi.NULL) == 0                        # nothing to copy
+    rc = lib.cyb_stage_upload(ffi.NULL, ffi.NULL, 64, ffi.NULL)
+    assert rc == lib.CYB_ERR_INVALID and b"null" in ffi.string(lib.cyb_last_error())
     with pytest.raises(_native.CybError):
         _native.check(rc)
 
