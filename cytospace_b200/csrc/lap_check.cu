@@ -88,9 +88,11 @@ constexpr int kBatch = 4;                        // 16-byte row loads in flight 
 __global__ void __launch_bounds__(kChkThreads, 2) lap_rowcheck_whole_kernel(
     const int32_t *__restrict__ cost, long long ld, int np, int no, const int32_t *__restrict__ person_obj,
     const long long *__restrict__ price, long long S, int32_t *__restrict__ count, long long *__restrict__ acc,
-    const int32_t *__restrict__ soff, long long *__restrict__ out, unsigned int *__restrict__ done) {
+    const int32_t *__restrict__ soff, long long *__restrict__ out, unsigned int *__restrict__ done,
+    unsigned int *__restrict__ rowctr) {
     extern __shared__ __align__(16) long long spw[];
     __shared__ long long part[2][kTeams][kTeam / 32];
+    __shared__ int s_next[2][kTeams];
     __shared__ long long r_viol[kTeams], r_tot[kTeams];
     __shared__ int r_bad[kTeams];
     for (int j = threadIdx.x; j < no; j += kChkThreads) spw[j] = price[j];
@@ -101,13 +103,19 @@ __global__ void __launch_bounds__(kChkThreads, 2) lap_rowcheck_whole_kernel(
     const int n4 = vec_ok ? (no >> 2) : 0;
     long long viol = 0, tot = 0;
     int bad = 0, it = 0;
-    const int i0 = blockIdx.x * kTeams + team, istep = gridDim.x * kTeams;
+    // Rows are handed out dynamically after the first one per team (10k rows over 2 368 teams is 4.2 rows each: a static
+    // deal leaves most teams idle during the fifth); the leader draws its ticket one row ahead.
+    const int i0 = blockIdx.x * kTeams + team, n_teams = gridDim.x * kTeams;
     // the row's certificate terms ride along with the stream: obj(i) is fetched one row ahead and
     // cost[i, obj(i)] with the row itself, so the team leader adds no dependent round trip per row
     int o_cur = (tt == 0 && i0 < np) ? __ldg(person_obj + i0) : -1;
-    for (int i = i0; i < np; i += istep, ++it) {
+    int i_next = np;
+    if (tt == 0 && i0 < np) i_next = (int)min((unsigned)np, atomicAdd(rowctr, 1u) + (unsigned)n_teams);
+    for (int i = i0; i < np; ++it) {
         const int32_t *r = cost + (long long)i * ld;
-        const int o_next = (tt == 0 && i + istep < np) ? __ldg(person_obj + i + istep) : -1;
+        const int o_next = (tt == 0 && i_next < np) ? __ldg(person_obj + i_next) : -1;
+        int i_next2 = np;
+        if (tt == 0 && i_next < np) i_next2 = (int)min((unsigned)np, atomicAdd(rowctr, 1u) + (unsigned)n_teams);
         const bool o_ok = o_cur >= 0 && o_cur < no;
         const int c_o = (tt == 0 && o_ok) ? __ldg(r + o_cur) : 0;
         long long m = LLONG_MAX;
@@ -136,6 +144,7 @@ __global__ void __launch_bounds__(kChkThreads, 2) lap_rowcheck_whole_kernel(
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, d));
         if (lane == 0) part[it & 1][team][wt] = m;
+        if (tt == 0) s_next[it & 1][team] = i_next;
         asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "r"(kTeam) : "memory");     // the team only
         if (tt == 0) {
 #pragma unroll
@@ -147,7 +156,9 @@ __global__ void __launch_bounds__(kChkThreads, 2) lap_rowcheck_whole_kernel(
                 viol = max(viol, (long long)c_o * S + spw[o_cur] - m);
             }
         }
+        i = s_next[it & 1][team];
         o_cur = o_next;
+        i_next = i_next2;
     }
     if (tt == 0) { r_viol[team] = viol; r_tot[team] = tot; r_bad[team] = bad; }
     __syncthreads();
@@ -275,7 +286,7 @@ extern "C" int cyb_lap_check_i32(const int32_t *cost_dev, int64_t ld, int64_t n_
         int grid = (int)std::min<long long>((long long)sms0 * per_sm, (np + kTeams - 1) / kTeams);
         lap_rowcheck_whole_kernel<<<grid, kChkThreads, smem, stream>>>(
             cost_dev, ld, (int)np, (int)no, person_obj_dev, reinterpret_cast<const long long *>(price_dev), np + 1, count, acc,
-            slot_offset_dev, reinterpret_cast<long long *>(out_dev), done);
+            slot_offset_dev, reinterpret_cast<long long *>(out_dev), done, done + 1);
         CYB_CUDA_CHECK(cudaGetLastError());
         return CYB_OK;
     }

@@ -375,6 +375,7 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
     __shared__ long long red_b1[32], red_b2[32];
     __shared__ int red_j[32], wcnt[32];
     __shared__ long long st_tm[8];
+    __shared__ long long st_ph[5];     // CTA 0: kernel start, phase-section start, ns in phase starts / auction rounds / before the first phase
     __shared__ long long st_acc[12];   // bids, max bidders, -, small rounds, ns bid / barrier / replay / sap, relax hits, sap ns select, sap ns trace
     __shared__ int ssrc[kSapMax], sfo[kSapMax], ssmap[kSapMax];
     __shared__ long long sfo_d[kSapMax];
@@ -401,6 +402,7 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
     auto owner_of = [&](int slot) -> int { return SMEMO ? sowner[slot] : __ldcg(P.slot_owner + slot); };
     auto obj_of_slot = [&](int slot) -> int { return capd ? __ldcg(P.slot_obj + slot) : slot; };
 
+    if (b == 0 && t == 0) { st_ph[0] = global_ns(); st_ph[2] = 0; st_ph[3] = 0; st_ph[4] = 0; }
     // ---- pass 0: state init and the cost range ------------------------------
     {
         int lmin = INT_MAX, lmax = INT_MIN;
@@ -455,6 +457,7 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
 
     while (!status) {
         ++phases;
+        if (b == 0 && t == 0) { st_ph[1] = global_ns(); if (phases == 1) st_ph[4] = st_ph[1] - st_ph[0]; }
         // ---- phase start: which pairs survive eps-CS at the new eps? --------
         if (phases > 1) {
             for (int i = b; i < np; i += G) {
@@ -508,6 +511,7 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
         }
         __syncthreads();
 
+        if (b == 0 && t == 0) { const long long n = global_ns(); st_ph[2] += n - st_ph[1]; st_ph[1] = n; }
         // A phase with eps > 1 ends as soon as <= partial persons are free: they stay free into the next phase (its
         // start re-derives the free list anyway), only the last phase has to place everybody.
         const int partial = eps > 1 ? P.partial : 0;
@@ -595,6 +599,7 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
             prevF = 0;
         }
 
+        if (b == 0 && t == 0) st_ph[3] += global_ns() - st_ph[1];
         // ---- shortest-augmenting-path finish -------------------------------------
         long long step = eps;                    // frontier window of the searches, adapted round by round
         if (b == 0 && t == 0) st_tm[0] = global_ns();
@@ -1223,6 +1228,7 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
         P.stats[16] = st_acc[3]; P.stats[17] = st_acc[4]; P.stats[18] = st_acc[5]; P.stats[19] = st_acc[6]; P.stats[20] = st_acc[7];
         P.stats[21] = paths; P.stats[27] = P.warm; P.stats[22] = st_acc[9]; P.stats[23] = st_acc[10]; P.stats[24] = st_acc[11];
         P.stats[25] = st_acc[2]; P.stats[26] = st_acc[8];
+        P.stats[28] = st_ph[2]; P.stats[29] = st_ph[3]; P.stats[30] = st_ph[4]; P.stats[31] = global_ns() - st_ph[0];
     }
 }
 

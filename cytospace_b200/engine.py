@@ -33,7 +33,8 @@ KERNELS_PER_CALL = {"cost_pearson": 7, "cost_log_tpm_extra": 2, "cost_spearman_e
 STAT_NAMES = ("status", "phases", "rounds", "bids", "passes", "cost_min", "cost_max", "scale",
               "grid", "smem_prices", "tail_mode", "max_bidders", "phase_scans", "tail_bids", "tails", "list_hits",
               "small_rounds", "ns_bid", "ns_barrier", "ns_resolve", "ns_tail", "paths", "ns_select", "ns_relax",
-              "ns_augment", "ns_sel_pass", "ns_sel_scan", "reserved")
+              "ns_augment", "ns_sel_pass", "ns_sel_scan", "warm",
+              "ns_phase_start", "ns_auction", "ns_init", "ns_total")
 #: with the default solver (auction rounds + shortest-augmenting-path finish, csrc/lap_sap.cu) the tail
 #: columns read: tail_bids = rows relaxed in searches, tails = searches, list_hits = search rounds
 

@@ -47,7 +47,7 @@
 extern "C" {
 #endif
 
-#define CYB_ABI_VERSION 7
+#define CYB_ABI_VERSION 8
 
 /* status codes */
 #define CYB_OK                 0
@@ -73,19 +73,23 @@ extern "C" {
                                operand error ~2^-22, fp32-accumulation bound         */
 
 /* number of int64 entries written to stats_dev by cyb_lap_solve_i32 */
-#define CYB_LAP_NSTATS 28
-/* stats_dev layout:
- *  [0] status (0 ok)        [1] eps-scaling phases      [2] bidding rounds
- *  [3] bids (= row scans in rounds)  [4] full-matrix row scans (phase starts)
- *  [5] cost minimum         [6] cost maximum            [7] scale S = n+1
- *  [8] grid size used       [9] 1 if the price vector was shared-memory resident
- *  [10] tail mode used (0 Gauss-Seidel FIFO, 1 in-CTA Jacobi rounds) [11] max bidders in a round
- *  [12] row scans at phase starts (rows whose pair was re-checked)
- *  [13] bids made in Gauss-Seidel tails (one CTA, no grid barrier)  [14] tails run
- *  [15] tail bids served from a candidate list (no row scan)
- *  [16] rounds with at most one bidder per CTA, and for those, as seen by CTA 0 (globaltimer ns):
+#define CYB_LAP_NSTATS 32
+/* stats_dev layout (csrc/lap_sap.cu; times are globaltimer ns as seen by CTA 0):
+ *  [0] status (0 ok)        [1] eps-scaling phases      [2] auction rounds
+ *  [3] bids (= row scans in auction rounds)  [4] phase starts with a re-check pass (phases - 1)
+ *  [5] cost minimum         [6] cost maximum            [7] scale S = persons + 1
+ *  [8] grid size used       [9] 1 if prices / search snapshot were shared-memory resident
+ *  [10] memory variant (2: holders / predecessors in global memory, 3: in shared memory)
+ *  [11] max bidders in a round  [12] rows re-checked at phase starts
+ *  [13] rows relaxed in searches  [14] searches  [15] search rounds
+ *  [16] auction rounds with at most one bidder per CTA, and for those:
  *  [17] time in the bid scan  [18] time in the grid barrier  [19] time in the record replay
- *  [20] ns spent in tails */
+ *  [20] time in searches    [21] augmenting paths applied
+ *  [22] search time: selection  [23] relaxation  [24] price update + augmentation + warm-start bookkeeping
+ *  [25] selection: classification pass  [26] selection: threshold / deal
+ *  [27] 1 if searches were warm-started
+ *  [28] time in phase starts (re-check pass + free list)  [29] time in all auction rounds
+ *  [30] time before the first phase (state init, cost range)  [31] total kernel time */
 
 int         cyb_abi_version(void);
 const char *cyb_last_error(void);

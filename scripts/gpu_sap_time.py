@@ -21,7 +21,7 @@ for name in names:
             spot, res, costm = eng.assign(scd, std, cn)
             ms.append(eng.last_ms("lap"))
         s = res.stats
-        keys = ("phases", "rounds", "bids", "tails", "list_hits", "tail_bids", "paths", "ns_tail", "ns_select", "ns_relax", "ns_augment", "ns_sel_pass", "ns_sel_scan", "ns_bid", "ns_barrier", "ns_resolve")
+        keys = ("phases", "rounds", "bids", "tails", "list_hits", "tail_bids", "paths", "ns_tail", "ns_select", "ns_relax", "ns_augment", "ns_sel_pass", "ns_sel_scan", "ns_bid", "ns_barrier", "ns_resolve", "small_rounds", "ns_phase_start", "ns_auction", "ns_init", "ns_total")
         print(name, env, "lap ms", [round(x, 2) for x in ms], "total", res.total, {k: s.get(k) for k in keys}, flush=True)
         for k in env: os.environ.pop(k, None)
     del scd, std
