@@ -136,10 +136,10 @@ __device__ __forceinline__ int4 ld_stream(const int4 *p, unsigned long long pol)
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(pol));
     return r;
 }
-__device__ __forceinline__ void prefetch_row_l2(const int32_t *r, int n) {
+__device__ __forceinline__ void prefetch_row_l2(const int32_t *r, int n, int tid = threadIdx.x) {
     const unsigned bytes = ((unsigned)n * 4u) & ~15u;
     const unsigned chunk = 8192u;
-    const unsigned off = threadIdx.x * chunk;
+    const unsigned off = (unsigned)tid * chunk;
     if (off < bytes && ((reinterpret_cast<uintptr_t>(r) & 15) == 0)) {
         const unsigned len = min(chunk, bytes - off);
         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const char *>(r) + off), "r"(len) : "memory");
@@ -230,22 +230,44 @@ __device__ __forceinline__ unsigned long long warp_min64(unsigned long long key)
     const unsigned mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xFFFFFFFFu);
     return ((unsigned long long)mhi << 32) | mlo;
 }
+// A row is scanned by a TEAM of ts threads (a power of two, 32 <= ts <= kThreads; consecutive warps): the whole CTA when it
+// has one row to scan, down to 128 threads when it has eight or more -- each row scan is a chain of load latency, reduction
+// and a leader epilogue, and only rows in flight side by side overlap those.  Teams synchronise on their own named barrier.
+struct Team {
+    int ts, tt, id;          // team size, thread index in the team, team index
+};
+__device__ __forceinline__ Team make_team(int n_teams) {
+    Team tm;
+    tm.ts = kThreads / n_teams;
+    tm.tt = (int)threadIdx.x & (tm.ts - 1);
+    tm.id = (int)threadIdx.x / tm.ts;
+    return tm;
+}
+// (Without shared-memory prices -- 50k columns -- a scan is bound by the price reads through L2, side-by-side rows only
+// thrash: measured 284 -> 298 ms; there a CTA keeps scanning one row at a time.)
+template <bool SMEMP>
+__device__ __forceinline__ int teams_for(int rows) { return !SMEMP ? 1 : rows >= 8 ? 8 : rows >= 4 ? 4 : rows >= 2 ? 2 : 1; }
+__device__ __forceinline__ void team_sync(const Team &tm) {
+    if (tm.ts == kThreads) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"r"(1 + tm.id), "r"(tm.ts) : "memory");
+}
 constexpr long long kPackMax = (1ll << 46) - 1;
 __device__ __forceinline__ unsigned long long pack_key(long long v, unsigned j) {
     return ((unsigned long long)min(v, kPackMax) << kPB) | j;
 }
 __device__ __forceinline__ Best packed_reduce(unsigned long long k1, unsigned long long k2, long long *red_b1,
-                                              long long *red_b2) {
+                                              long long *red_b2, const Team &tm) {
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const int w0 = (tm.id * tm.ts) >> 5, nw = tm.ts >> 5;        // the team's warps
     const unsigned long long w1 = warp_min64(k1);
     const unsigned long long w2 = warp_min64(k1 == w1 ? k2 : k1);
     unsigned long long *rk1 = reinterpret_cast<unsigned long long *>(red_b1);
     unsigned long long *rk2 = reinterpret_cast<unsigned long long *>(red_b2);
     if (lane == 0) { rk1[w] = w1; rk2[w] = w2; }
-    __syncthreads();
+    team_sync(tm);
     Best s{LLONG_MAX, LLONG_MAX, -1};
-    if (w == 0) {
-        const unsigned long long q1 = lane < kWarps ? rk1[lane] : ~0ull, q2 = lane < kWarps ? rk2[lane] : ~0ull;
+    if (w == w0) {
+        const unsigned long long q1 = lane < nw ? rk1[w0 + lane] : ~0ull, q2 = lane < nw ? rk2[w0 + lane] : ~0ull;
         const unsigned long long W1 = warp_min64(q1);
         const unsigned long long W2 = warp_min64(q1 == W1 ? q2 : q1);
         const long long v1 = (long long)(W1 >> kPB), v2 = (long long)(W2 >> kPB);
@@ -253,24 +275,24 @@ __device__ __forceinline__ Best packed_reduce(unsigned long long k1, unsigned lo
         s.b1 = (W1 == ~0ull) ? LLONG_MAX : (v1 == kPackMax ? kInf : v1);
         s.b2 = (W2 == ~0ull) ? LLONG_MAX : (v2 == kPackMax ? kInf : v2);
     }
-    __syncthreads();
+    team_sync(tm);
     return s;
 }
 
-// CTA-wide scan of one person's row: min / second-min / argmin of (c-cmin)*S + price[.]; valid in thread 0.
+// Team-wide scan of one person's row: min / second-min / argmin of (c-cmin)*S + price[.]; valid in the team's thread 0.
 template <bool SMEMP>
 __device__ __forceinline__ Best scan_row(const int32_t *__restrict__ r, int n, int cmin, int S,
                                          const long long *__restrict__ price, bool vec_ok,
-                                         long long *red_b1, long long *red_b2, int *red_j, bool packed) {
+                                         long long *red_b1, long long *red_b2, int *red_j, bool packed, const Team &tm) {
     Best s{LLONG_MAX, LLONG_MAX, -1};
-    const int t = threadIdx.x;
+    const int t = tm.tt, kStep = tm.ts;
     const unsigned long long pol = l2_policy_evict_first();
     int jtail = 0;
     if (vec_ok) {
         const int4 *r4 = reinterpret_cast<const int4 *>(r);
         const int n4 = n >> 2;
 #pragma unroll 8
-        for (int q = t; q < n4; q += kThreads) {
+        for (int q = t; q < n4; q += kStep) {
             const int4 c = ld_stream(r4 + q, pol);
             const int j = q << 2;
             long long p0, p1, p2, p3;
@@ -290,14 +312,14 @@ __device__ __forceinline__ Best scan_row(const int32_t *__restrict__ r, int n, i
         }
         jtail = n4 << 2;
     }
-    for (int j = jtail + t; j < n; j += kThreads) {
+    for (int j = jtail + t; j < n; j += kStep) {
         const long long p = SMEMP ? price[j] : __ldcg(price + j);
         upd(s, (long long)(__ldg(r + j) - cmin) * S + p, j);
     }
     if (packed) {
         const unsigned long long k1 = s.j1 >= 0 ? pack_key(s.b1, (unsigned)s.j1) : ~0ull;
         const unsigned long long k2 = s.b2 != LLONG_MAX ? pack_key(s.b2, (unsigned)kPM) : ~0ull;
-        return packed_reduce(k1, k2, red_b1, red_b2);
+        return packed_reduce(k1, k2, red_b1, red_b2, tm);
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
@@ -307,11 +329,12 @@ __device__ __forceinline__ Best scan_row(const int32_t *__restrict__ r, int n, i
         o.j1 = __shfl_xor_sync(0xffffffffu, s.j1, d);
         s = combine(s, o);
     }
-    const int lane = t & 31, w = t >> 5;
+    const int lane = (int)threadIdx.x & 31, w = (int)threadIdx.x >> 5;
+    const int w0 = (tm.id * tm.ts) >> 5, nw = tm.ts >> 5;
     if (lane == 0) { red_b1[w] = s.b1; red_b2[w] = s.b2; red_j[w] = s.j1; }
-    __syncthreads();
-    if (w == 0) {
-        if (lane < kWarps) { s.b1 = red_b1[lane]; s.b2 = red_b2[lane]; s.j1 = red_j[lane]; }
+    team_sync(tm);
+    if (w == w0) {
+        if (lane < nw) { s.b1 = red_b1[w0 + lane]; s.b2 = red_b2[w0 + lane]; s.j1 = red_j[w0 + lane]; }
         else { s.b1 = LLONG_MAX; s.b2 = LLONG_MAX; s.j1 = -1; }
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) {
@@ -322,7 +345,7 @@ __device__ __forceinline__ Best scan_row(const int32_t *__restrict__ r, int n, i
             s = combine(s, o);
         }
     }
-    __syncthreads();
+    team_sync(tm);
     return s;
 }
 
@@ -450,8 +473,8 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
     if ((long long)cmax - (long long)cmin >= (1ll << 31) - 1 || cmin <= -(1 << 30) || cmax >= (1 << 30)) status = CYB_ERR_OVERFLOW;
     int cur = 0, prevF = 0;
     const bool packed = ((long long)cmax - (long long)cmin + 1) * S < (1ll << 45) && P.packed_reduce;
-    auto scan = [&](const int32_t *r) -> Best {
-        return scan_row<SMEMP>(r, no, cmin, S, price_rd, vec_ok, red_b1, red_b2, red_j, packed);
+    auto scan = [&](const int32_t *r, const Team &tm) -> Best {
+        return scan_row<SMEMP>(r, no, cmin, S, price_rd, vec_ok, red_b1, red_b2, red_j, packed, tm);
     };
     const int sap_t = min(P.sap_t, kSapMax);
 
@@ -460,27 +483,37 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
         if (b == 0 && t == 0) { st_ph[1] = global_ns(); if (phases == 1) st_ph[4] = st_ph[1] - st_ph[0]; }
         // ---- phase start: which pairs survive eps-CS at the new eps? --------
         if (phases > 1) {
-            for (int i = b; i < np; i += G) {
-                const int o = __ldcg(P.person_obj + i);
+            // thread 0's certificate terms of a row (its object, slot, cost entry, slot price) are requested ahead of the
+            // scan they belong to: no dependent round trip is left after the scan
+            // (rows b, b + G, ... of this CTA, dealt over its scanning teams)
+            const Team tm = make_team(teams_for<SMEMP>(b < np ? (np - b - 1) / G + 1 : 0));
+            const bool lead = tm.tt == 0;
+            const int istep = G * (kThreads / tm.ts), i0 = b + G * tm.id;
+            int o_nx = i0 < np ? __ldcg(P.person_obj + i0) : -1;
+            int ps_nx = (lead && i0 < np) ? __ldcg(P.person_slot + i0) : -1;
+            for (int i = i0; i < np; i += istep) {
+                const int o = o_nx, ps = ps_nx;
+                if (i + istep < np) { o_nx = __ldcg(P.person_obj + i + istep); if (lead) ps_nx = __ldcg(P.person_slot + i + istep); }
                 int f = 1;
-                if (i + G < np && P.prefetch) prefetch_row_l2(rowptr(i + G), no);
+                if (i + istep < np && P.prefetch) prefetch_row_l2(rowptr(i + istep), no, tm.tt);
                 if (o >= 0) {
                     const int32_t *r = rowptr(i);
-                    const Best s = scan(r);
-                    if (t == 0) {
+                    int c_o = 0; long long sp = 0;
+                    if (lead) { c_o = __ldg(r + o); sp = __ldcg(P.slot_price + ps); }
+                    const Best s = scan(r, tm);
+                    if (lead) {
                         const long long alt = (s.j1 == o) ? s.b2 : s.b1;
-                        const long long base = (long long)(__ldg(r + o) - cmin) * S;
+                        const long long base = (long long)(c_o - cmin) * S;
                         const long long lam = SMEMP ? sarr[o] : __ldcg(P.lambda + o);
-                        const int ps = __ldcg(P.person_slot + i);
                         f = 0;
                         if (alt < kInf / 2) {
                             if (base + lam > alt + eps) f = ps + 2;                       // drop: vacate slot ps
-                            else if (base + __ldcg(P.slot_price + ps) > alt + eps)
+                            else if (base + sp > alt + eps)
                                 P.slot_price[ps] = alt + eps - base;                      // clamp (>= lambda[o])
                         }
                     }
                 }
-                if (t == 0) P.flag[i] = f;
+                if (lead) P.flag[i] = f;
             }
             GRID_BARRIER();
         }
@@ -522,12 +555,15 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
             const bool timed = (b == 0 && t == 0 && F <= G);
             const long long tm0 = timed ? global_ns() : 0;
             const int myn = F > b ? (F - b - 1) / G + 1 : 0;
-            if (myn > 0 && P.prefetch) prefetch_row_l2(rowptr(myq[0]), no);
-            for (int q = 0; q < myn; ++q) {
+            // this CTA's bidders, dealt over its scanning teams (one team = the whole CTA when it has a single bidder)
+            const Team tm = make_team(teams_for<SMEMP>(myn));
+            const int nt = kThreads / tm.ts;
+            if (tm.id < myn && P.prefetch) prefetch_row_l2(rowptr(myq[tm.id]), no, tm.tt);
+            for (int q = tm.id; q < myn; q += nt) {
                 const int i = myq[q];
-                if (q + 1 < myn && P.prefetch) prefetch_row_l2(rowptr(myq[q + 1]), no);
-                const Best s = scan(rowptr(i));
-                if (t == 0) {
+                if (q + nt < myn && P.prefetch) prefetch_row_l2(rowptr(myq[q + nt]), no, tm.tt);
+                const Best s = scan(rowptr(i), tm);
+                if (tm.tt == 0) {
                     const int o = s.j1;
                     const long long lam = SMEMP ? sarr[o] : __ldcg(P.lambda + o);
                     const long long bid = lam + (s.b2 < kInf / 2 ? s.b2 - s.b1 : 0) + eps;
@@ -647,7 +683,7 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
                 const int i = ssrc[k];
                 const int32_t *r = rowptr(i);
                 // over C + g (g = lambda - 2^60: a common shift; negative, hence the unpacked reduction)
-                const Best s = scan_row<SMEMP>(r, no, cmin, S, price_rd, vec_ok, red_b1, red_b2, red_j, false);
+                const Best s = scan_row<SMEMP>(r, no, cmin, S, price_rd, vec_ok, red_b1, red_b2, red_j, false, make_team(1));
                 if (t == 0) sh_ll[0] = s.b1;
                 __syncthreads();
                 const long long b1 = sh_ll[0];
