@@ -114,7 +114,7 @@ struct SapParams {
     int wpc;                         // label words (32 objects) a CTA classifies per round
     int qcap;
     long long max_rounds;
-    int sap_t, sap_k, multi, partial;
+    int sap_t, sap_k, multi, partial, max_teams;
     int warm;                        // 1: a search that follows another one in the phase starts from the surviving forest
     int theta, eps0_div;
     int packed_reduce, prefetch;
@@ -245,8 +245,10 @@ __device__ __forceinline__ Team make_team(int n_teams) {
 }
 // (Without shared-memory prices -- 50k columns -- a scan is bound by the price reads through L2, side-by-side rows only
 // thrash: measured 284 -> 298 ms; there a CTA keeps scanning one row at a time.)
-template <bool SMEMP>
-__device__ __forceinline__ int teams_for(int rows) { return !SMEMP ? 1 : rows >= 8 ? 8 : rows >= 4 ? 4 : rows >= 2 ? 2 : 1; }
+__device__ __forceinline__ int teams_for(int rows, int max_teams) {
+    const int n = rows >= 8 ? 8 : rows >= 4 ? 4 : rows >= 2 ? 2 : 1;
+    return min(n, max_teams);
+}
 __device__ __forceinline__ void team_sync(const Team &tm) {
     if (tm.ts == kThreads) __syncthreads();
     else asm volatile("bar.sync %0, %1;" ::"r"(1 + tm.id), "r"(tm.ts) : "memory");
@@ -486,7 +488,7 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
             // thread 0's certificate terms of a row (its object, slot, cost entry, slot price) are requested ahead of the
             // scan they belong to: no dependent round trip is left after the scan
             // (rows b, b + G, ... of this CTA, dealt over its scanning teams)
-            const Team tm = make_team(teams_for<SMEMP>(b < np ? (np - b - 1) / G + 1 : 0));
+            const Team tm = make_team(teams_for(b < np ? (np - b - 1) / G + 1 : 0, P.max_teams));
             const bool lead = tm.tt == 0;
             const int istep = G * (kThreads / tm.ts), i0 = b + G * tm.id;
             int o_nx = i0 < np ? __ldcg(P.person_obj + i0) : -1;
@@ -556,7 +558,7 @@ __global__ void __launch_bounds__(kThreads, 1) lap_sap_kernel(const SapParams P)
             const long long tm0 = timed ? global_ns() : 0;
             const int myn = F > b ? (F - b - 1) / G + 1 : 0;
             // this CTA's bidders, dealt over its scanning teams (one team = the whole CTA when it has a single bidder)
-            const Team tm = make_team(teams_for<SMEMP>(myn));
+            const Team tm = make_team(teams_for(myn, P.max_teams));
             const int nt = kThreads / tm.ts;
             if (tm.id < myn && P.prefetch) prefetch_row_l2(rowptr(myq[tm.id]), no, tm.tt);
             for (int q = tm.id; q < myn; q += nt) {
@@ -1419,6 +1421,8 @@ extern "C" int cyb_lap_solve_i32(const int32_t *cost_dev, int64_t ld, int64_t n_
     if (const char *e = getenv("CYB_LAP_SMEM_OWNER")) smemo = smemo && atoi(e);
     if (smemo) dyn += owner_bytes;
     if (!smemo) P.warm = 0;
+    P.max_teams = smemp ? 8 : 1;
+    if (const char *e = getenv("CYB_LAP_TEAMS")) P.max_teams = std::max(1, std::min(8, atoi(e)));
 
     const void *fn = smemp ? (smemo ? (const void *)lap_sap_kernel<true, true> : (const void *)lap_sap_kernel<true, false>)
                            : (const void *)lap_sap_kernel<false, false>;
