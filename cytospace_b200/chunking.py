@@ -155,16 +155,18 @@ def solve_chunks(engine, sc_np, st_np, plan: list[Chunk], log_tpm: bool = False,
     if tp is None:
         out = []
         sc_dev = st_dev = None
+        # (explicit dtypes: the chunk paths, distributed or not, never narrow on upload -- same bits on every route)
+        keep = lambda x: None if (torch.is_tensor(x) or np.asarray(x).dtype == np.float32) else torch.float64
         if len(plan) > 1:
             # upload once, slice the chunks' columns on the device
-            sc_dev, st_dev = engine.to_device(sc_np), engine.to_device(st_np)
+            sc_dev, st_dev = engine.to_device(sc_np, keep(sc_np)), engine.to_device(st_np, keep(st_np))
         for ch in plan:
             if sc_dev is None:
                 sc, st = sc_np, st_np
                 if len(ch.sc_index) != sc_np.shape[1] or not _is_arange(ch.sc_index):
-                    sc = _columns(engine, engine.to_device(sc_np), ch.sc_index)
+                    sc = _columns(engine, engine.to_device(sc_np, keep(sc_np)), ch.sc_index)
                 if ch.st_index is not None:
-                    st = _columns(engine, engine.to_device(st_np), ch.st_index)
+                    st = _columns(engine, engine.to_device(st_np, keep(st_np)), ch.st_index)
             else:
                 sc = _columns(engine, sc_dev, ch.sc_index)
                 st = st_dev if ch.st_index is None else _columns(engine, st_dev, ch.st_index)

@@ -11,7 +11,7 @@
 // made to wait for it: asynchronous towards the device like the rest of the ABI, and the source may be reused on return.
 #include "common.h"
 
-#include <emmintrin.h>
+#include <immintrin.h>
 
 #include <atomic>
 #include <condition_variable>
@@ -41,6 +41,49 @@ void copy_nontemporal(char *dst, const char *src, size_t n) {
     if (n & 63) memcpy(dst, src, n & 63);
 }
 
+// dst[i] = (float) src[i], non-temporal stores; returns false when some value does not survive the round trip exactly
+// (dst is 64-byte aligned: piece starts).  AVX2 where the host has it (8 values per step), else SSE2.
+__attribute__((target("avx2"))) bool narrow_nontemporal_avx2(float *dst, const double *src, size_t n) {
+    __m256d ok = _mm256_castsi256_pd(_mm256_set1_epi32(-1));
+    const size_t oct = n / 8;
+    for (size_t i = 0; i < oct; ++i) {
+        const __m256d a = _mm256_loadu_pd(src), b = _mm256_loadu_pd(src + 4);
+        const __m128 fa = _mm256_cvtpd_ps(a), fb = _mm256_cvtpd_ps(b);
+        _mm256_stream_ps(dst, _mm256_set_m128(fb, fa));
+        ok = _mm256_and_pd(ok, _mm256_and_pd(_mm256_cmp_pd(_mm256_cvtps_pd(fa), a, _CMP_EQ_OQ),
+                                             _mm256_cmp_pd(_mm256_cvtps_pd(fb), b, _CMP_EQ_OQ)));
+        src += 8; dst += 8;
+    }
+    _mm_sfence();
+    bool exact = _mm256_movemask_pd(ok) == 15;
+    for (size_t i = 0; i < (n & 7); ++i) {
+        dst[i] = (float)src[i];
+        exact = exact && (double)dst[i] == src[i];
+    }
+    return exact;
+}
+
+bool narrow_nontemporal(float *dst, const double *src, size_t n) {
+    static const bool have_avx2 = __builtin_cpu_supports("avx2");
+    if (have_avx2) return narrow_nontemporal_avx2(dst, src, n);
+    __m128d ok = _mm_castsi128_pd(_mm_set1_epi32(-1));
+    const size_t quads = n / 4;
+    for (size_t i = 0; i < quads; ++i) {
+        const __m128d a = _mm_loadu_pd(src), b = _mm_loadu_pd(src + 2);
+        const __m128 fa = _mm_cvtpd_ps(a), fb = _mm_cvtpd_ps(b);                 // MXCSR rounding: nearest even, like numpy's astype
+        _mm_stream_ps(dst, _mm_movelh_ps(fa, fb));
+        ok = _mm_and_pd(ok, _mm_and_pd(_mm_cmpeq_pd(_mm_cvtps_pd(fa), a), _mm_cmpeq_pd(_mm_cvtps_pd(fb), b)));
+        src += 4; dst += 4;
+    }
+    _mm_sfence();
+    bool exact = _mm_movemask_pd(ok) == 3;
+    for (size_t i = 0; i < (n & 3); ++i) {
+        dst[i] = (float)src[i];
+        exact = exact && (double)dst[i] == src[i];
+    }
+    return exact;
+}
+
 struct Stager {
     int device = -1, n_threads = 0, n_pieces = 0;
     size_t piece = 0;
@@ -55,8 +98,9 @@ struct Stager {
     // the job in flight
     const char *src = nullptr;
     char *dst = nullptr;
-    size_t bytes = 0, n_jobs = 0, next = 0, finished = 0;
-    int error = 0;
+    size_t bytes = 0, n_jobs = 0, next = 0, finished = 0;      // bytes: of the DEVICE buffer (= pinned bytes)
+    int narrow = 0;                                            // 1: src holds float64, the pieces and dst hold float32
+    int error = 0, inexact = 0;
     bool quit = false;
 
     void run() {
@@ -74,8 +118,10 @@ struct Stager {
             const size_t lo = p * piece, len = std::min(piece, bytes - lo);
             char *buf = ring + (size_t)slot * piece;
             bool ok = !used[slot] || cudaEventSynchronize(drained[slot]) == cudaSuccess;
+            bool exact = true;
             if (ok) {
-                copy_nontemporal(buf, src + lo, len);
+                if (narrow) exact = narrow_nontemporal(reinterpret_cast<float *>(buf), reinterpret_cast<const double *>(src + 2 * lo), len / 4);
+                else copy_nontemporal(buf, src + lo, len);
                 ok = cudaMemcpyAsync(dst + lo, buf, len, cudaMemcpyHostToDevice, copy_stream) == cudaSuccess &&
                      cudaEventRecord(drained[slot], copy_stream) == cudaSuccess;
             }
@@ -83,6 +129,7 @@ struct Stager {
             used[slot] = 1;
             done_flag[p] = 1;
             if (!ok) error = 1;
+            if (!exact) inexact = 1;
             ++finished;
             cv_slot.notify_all();
             if (finished == n_jobs) cv_done.notify_all();
@@ -102,10 +149,8 @@ int env_int(const char *name, int dflt, int lo, int hi) {
 
 }  // namespace
 
-extern "C" int cyb_stage_upload(const void *src_host, void *dst_dev, size_t bytes, void *stream_v) {
-    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
-    if (bytes == 0) return CYB_OK;
-    if (!src_host || !dst_dev) return cyb::set_error(CYB_ERR_INVALID, "cyb_stage_upload: null pointer argument");
+namespace {
+int stage_upload(const void *src_host, void *dst_dev, size_t bytes, int narrow, int32_t *inexact_host, cudaStream_t stream) {
     std::lock_guard<std::mutex> guard(g_stager_mutex);
     int dev = 0;
     CYB_CUDA_CHECK(cudaGetDevice(&dev));
@@ -132,7 +177,7 @@ extern "C" int cyb_stage_upload(const void *src_host, void *dst_dev, size_t byte
         Stager *s = new Stager();
         s->device = dev;
         const int hw = (int)std::thread::hardware_concurrency();
-        s->n_threads = env_int("CYB_STAGE_THREADS", std::max(1, std::min(8, hw > 0 ? hw : 8)), 1, 64);
+        s->n_threads = env_int("CYB_STAGE_THREADS", std::max(1, std::min(16, hw > 0 ? hw : 8)), 1, 64);
         s->piece = (size_t)env_int("CYB_STAGE_PIECE_MB", 8, 1, 256) << 20;
         s->n_pieces = env_int("CYB_STAGE_PIECES", 3 * s->n_threads, 2, 512);
         const size_t ring_bytes = s->piece * (size_t)s->n_pieces;
@@ -159,12 +204,14 @@ extern "C" int cyb_stage_upload(const void *src_host, void *dst_dev, size_t byte
         s->src = static_cast<const char *>(src_host);
         s->dst = static_cast<char *>(dst_dev);
         s->bytes = bytes;
+        s->narrow = narrow;
         s->n_jobs = (bytes + s->piece - 1) / s->piece;
-        s->next = 0; s->finished = 0; s->error = 0;
+        s->next = 0; s->finished = 0; s->error = 0; s->inexact = 0;
         s->done_flag.assign(s->n_jobs, 0);
         s->cv_work.notify_all();
         s->cv_done.wait(lk, [&] { return s->finished == s->n_jobs; });
         err = s->error;
+        if (inexact_host) *inexact_host = s->inexact;
     }
     if (err) {
         cudaGetLastError();
@@ -173,4 +220,19 @@ extern "C" int cyb_stage_upload(const void *src_host, void *dst_dev, size_t byte
     CYB_CUDA_CHECK(cudaEventRecord(s->fence, s->copy_stream));
     CYB_CUDA_CHECK(cudaStreamWaitEvent(stream, s->fence, 0));
     return CYB_OK;
+}
+}  // namespace
+
+extern "C" int cyb_stage_upload(const void *src_host, void *dst_dev, size_t bytes, void *stream_v) {
+    if (bytes == 0) return CYB_OK;
+    if (!src_host || !dst_dev) return cyb::set_error(CYB_ERR_INVALID, "cyb_stage_upload: null pointer argument");
+    return stage_upload(src_host, dst_dev, bytes, 0, nullptr, static_cast<cudaStream_t>(stream_v));
+}
+
+extern "C" int cyb_stage_upload_f64_as_f32(const double *src_host, float *dst_dev, size_t n, int32_t *inexact_host,
+                                           void *stream_v) {
+    if (inexact_host) *inexact_host = 0;
+    if (n == 0) return CYB_OK;
+    if (!src_host || !dst_dev) return cyb::set_error(CYB_ERR_INVALID, "cyb_stage_upload_f64_as_f32: null pointer argument");
+    return stage_upload(src_host, dst_dev, n * sizeof(float), 1, inexact_host, static_cast<cudaStream_t>(stream_v));
 }

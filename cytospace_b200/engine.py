@@ -99,6 +99,7 @@ class AssignmentEngine:
         self._ws = {}
         #: kernels of this library launched so far (every C-ABI call launches a fixed number: see KERNELS_PER_CALL)
         self.launches = 0
+        self.h2d_bytes = 0                 # bytes to_device() has sent over PCIe (the device tensors' sizes)
         self.profile = False          # True: bracket the cost-build and LAP launches with CUDA events
         self._events = {}
         sm, maj, mnr, mem = (self.ffi.new("int *"), self.ffi.new("int *"), self.ffi.new("int *"),
@@ -134,6 +135,11 @@ class AssignmentEngine:
 
     #: host arrays at least this large go through the pinned staging ring
     STAGE_MIN_BYTES = 32 << 20
+    #: large float64 host arrays cross PCIe as float32 (narrowed by the staging threads; half the bytes).  Exact for count
+    #: matrices; on normalised data the correlation moves by < 1e-8 (include/cytospace_b200.h).  ``CYB_STAGE_F32=0`` or
+    #: ``engine.stage_float32 = False`` keeps float64 on the wire.
+    stage_float32 = os.environ.get("CYB_STAGE_F32", "1") != "0"
+    last_stage_exact = True
 
     @_on_engine_device
     def to_device(self, x, dtype=None) -> torch.Tensor:
@@ -142,7 +148,8 @@ class AssignmentEngine:
         Expression matrices reach ``solve_linear_assignment_problem`` as pageable numpy arrays
         (cytospace.py:398-409).  Anything that is not float32 / float64 (``read_csv`` count matrices are
         int64) is cast to float64 on the host as the reference's ``normalize_data`` does
-        (common.py:143: ``np.nan_to_num(data).astype(float)``).  Large arrays are uploaded through the native library's ring
+        (common.py:143: ``np.nan_to_num(data).astype(float)``).  Large float64 arrays land as float32 unless
+        ``stage_float32`` is off or ``dtype`` is given.  Large arrays are uploaded through the native library's ring
         of pinned pieces (``cyb_stage_upload``; a plain ``cudaMemcpy`` from pageable memory runs at a fraction of the
         PCIe rate)."""
         if torch.is_tensor(x):
@@ -160,12 +167,24 @@ class AssignmentEngine:
         if not x.flags.c_contiguous:
             x = np.ascontiguousarray(x)
         if x.nbytes < self.STAGE_MIN_BYTES:
+            self.h2d_bytes += x.nbytes
             return torch.from_numpy(x).to(self.device)
-        return self._staged_upload(x)
+        out = self._staged_upload(x, narrow=(dtype is None and x.dtype == np.float64 and self.stage_float32))
+        self.h2d_bytes += out.numel() * out.element_size()
+        return out
 
-    def _staged_upload(self, x: np.ndarray) -> torch.Tensor:
+    def _staged_upload(self, x: np.ndarray, narrow: bool = False) -> torch.Tensor:
         """``cyb_stage_upload``: worker threads of the native library copy pageable -> pinned pieces with
-        non-temporal stores and enqueue one DMA per piece; returns when the last piece is enqueued."""
+        non-temporal stores and enqueue one DMA per piece; returns when the last piece is enqueued.
+        ``narrow``: a float64 array arrives as float32 (``cyb_stage_upload_f64_as_f32``; ``last_stage_exact`` tells
+        whether every value survived exactly)."""
+        if narrow:
+            out = torch.empty(x.shape, dtype=torch.float32, device=self.device)
+            flag = _native.ffi().new("int32_t *")
+            _native.check(self.lib.cyb_stage_upload_f64_as_f32(_native.ffi().cast("const double *", x.ctypes.data),
+                                                               _native.ptr("float *", out), x.size, flag, self._stream()))
+            self.last_stage_exact = not bool(flag[0])
+            return out
         out = torch.empty(x.shape, dtype=torch.from_numpy(x[:0]).dtype, device=self.device)
         _native.check(self.lib.cyb_stage_upload(_native.ffi().cast("const void *", x.ctypes.data),
                                                 _native.ptr("void *", out), x.nbytes, self._stream()))

@@ -41,7 +41,7 @@ def _solve(cost_matrix):
     if not np.isfinite(amax):
         raise ValueError("cost matrix contains NaN or inf")
     scale = float(COST_SCALE) if amax <= 1000.0 else float(2 ** 29) / amax
-    dev = eng.quantise(eng.to_device(c64), scale)
+    dev = eng.quantise(eng.to_device(c64, torch.float64), scale)       # (explicit dtype: a cost matrix is never narrowed)
     res = eng.lap_solve(dev, n_persons=cost.shape[0], n_objects=cost.shape[0])    # persons = rows, objects = columns
     rowsol = res.person_obj.cpu().numpy()
     colsol = res.slot_owner.cpu().numpy()

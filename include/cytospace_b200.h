@@ -47,7 +47,7 @@
 extern "C" {
 #endif
 
-#define CYB_ABI_VERSION 8
+#define CYB_ABI_VERSION 9
 
 /* status codes */
 #define CYB_OK                 0
@@ -307,9 +307,17 @@ int cyb_narrow_f64_to_f32(const double *x_dev, int64_t n, float *out_dev, int32_
  * solver (cytospace/cytospace.py:398-443; `.to_numpy()` of the input DataFrames) -- through a process-wide ring of
  * pinned pieces filled by worker threads with non-temporal stores, one DMA per piece on an internal copy stream.
  * Returns when every piece is enqueued (src_host may be reused); `stream` waits for the last DMA.  Ordered after the
- * work already queued on `stream`.  Environment: CYB_STAGE_THREADS (default min(8, cores)), CYB_STAGE_PIECE_MB (8),
+ * work already queued on `stream`.  Environment: CYB_STAGE_THREADS (default min(16, cores)), CYB_STAGE_PIECE_MB (8),
  * CYB_STAGE_PIECES (3 x threads). */
 int cyb_stage_upload(const void *src_host, void *dst_dev, size_t bytes, void *stream);
+
+/* The same upload for a float64 host array that lands on the device as float32: the worker threads narrow while they
+ * copy (round to nearest even, like numpy's astype), so half the bytes cross PCIe.  *inexact_host (may be NULL) is set to
+ * 1 when some value does not survive the round trip exactly (NaN counts as inexact), else 0.  The kernels accept
+ * float32 input and widen on load: count matrices (integers below 2^24) are exact; on log2(TPM+1) data the rounding
+ * (2^-24 relative per value) moves the correlation by < 1e-8 -- 0.2 % of the integer cost entries change by one unit,
+ * next to the 2e-6 tolerance of the fp16 hi/lo GEMM itself (tests/test_gpu_path.py). */
+int cyb_stage_upload_f64_as_f32(const double *src_host, float *dst_dev, size_t n, int32_t *inexact_host, void *stream);
 
 #ifdef __cplusplus
 }

@@ -16,12 +16,14 @@ if os.environ.get("PLAIN"):
     xp = torch.from_numpy(x).pin_memory(); t3 = time.perf_counter(); d = xp.cuda(non_blocking=True); torch.cuda.synchronize()
     print("cores %%d  plain pageable .cuda(): %%.1f / %%.1f ms   pinned: %%.1f ms" %% (os.cpu_count(), (t1 - t0) * 1e3, (t2 - t1) * 1e3, (time.perf_counter() - t3) * 1e3))
 else:
-    eng.to_device(x); torch.cuda.synchronize()
-    ts = []
-    for _ in range(4):
-        t0 = time.perf_counter(); d = eng.to_device(x); torch.cuda.synchronize(); ts.append((time.perf_counter() - t0) * 1e3)
-    assert torch.equal(d[::997].cpu(), torch.from_numpy(x[::997]))
-    print("threads=%%s piece=%%sMB pieces=%%s: %%.1f ms = %%.1f GB/s" %% (os.environ.get("CYB_STAGE_THREADS"), os.environ.get("CYB_STAGE_PIECE_MB"), os.environ.get("CYB_STAGE_PIECES"), min(ts), x.nbytes / min(ts) / 1e6))
+    for narrow in (False, True):
+        eng.stage_float32 = narrow
+        eng.to_device(x); torch.cuda.synchronize()
+        ts = []
+        for _ in range(4):
+            t0 = time.perf_counter(); d = eng.to_device(x); torch.cuda.synchronize(); ts.append((time.perf_counter() - t0) * 1e3)
+        assert torch.equal(d[::997].cpu(), torch.from_numpy(x[::997].astype(np.float32 if narrow else np.float64)))
+        print("threads=%%s piece=%%sMB pieces=%%s %%s: %%.1f ms = %%.1f GB/s of host float64" %% (os.environ.get("CYB_STAGE_THREADS"), os.environ.get("CYB_STAGE_PIECE_MB"), os.environ.get("CYB_STAGE_PIECES"), "float32 on the wire" if narrow else "float64 on the wire", min(ts), x.nbytes / min(ts) / 1e6))
 """ % ROOT
 
 
@@ -34,6 +36,5 @@ def run(**env):
 if __name__ == "__main__":
     run(PLAIN=1)
     for thr in (4, 8, 12, 16):
-        for piece in (2, 8, 32):
+        for piece in (4, 8):
             run(CYB_STAGE_THREADS=thr, CYB_STAGE_PIECE_MB=piece, CYB_STAGE_PIECES=3 * thr)
-    run(CYB_STAGE_THREADS=16, CYB_STAGE_PIECE_MB=8, CYB_STAGE_PIECES=96)

@@ -166,15 +166,47 @@ def test_more_spots_than_cells_and_integer_counts(engine):
 
 
 def test_staged_upload_equals_plain_copy(engine):
-    """Host arrays above STAGE_MIN_BYTES travel through the pinned ring: byte-identical on the device."""
+    """Host arrays above STAGE_MIN_BYTES travel through the pinned ring.  With an explicit dtype (or
+    ``stage_float32`` off) the device copy is byte-identical; by default a float64 array lands as float32,
+    narrowed by the staging threads exactly like ``astype(np.float32)``, and the engine records whether every
+    value survived."""
     rng = np.random.default_rng(9)
-    x = rng.standard_normal((3000, 5001))                      # 120 MB, not a multiple of the slab size
+    x = rng.standard_normal((3000, 5001))                      # 120 MB, not a multiple of the piece size
     assert x.nbytes > engine.STAGE_MIN_BYTES
-    d = engine.to_device(x)
+    d = engine.to_device(x, torch.float64)
     torch.cuda.synchronize()
     assert torch.equal(d.cpu(), torch.from_numpy(x))
-    xi = rng.integers(0, 50, (2000, 3000))                     # int64 -> float64 on the host
-    assert torch.equal(engine.to_device(xi).cpu(), torch.from_numpy(xi.astype(np.float64)))
+    d32 = engine.to_device(x)
+    assert d32.dtype == torch.float32 and torch.equal(d32.cpu(), torch.from_numpy(x.astype(np.float32)))
+    assert engine.last_stage_exact is False
+    engine.stage_float32 = False
+    try:
+        assert torch.equal(engine.to_device(x).cpu(), torch.from_numpy(x))
+    finally:
+        del engine.stage_float32                               # back to the class default
+    xi = rng.integers(0, 50, (3000, 3000))                     # int64 counts -> float64 on the host -> exact float32 on the wire
+    di = engine.to_device(xi)
+    assert di.dtype == torch.float32 and torch.equal(di.cpu().double(), torch.from_numpy(xi.astype(np.float64)))
+    assert engine.last_stage_exact is True
+    xn = x.copy(); xn[5, 7] = np.nan; xn[9, 1] = np.inf       # NaN / inf pass through (NaN counts as inexact)
+    dn = engine.to_device(xn).cpu().numpy()
+    assert np.isnan(dn[5, 7]) and np.isinf(dn[9, 1])
+
+
+def test_float32_staging_moves_the_cost_by_at_most_one_unit(engine):
+    """The plugin call uploads large float64 matrices as float32 (half the PCIe bytes).  Tolerance, stated here: on
+    log2(TPM+1) data the integer cost changes by at most 1 unit (1e-6 on r) in well under 1 % of the entries, and
+    stays within the cost-build tolerance of the float64 oracle."""
+    sc, st, cn = syn.structured_counts(900, 900, 5000, 1, seed=77)          # 36 MB each: above STAGE_MIN_BYTES
+    sc_n, st_n = co.normalize_data(sc), co.normalize_data(st)
+    assert sc_n.nbytes > engine.STAGE_MIN_BYTES and sc_n.dtype == np.float64
+    c32 = engine.cost_build(engine.to_device(sc_n), engine.to_device(st_n))[:, :900].cpu().numpy()
+    assert engine.last_stage_exact is False
+    c64 = engine.cost_build(engine.to_device(sc_n, torch.float64), engine.to_device(st_n, torch.float64))[:, :900].cpu().numpy()
+    diff = np.abs(c32.astype(np.int64) - c64)
+    assert diff.max() <= 1 and (diff != 0).mean() < 0.01
+    ref = co.cost_matrix_i32(sc_n, st_n)                                    # spots x cells, float64 oracle
+    assert np.abs(c32.T.astype(np.int64) - ref).max() <= 3
 
 
 @pytest.mark.gpu
