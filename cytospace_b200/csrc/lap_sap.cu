@@ -1,7 +1,7 @@
 // Exact dense linear assignment (transportation form) on sm_100a -- the solver behind
-// cyb_lap_solve_i32: eps-scaling auction rounds for the bulk of every phase, and a grid-wide
-// multi-source SHORTEST-AUGMENTING-PATH finish for the last free persons of the phase, all in ONE
-// persistent cooperative kernel (one CTA per SM).
+// cyb_lap_solve_i32: eps-scaling auction rounds, phases with eps > 1 left INCOMPLETE (their last free persons
+// are handed to the next phase), and a grid-wide multi-source SHORTEST-AUGMENTING-PATH finish for the last free
+// persons of the eps = 1 phase, all in ONE persistent cooperative kernel (one CTA per SM).
 //
 // Replaces the third-party `lapjv.lapjv(cost)` call CytoSPACE makes at
 // cytospace/linear_assignment_solvers/linear_assignment_solvers.py:38 (from
@@ -27,7 +27,13 @@
 // parallel (bandwidth-shaped work), per search.  oracle/sap_model.c is the CPU model of exactly this
 // algorithm (the experiment that sized it, and the reference the tests compare assignments with).
 //
-// SAP finish (runs when <= sap_t persons are free), residual graph at the current eps:
+// Incomplete phases.  The next phase start drops every pair that violates the tighter eps and rebuilds the free list
+// anyway, so placing the hardest persons of a phase with eps > 1 is wasted work: such a phase stops when <= `partial`
+// persons are free (eps-CS holds for every assigned pair at all times; only the last phase must place everybody).
+// 46 -> 8 searches and 1 498 -> 721 search rounds at 10k x 10k; with it a gentler schedule (theta = 8) pays.
+//
+// SAP finish (runs when <= sap_t persons are free; with the default partial >= sap_t only in the eps = 1 phase),
+// residual graph at the current eps:
 //   assigned person i (object o_i) -> object k != o_i : len = C[i,k]+lambda[k]+eps - (C[i,o_i]+lambda[o_i]) >= 0
 //   free person i                  -> object k        : len = C[i,k]+lambda[k] - min_k'(C[i,k']+lambda[k'])   >= 0
 //   object o -> every person it holds                 : len = 0
@@ -55,7 +61,9 @@
 //
 // Tuning knobs (environment, read at launch): CYB_LAP_SAP_T (free persons at which the search
 // takes over), CYB_LAP_SAP_K (rows per search round), CYB_LAP_SAP_MULTI (paths per search, <= 32),
-// CYB_LAP_WARM (0: every search starts from scratch), CYB_LAP_THETA, CYB_LAP_EPS0, CYB_LAP_SMEM_PRICES=0 / CYB_LAP_SMEM_OWNER=0 (force the L2 paths).
+// CYB_LAP_WARM (0: every search starts from scratch), CYB_LAP_PARTIAL (0: every phase is completed), CYB_LAP_THETA,
+// CYB_LAP_EPS0, CYB_LAP_TEAMS (rows a CTA scans side by side, <= 8), CYB_LAP_SMEM_PRICES=0 / CYB_LAP_SMEM_OWNER=0 (force
+// the L2 paths).
 
 #include <algorithm>
 #include <climits>
