@@ -16,8 +16,10 @@ Contents
   ``calculate_cost`` ``linear_assignment_solvers.py:42-69``,
   ``normalize_data`` ``common.py:142-147``); pinned against the reference's
   own functions imported with stubs (``tests/golden/make_golden.py``).
-* ``auction_model`` -- sequential model of the device auction (exactness and
-  round-count checks without a GPU).
+* ``sap_model`` -- sequential model of the device solver (``sap_model.c``: auction rounds, incomplete
+  phases, warm-started shortest-augmenting-path searches); the GPU tests require identical assignments,
+  prices and counters.  ``auction_model`` is the round-1 model (pure auction), kept as the comparator of
+  the experiment behind the redesign.
 """
 from __future__ import annotations
 
