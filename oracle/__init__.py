@@ -165,7 +165,7 @@ def auction_model(m, cap=None, theta=4, eps0_div=4, tail_t=0, round_cap=0, varia
     return person_obj, slot_owner, int(total[0]), lam, stats, rlog[:min(round_cap, int(stats[1]))]
 
 
-def sap_model(m, cap=None, theta=4, eps0_div=4, sap_t=64, K=148, multi=0, warm=0, partial=0):
+def sap_model(m, cap=None, theta=4, eps0_div=4, sap_t=64, K=148, multi=0, warm=0, partial=0, chain=0):
     """Sequential model of the hybrid device solver (auction rounds + shortest-augmenting-path finish,
     ``sap_model.c``).  Same orientation as ``auction_model``.  Returns (person_obj, slot_owner, total,
     lambda, stats, phase_log) -- stats / phase_log columns are documented in sap_model.c."""
@@ -179,6 +179,7 @@ def sap_model(m, cap=None, theta=4, eps0_div=4, sap_t=64, K=148, multi=0, warm=0
     lam = np.zeros(O, np.int64); total = np.zeros(1, np.int64); stats = np.zeros(8, np.int64)
     ctypes.c_int.in_dll(lib, "sap_warm").value = int(warm)
     ctypes.c_int.in_dll(lib, "sap_partial").value = int(partial)
+    ctypes.c_int.in_dll(lib, "sap_chain").value = int(chain)
     rc = lib.sap_model_i32(P, O, _ptr(m, ctypes.c_int32), m.shape[1], _ptr(capa, ctypes.c_int32),
                            _ptr(person_obj, ctypes.c_int32), _ptr(slot_owner, ctypes.c_int32),
                            _ptr(lam, ctypes.c_int64), _ptr(total, ctypes.c_int64),

@@ -38,6 +38,15 @@ int64_t sap_phase_log[64][8];
 /* 1: a search that follows another one in the same phase starts from the surviving part of its shortest-path forest
  * (labels shifted by D, trees of the persons that got assigned dropped) instead of from scratch */
 int sap_warm = 0;
+/* > 0: CHAINED relaxations.  When the rows of a frontier object lower the label of an object k to nd <= T (inside this
+ * round's window, below D) the best such discovery (smallest (nd, k); k must have a holder) is relaxed in the SAME round
+ * with the label nd, up to sap_chain hops deep -- a round then advances the search by up to 1 + sap_chain arcs instead of
+ * one (the searches are depth-bound: ~90 rounds each at 10k).  Everything is judged against the round-start snapshot, so
+ * the result does not depend on the order of the relaxations; an object whose chained label is its final label of the
+ * round is not dirty afterwards.  Objects with more than SAP_CHAIN_CAP slots do not start chains (the device relaxes at
+ * most that many rows per pass); the repair round of a warm search does not chain. */
+int sap_chain = 0;
+#define SAP_CHAIN_CAP 32
 int sap_partial = 0;      /* > 0: a phase with eps > 1 ends as soon as <= sap_partial persons are free (they stay free into the next phase) */
 
 typedef struct { int64_t d; int32_t o; } lab_t;
@@ -79,6 +88,9 @@ int sap_model_i32(int P, int O, const int32_t *m, int64_t ld, const int32_t *cap
     /* search state */
     int64_t *d = (int64_t *)malloc(sizeof(int64_t) * (size_t)O);
     int64_t *snap = (int64_t *)malloc(sizeof(int64_t) * (size_t)O);
+    int64_t *chainlab = (int64_t *)malloc(sizeof(int64_t) * (size_t)O);     /* smallest label an object was chain-relaxed with this round */
+    int32_t *cq_o = (int32_t *)malloc(sizeof(int32_t) * (size_t)O * 4 + 64); int64_t *cq_d = (int64_t *)malloc(sizeof(int64_t) * (size_t)O * 4 + 64);
+    int32_t *cq_h = (int32_t *)malloc(sizeof(int32_t) * (size_t)O * 4 + 64);
     int32_t *pred = (int32_t *)malloc(sizeof(int32_t) * (size_t)O);
     int32_t *nfreeslot = (int32_t *)malloc(sizeof(int32_t) * (size_t)O);
     lab_t *cand = (lab_t *)malloc(sizeof(lab_t) * (size_t)O);
@@ -248,6 +260,7 @@ int sap_model_i32(int P, int O, const int32_t *m, int64_t ld, const int32_t *cap
                         }
                         T = Tq;
                     }
+                    const int chain_now = repair ? 0 : (sap_chain > 3 ? 3 : sap_chain);
                     if (repair) repair = 0;
                     else if (wC < K && wC < wE) step *= 2;                 /* the window was too small (not: too little left) */
                     else if (wC > 4 * K && step > 1) step /= 2;
@@ -260,9 +273,15 @@ int sap_model_i32(int P, int O, const int32_t *m, int64_t ld, const int32_t *cap
                     for (int q = 0; q < nfront; ++q) indirty[front[q]] = 0;
                     Tg = Tnext;
                     int64_t rows = 0;
-                    for (int q = 0; q < nfront; ++q) {
-                        const int o = front[q];
-                        const int64_t dl = snap[o];
+                    /* work queue: the frontier (hop 0), then the chained discoveries; the outcome is order-independent */
+                    int qn = 0;
+                    for (int q = 0; q < nfront; ++q) { cq_o[qn] = front[q]; cq_d[qn] = snap[front[q]]; cq_h[qn] = 0; ++qn; }
+                    if (chain_now) for (int o = 0; o < O; ++o) chainlab[o] = SAP_INF;
+                    for (int q = 0; q < qn; ++q) {
+                        const int o = cq_o[q];
+                        const int64_t dl = cq_d[q];
+                        const int may_chain = cq_h[q] < chain_now && soff[o + 1] - soff[o] <= SAP_CHAIN_CAP;
+                        int kbest = -1; int64_t ndbest = SAP_INF;
                         for (int t = soff[o]; t < soff[o + 1]; ++t) {
                             const int i = slot_owner[t];
                             if (i < 0) continue;
@@ -273,12 +292,28 @@ int sap_model_i32(int P, int O, const int32_t *m, int64_t ld, const int32_t *cap
                                 if (k == o || lambda[k] >= SAP_INF / 2) continue;
                                 const int64_t nd = dl + (int64_t)(r[k] - cmin) * S + lambda[k] + eps - base;
                                 if (nd < dl) { rc = -5; goto done; }          /* eps-CS violated: model bug */
-                                if (nd < snap[k] && (nd < d[k] || (nd == d[k] && t < pred[k]))) {
+                                if (nd >= snap[k]) continue;                    /* counts iff strictly below the round-start label */
+                                if (nd < d[k] || (nd == d[k] && t < pred[k])) {
                                     d[k] = nd; pred[k] = t;
                                     if (!indirty[k]) { indirty[k] = 1; dirty[ndirty++] = k; }
                                 }
+                                if (may_chain && nd <= T && nd < D && (soff[k + 1] - soff[k]) - nfreeslot[k] > 0 &&
+                                    (nd < ndbest || (nd == ndbest && k < kbest))) { ndbest = nd; kbest = k; }
                             }
                         }
+                        if (kbest >= 0) {
+                            cq_o[qn] = kbest; cq_d[qn] = ndbest; cq_h[qn] = cq_h[q] + 1; ++qn;
+                            if (ndbest < chainlab[kbest]) chainlab[kbest] = ndbest;
+                        }
+                    }
+                    if (chain_now) {
+                        /* chain-relaxed with what turned out to be its label at the end of the round: nothing left to do for it */
+                        int nk = 0;
+                        for (int q2 = 0; q2 < ndirty; ++q2) {
+                            const int o2 = dirty[q2];
+                            if (chainlab[o2] == d[o2]) indirty[o2] = 0; else dirty[nk++] = o2;
+                        }
+                        ndirty = nk;
                     }
                     st[5] += rows;
                 }

@@ -97,7 +97,7 @@ def test_sap_finish_model_equals_expanded_jv(n_obj, seed, high, knobs, theta):
     want = oracle.lapjv_i32(compact, row_map)[2][0]
     # partial > 0: phases with eps > 1 stop early and hand their free persons to the next phase
     po, so, tot, lam, stats, _ = oracle.sap_model(np.ascontiguousarray(compact.T), cap, theta=theta, sap_t=sap_t, K=K, multi=multi,
-                                                  warm=seed & 1, partial=(0, 2, 64)[(seed >> 1) % 3])
+                                                  warm=seed & 1, partial=(0, 2, 64)[(seed >> 1) % 3], chain=(seed >> 3) % 3)
     assert tot == want
     assert np.array_equal(np.bincount(po, minlength=n_obj), cap)
     soff = np.concatenate([[0], np.cumsum(cap)])
@@ -112,7 +112,8 @@ def test_sap_finish_model_on_golden_instances(lap_golden, name):
     cost = lap_golden[f"{name}_cost"]
     opt = int(lap_golden[f"{name}_opt"])
     for kw in (dict(), dict(sap_t=4, K=8, multi=1, theta=4), dict(sap_t=0),       # sap_t = 0: pure auction
-               dict(theta=4, sap_t=64, K=296, multi=16, partial=64, warm=1)):
+               dict(theta=4, sap_t=64, K=296, multi=16, partial=64, warm=1),
+               dict(theta=8, sap_t=64, K=296, multi=16, partial=64, warm=1, chain=2), dict(sap_t=4, K=8, multi=1, theta=4, chain=1)):
         po, so, tot, lam, stats, _ = oracle.sap_model(cost, **kw)
         assert tot == opt and sorted(po.tolist()) == list(range(cost.shape[0]))
         assert np.array_equal(so[po], np.arange(cost.shape[0]))
