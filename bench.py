@@ -429,6 +429,19 @@ def run_b200(args, wl):
         step_e2e()
     torch.cuda.synchronize(dev)
     h2d_wire = eng.h2d_bytes - b0
+    # the same call with float64 on the wire (CYB_STAGE_F32=0 / engine.stage_float32 = False): reported next to the default
+    eng.stage_float32 = False
+    try:
+        with contextlib.redirect_stdout(sys.stderr):
+            e2e64_ms, _, _, _, _ = timed(step_e2e, max(1, min(args.steps, 3)), 1, track=False)
+        b0 = eng.h2d_bytes
+        with contextlib.redirect_stdout(sys.stderr):
+            step_e2e()
+        torch.cuda.synchronize(dev)
+        h2d_wire64 = eng.h2d_bytes - b0
+    finally:
+        del eng.stage_float32
+    e2e64_steps = max(1, min(args.steps, 3))
     # certificate = one coalesced read of the whole cost matrix: the row-scan bandwidth probe, and a
     # full-size optimality proof of the last solve
     for _ in range(3):
@@ -494,7 +507,9 @@ def run_b200(args, wl):
                                     "executed_frac": 2.0 * n_spots * n_cells * kop / (cost_ms / 1e3) / 1e12 / tf_burst,
                                     "note": "ms covers standardise pre-pass + GEMM; f16x3 executes 3x the algorithmic flop"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_wire, "d2h_bytes_per_step": d2h,
-                    "host_bytes_per_step": h2d, "ms_per_step": e2e_ms / args.steps},
+                    "host_bytes_per_step": h2d, "ms_per_step": e2e_ms / args.steps,
+                    "float64_on_the_wire": {"value": total_cells / (e2e64_ms / e2e64_steps / 1e3), "unit": UNIT,
+                                            "ms_per_step": e2e64_ms / e2e64_steps, "h2d_bytes_per_step": h2d_wire64}},
             "gpu_launches": launches,
             "clocks": clocks,
             "certificate": cert,
